@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_kat.npz"))
+
+
+@pytest.fixture(scope="session")
+def weight_digests():
+    out = {}
+    with open(os.path.join(ROOT, "tests", "golden", "weights_sha256.txt")) as f:
+        for line in f:
+            k, v = line.split()
+            out[k] = v
+    return out
