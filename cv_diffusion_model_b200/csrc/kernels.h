@@ -1,0 +1,123 @@
+// Launch wrappers of every kernel of the LCM-UNet hot path (host-callable, enqueue only).
+// `bf16act` selects the activation storage type: 0 = fp32 (verification mode), 1 = bf16.
+#pragma once
+#include "common.cuh"
+
+namespace lcm {
+
+// ---- a2: SinusoidalPosEmb + time_mlp (efficient_unet.py:60-76, 412-417) ------------------------
+// t_dev (int64[N]) or, when null, the scalar t for every sample.  Writes silu(t_emb) [N][ted]
+// (every consumer applies SiLU first, efficient_unet.py:189-190) and optionally t_emb itself.
+void launch_time_embed(const long long* t_dev, long long t_scalar, int N, int base, int ted, const float* w1,
+                       const float* b1, const float* w3, const float* b3, float* temb, float* silu_temb,
+                       cudaStream_t st);
+
+// ---- a4.3: all blocks' FiLM linears in one launch: out[n][r] = b[r] + W[r][:] . silu_temb[n][:] ---
+void launch_film(const float* silu_temb, const float* W, const float* b, float* out, int N, int rows, int ted,
+                 cudaStream_t st);
+
+// ---- a4.1: GroupNorm finalise: channel statistics -> per-(image, channel) affine (a, b) ------------
+// channel c < C0 comes from stats0, the rest from stats1 (concat inputs).  film (optional) points at
+// this block's [scale | shift] rows: a' = a(1+scale), b' = b(1+scale)+shift.
+void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
+                    const float* gamma, const float* beta, const float* film, int film_ld, float2* coef, int N,
+                    cudaStream_t st);
+
+// ---- a4.2: 1x1 convs as GEMM, CUDA-core version (fp32 mode and cross-check) -----------------------
+// W is row-major [Nc][Ktot] in the activation storage type.
+void launch_gemm_simt(const GemmParams& p, int bf16act, cudaStream_t st);
+
+// ---- a4.4 + SE pool: depthwise 3x3 with affine+ReLU6 prologue, pooled sums epilogue ---------------
+// in/out NHWC [N][H][W][C]; coef [N][C]; w [9][C] fp32; pool [N][C] fp32 sums (atomically accumulated).
+void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, float* pool, int N, int H, int W,
+                   int C, int bf16act, int fast, cudaStream_t st);
+
+// ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0) -------------------------------
+void launch_se_gate(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st);
+
+// ---- a3/a6/a7: dense 3x3 convs ------------------------------------------------------------------
+enum Conv3Mode : int { CONV_S1 = 0, CONV_S2 = 1, CONV_UP2 = 2 };
+// generic NHWC->NHWC, CUDA-core implicit GEMM; W row-major [Co][9*Ci] (k = tap*Ci + ci), bias fp32.
+// Hin,Win are the stored input size; output is Hin x Win (S1), Hin/2 (S2, pad 1) or 2*Hin (UP2: bilinear x2 first).
+void launch_conv3x3_simt(const void* in, const void* Wt, const float* bias, void* out, double* stats, int N,
+                         int Hin, int Win, int Ci, int Co, int mode, int bf16act, cudaStream_t st);
+// init_conv: x = cat([xa, xb]) fp32 NCHW -> NHWC; w fp32 [9*Cin][Co] (k = tap*Cin + ci), bias.
+void launch_init_conv(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const float* w,
+                      const float* bias, void* out, double* stats, int N, int H, int W, int Co, int bf16act,
+                      cudaStream_t st);
+// final: GN+SiLU prologue, 3x3 conv to Cout (<=4), fp32 NCHW output; optional fused LCMScheduler.step.
+struct FinalStep {
+  int enabled;           // 0: write eps only
+  const float* noise;    // null on the last step
+  float* latents;        // x_t in, x_prev out (in place)
+  float* clamped;        // optional clamp(x_prev,-1,1) output
+  float* trace;          // optional copy of x_prev
+  float sb_t, sa_t, sa_p, sb_p;
+};
+void launch_final_conv(const void* in, const float2* coef, const float* w, const float* bias, float* eps,
+                       const FinalStep& step, int N, int H, int W, int Ci, int Co, int bf16act, cudaStream_t st);
+
+// ---- a5: linear attention --------------------------------------------------------------------------
+// qkv NHWC [N][P][3*inner] (q | k | v, each heads*32); state [N][heads][32][33] fp32 (col 32 = k_sum), zeroed.
+void launch_attn_kv(const void* qkv, float* state, int N, int P, int heads, int bf16act, cudaStream_t st);
+void launch_attn_apply(const void* qkv, const float* state, void* out, int N, int P, int heads, int bf16act,
+                       cudaStream_t st);
+// y = a*u + b + x (to_out GroupNorm + residual), channel statistics of y.
+void launch_affine_residual(const void* u, const float2* coef, const void* x, void* y, double* stats, int N, int P,
+                            int C, int bf16act, cudaStream_t st);
+
+// ---- a11: LCMScheduler.step / add_noise stand-alone ---------------------------------------------------
+void launch_lcm_step(const float* eps, const float* sample, const float* noise, float* prev, float* x0,
+                     long long numel, int prediction, float sb_t, float sa_t, float sa_p, float sb_p, cudaStream_t st);
+void launch_lcm_mix(const float* a, const float* b, const long long* t, const float* abar, float* out, int batch,
+                    long long per_sample, int velocity, cudaStream_t st);
+
+// ---- weight packing ---------------------------------------------------------------------------------
+enum PackKind : int {
+  PACK_COPY = 0,     // dst_f32[i] = src[i]
+  PACK_MAT = 1,      // src [R][Cc] -> logical W(r, off + c)
+  PACK_CONV3 = 2,    // src [Co][Ci][3][3] -> logical W(co, off + tap*Ci + ci)
+  PACK_DW = 3,       // src [C][1][3][3] -> dst_f32[tap*C + c]
+  PACK_CONV3_KN = 4, // src [Co][Ci][3][3] -> dst_f32[(tap*Ci+ci)*Co + co]
+  PACK_IDENTITY = 5  // logical W(r, off + c) = (r == c)
+};
+enum WLayout : int { WL_ROWMAJOR = 0, WL_UMMA = 1 };
+struct PackJob {
+  int kind;
+  int layout;      // WLayout (for logical-matrix kinds)
+  int bf16;        // destination element type for logical-matrix kinds
+  void* dst;       // plan-time: byte offset in the weight arena; resolved to a pointer before launch
+  int R, Cc, Ci;   // rows (out channels), columns taken from this source, conv input channels
+  int src_ld;      // PACK_MAT: source row stride (elements)
+  int src_col0;    // PACK_MAT: first source column of the slice
+  int tap_stride;  // PACK_CONV3: logical columns per tap (Ci, or Ci rounded up to 64 for WL_UMMA)
+  int ld;          // K extent of the logical matrix (padded for WL_UMMA)
+  int off;         // column offset of this source in the logical matrix
+  int block_n;     // WL_UMMA: rows per N tile
+};
+void launch_pack(const PackJob& job, const float* src, cudaStream_t st);
+// element offset of logical (n, k) in the tcgen05 weight image (shared with the kernel's consumer side)
+__host__ __device__ inline long long umma_weight_offset(int n, int k, int Ktot, int block_n) {
+  // [n tile][k chunk of 64][row within tile: 128 B, 16-byte units XOR-swizzled by (row & 7)]
+  int nchunks = (Ktot + 63) / 64;
+  int nt = n / block_n, r = n % block_n, kc = k / 64, kk = k % 64;
+  long long base = ((long long)nt * nchunks + kc) * (long long)block_n * 64;
+  int unit = (kk / 8) ^ (r & 7);
+  return base + (long long)r * 64 + unit * 8 + (kk % 8);
+}
+
+// NHWC (storage type) -> fp32 NCHW, for taps
+void launch_nhwc_to_nchw(const void* in, float* out, int N, int H, int W, int C, int bf16act, cudaStream_t st);
+
+// ---- tcgen05 kernels (gemm_tcgen05.cu) ------------------------------------------------------------------
+// 1x1 GEMM and dense 3x3 implicit GEMM on the 5th-gen tensor cores.  W in WL_UMMA layout (bf16).
+struct ConvGeom {   // conv3x3 producer geometry (mode < 0: plain 1x1 GEMM)
+  int mode;         // Conv3Mode or -1
+  int Hin, Win, Hout, Wout, Ci;
+  const float* bias;
+};
+int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_sms, cudaStream_t st);
+int gemm_tc_pick_block_n(int Nc);
+
+}  // namespace lcm

@@ -1,0 +1,287 @@
+// Small kernels of the hot path: time embedding, FiLM, GroupNorm finalise, SE gate, scheduler step,
+// weight packing, layout conversion.  None of these moves a full activation tensor; they exist so
+// that the heavy kernels' prologues are a single per-(image, channel) affine.
+#include "kernels.h"
+
+namespace lcm {
+
+// ------------------------------------------------------------------------------------------------
+// SinusoidalPosEmb -> Linear -> SiLU -> Linear  (efficient_unet.py:68-76, 412-417).
+// One block per sample.  freqs follow the reference's fp32 op order:
+//   (float(-ln 1e4) * float(i)) / float(half) -> expf ; args = float(t) * freq ; [cos | sin].
+__global__ void time_embed_kernel(const long long* __restrict__ t_dev, long long t_scalar, int base, int ted,
+                                  const float* __restrict__ w1, const float* __restrict__ b1,
+                                  const float* __restrict__ w3, const float* __restrict__ b3,
+                                  float* __restrict__ temb, float* __restrict__ silu_temb) {
+  extern __shared__ float sm[];
+  float* emb = sm;          // [base]
+  float* hid = sm + base;   // [ted]
+  const int n = blockIdx.x;
+  const float t = (float)(t_dev ? t_dev[n] : t_scalar);
+  const int half = base / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float f = expf((-9.210340371976184f * (float)i) / (float)half);
+    float a = t * f;
+    emb[i] = cosf(a);
+    emb[half + i] = sinf(a);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < ted; j += blockDim.x) {
+    float acc = b1[j];
+    for (int i = 0; i < base; ++i) acc = fmaf(w1[j * base + i], emb[i], acc);
+    hid[j] = acc / (1.f + expf(-acc));
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < ted; j += blockDim.x) {
+    float acc = b3[j];
+    for (int i = 0; i < ted; ++i) acc = fmaf(w3[j * ted + i], hid[i], acc);
+    if (temb) temb[(size_t)n * ted + j] = acc;
+    silu_temb[(size_t)n * ted + j] = acc / (1.f + expf(-acc));
+  }
+}
+
+void launch_time_embed(const long long* t_dev, long long t_scalar, int N, int base, int ted, const float* w1,
+                       const float* b1, const float* w3, const float* b3, float* temb, float* silu_temb,
+                       cudaStream_t st) {
+  time_embed_kernel<<<N, 128, (base + ted) * sizeof(float), st>>>(t_dev, t_scalar, base, ted, w1, b1, w3, b3, temb,
+                                                                  silu_temb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// All blocks' FiLM projections (efficient_unet.py:189-192,215): one warp per output row, looping
+// over the batch with the weight row held in registers.
+__global__ void film_kernel(const float* __restrict__ s, const float* __restrict__ W, const float* __restrict__ b,
+                            float* __restrict__ out, int N, int rows, int ted) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float w[16];  // ted <= 512
+  const int per = (ted + 31) / 32;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) w[j] = (j < per && j * 32 + lane < ted) ? W[(size_t)row * ted + j * 32 + lane] : 0.f;
+  const float bias = b[row];
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < per && j * 32 + lane < ted) acc = fmaf(w[j], s[(size_t)n * ted + j * 32 + lane], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(size_t)n * rows + row] = acc + bias;
+  }
+}
+
+void launch_film(const float* silu_temb, const float* W, const float* b, float* out, int N, int rows, int ted,
+                 cudaStream_t st) {
+  const int warps = 8;
+  film_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(silu_temb, W, b, out, N, rows, ted);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm finalise (efficient_unet.py:170-171,207,212 ; F.group_norm semantics: biased variance,
+// eps = 1e-5 inside the sqrt).  One block per image.
+__global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const double* __restrict__ s1, int C1,
+                               int groups, double count, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
+                               float2* __restrict__ coef) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int n = blockIdx.x;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double sum = 0.0, sq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double* p = (c < C0) ? s0 + ((size_t)n * C0 + c) * 2 : s1 + ((size_t)n * C1 + (c - C0)) * 2;
+      sum += p[0];
+      sq += p[1];
+    }
+    double mean = sum / count;
+    double var = sq / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float a = gamma[c] * s_rstd[g];
+    float b = beta[c] - s_mean[g] * a;
+    if (film) {
+      const float sc = 1.f + film[(size_t)n * film_ld + c];
+      const float sh = film[(size_t)n * film_ld + C + c];
+      a *= sc;
+      b = fmaf(b, sc, sh);
+    }
+    coef[(size_t)n * C + c] = make_float2(a, b);
+  }
+}
+
+void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
+                    const float* gamma, const float* beta, const float* film, int film_ld, float2* coef, int N,
+                    cudaStream_t st) {
+  gn_coef_kernel<<<N, 256, 0, st>>>(stats0, C0, stats1, C1, groups, count, gamma, beta, film, film_ld, coef);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Squeeze-and-Excitation gate (efficient_unet.py:96-100).  One block per image; fc weights fp32
+// [SQ][C] and [C][SQ].  Output is a prologue coefficient (gate, 0) for the project GEMM.
+__global__ void se_gate_kernel(const float* __restrict__ pool, float inv_count, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2,
+                               const float* __restrict__ b2, float2* __restrict__ coef, int C, int SQ) {
+  extern __shared__ float sm[];
+  float* mean = sm;       // [C]
+  float* hid = sm + C;    // [SQ]
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(size_t)n * C + c] * inv_count;
+  __syncthreads();
+  for (int j = warp; j < SQ; j += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) hid[j] = fminf(fmaxf(acc + b1[j], 0.f), 6.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nw) {
+    float acc = 0.f;
+    for (int j = lane; j < SQ; j += 32) acc = fmaf(w2[(size_t)c * SQ + j], hid[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) coef[(size_t)n * C + c] = make_float2(1.f / (1.f + expf(-(acc + b2[c]))), 0.f);
+  }
+}
+
+void launch_se_gate(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st) {
+  se_gate_kernel<<<N, 512, (C + SQ) * sizeof(float), st>>>(pool, inv_count, w1, b1, w2, b2, coef, C, SQ);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LCMScheduler.step (lcm_scheduler.py:214-242) and add_noise/get_velocity (:255-305), stand-alone.
+__global__ void lcm_step_kernel(const float* __restrict__ eps, const float* __restrict__ sample,
+                                const float* __restrict__ noise, float* __restrict__ prev, float* __restrict__ x0o,
+                                long long numel, int prediction, float sb_t, float sa_t, float sa_p, float sb_p) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float e = eps[i], x = sample[i];
+    float x0 = prediction == 0 ? (x - sb_t * e) / sa_t : sa_t * x - sb_t * e;
+    if (x0o) x0o[i] = x0;
+    prev[i] = noise ? sa_p * x0 + sb_p * noise[i] : x0;
+  }
+}
+
+void launch_lcm_step(const float* eps, const float* sample, const float* noise, float* prev, float* x0,
+                     long long numel, int prediction, float sb_t, float sa_t, float sa_p, float sb_p,
+                     cudaStream_t st) {
+  int blocks = (int)((numel + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  lcm_step_kernel<<<blocks, 256, 0, st>>>(eps, sample, noise, prev, x0, numel, prediction, sb_t, sa_t, sa_p, sb_p);
+}
+
+__global__ void lcm_mix_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                               const long long* __restrict__ t, const float* __restrict__ abar,
+                               float* __restrict__ out, long long per_sample, int velocity) {
+  const int n = blockIdx.y;
+  const float ab = abar[t[n]];
+  const float sa = sqrtf(ab), sb = sqrtf(1.f - ab);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = (long long)n * per_sample + i;
+    out[j] = velocity ? sa * b[j] - sb * a[j] : sa * a[j] + sb * b[j];
+  }
+}
+
+void launch_lcm_mix(const float* a, const float* b, const long long* t, const float* abar, float* out, int batch,
+                    long long per_sample, int velocity, cudaStream_t st) {
+  int bx = (int)((per_sample + 255) / 256);
+  if (bx > 1024) bx = 1024;
+  lcm_mix_kernel<<<dim3(bx, batch), 256, 0, st>>>(a, b, t, abar, out, per_sample, velocity);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: fp32 state_dict tensors -> the layouts the kernels read.
+template <typename T>
+__device__ __forceinline__ void put_logical(const PackJob& j, int n, int k, float v) {
+  long long o = (j.layout == WL_UMMA) ? umma_weight_offset(n, k, j.ld, j.block_n) : (long long)n * j.ld + k;
+  reinterpret_cast<T*>(j.dst)[o] = from_f<T>(v);
+}
+
+__global__ void pack_kernel(PackJob j, const float* __restrict__ src, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    switch (j.kind) {
+      case PACK_COPY:
+        reinterpret_cast<float*>(j.dst)[i] = src[i];
+        break;
+      case PACK_MAT: {
+        int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
+        const float v = src[(size_t)r * j.src_ld + j.src_col0 + c];
+        if (j.bf16) put_logical<bf16>(j, r, j.off + c, v); else put_logical<float>(j, r, j.off + c, v);
+        break;
+      }
+      case PACK_IDENTITY: {
+        int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
+        float v = (r == c) ? 1.f : 0.f;
+        if (j.bf16) put_logical<bf16>(j, r, j.off + c, v); else put_logical<float>(j, r, j.off + c, v);
+        break;
+      }
+      case PACK_CONV3: {  // src [Co][Ci][3][3]
+        int tap = (int)(i % 9);
+        long long q = i / 9;
+        int ci = (int)(q % j.Ci), co = (int)(q / j.Ci);
+        int k = j.off + tap * j.tap_stride + ci;
+        if (j.bf16) put_logical<bf16>(j, co, k, src[i]); else put_logical<float>(j, co, k, src[i]);
+        break;
+      }
+      case PACK_CONV3_KN: {
+        int tap = (int)(i % 9);
+        long long q = i / 9;
+        int ci = (int)(q % j.Ci), co = (int)(q / j.Ci);
+        reinterpret_cast<float*>(j.dst)[(size_t)(tap * j.Ci + ci) * j.R + co] = src[i];
+        break;
+      }
+      case PACK_DW: {  // src [C][1][3][3]
+        int tap = (int)(i % 9), c = (int)(i / 9);
+        reinterpret_cast<float*>(j.dst)[(size_t)tap * j.R + c] = src[i];
+        break;
+      }
+    }
+  }
+}
+
+void launch_pack(const PackJob& job, const float* src, cudaStream_t st) {
+  long long total = 0;
+  switch (job.kind) {
+    case PACK_COPY: total = (long long)job.R * job.Cc; break;
+    case PACK_MAT: case PACK_IDENTITY: total = (long long)job.R * job.Cc; break;
+    case PACK_CONV3: case PACK_CONV3_KN: total = (long long)job.R * job.Ci * 9; break;
+    case PACK_DW: total = (long long)job.R * 9; break;
+  }
+  if (total == 0) return;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_kernel<<<blocks, 256, 0, st>>>(job, src, total);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int HW, int C, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / ((long long)HW * C);
+    long long r = i % ((long long)HW * C);
+    int c = (int)(r / HW), p = (int)(r % HW);
+    out[i] = to_f<T>(in[(n * HW + p) * C + c]);
+  }
+}
+
+void launch_nhwc_to_nchw(const void* in, float* out, int N, int H, int W, int C, int bf16act, cudaStream_t st) {
+  long long total = (long long)N * H * W * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (bf16act) nhwc_to_nchw_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)in, out, H * W, C, total);
+  else nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, out, H * W, C, total);
+}
+
+}  // namespace lcm

@@ -1,0 +1,131 @@
+// Single-kernel C entry points (include/lcm_unet.h, "single-kernel entry points"): unit parity, ncu.
+#include <vector>
+
+#include "../../include/lcm_unet.h"
+#include "kernels.h"
+
+using namespace lcm;
+
+namespace {
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  float* out;
+  int repeat;
+  Timer(cudaStream_t s, float* o, int r) : st(s), out(o), repeat(r) {
+    if (out) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  }
+  void stop() {
+    if (out) {
+      cudaEventRecord(b, st); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms, a, b); *out = ms / repeat;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+  }
+};
+int finish(cudaStream_t st) {
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : LCM_ERR_CUDA;
+}
+}  // namespace
+
+extern "C" {
+
+int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
+                int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream) {
+  if (!segs || nseg < 1 || nseg > LCM_MAX_SEGS || !w_dev || !out_dev || repeat < 1) return LCM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = precision == LCM_PREC_BF16, tc = bf && impl == 1;
+  GemmParams gp{};
+  int Ktot = 0, Kpad = 0;
+  std::vector<int> off, poff;
+  for (int i = 0; i < nseg; ++i) { off.push_back(Ktot); poff.push_back(Kpad); Ktot += segs[i].K; Kpad += (segs[i].K + 63) / 64 * 64; }
+  const int block_n = tc ? gemm_tc_pick_block_n(Nc) : 0;
+  const size_t wbytes = tc ? (size_t)Nc * Kpad * 2 : (size_t)Nc * Ktot * (bf ? 2 : 4);
+  void* wbuf = nullptr;
+  if (cudaMalloc(&wbuf, wbytes) != cudaSuccess) return LCM_ERR_CUDA;
+  cudaMemsetAsync(wbuf, 0, wbytes, st);
+  for (int i = 0; i < nseg; ++i) {
+    PackJob j{};
+    j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = bf; j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
+    j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = tc ? Kpad : Ktot; j.off = tc ? poff[i] : off[i]; j.block_n = block_n;
+    launch_pack(j, w_dev, st);
+    gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
+    gp.seg[i].coef = (const float2*)segs[i].coef; gp.seg[i].coef_ld = segs[i].K; gp.seg[i].coef_off = 0;
+    gp.seg[i].mode = segs[i].coef ? segs[i].mode : XF_NONE;
+  }
+  gp.nseg = nseg; gp.Ktot = Ktot; gp.W = wbuf; gp.out = out_dev; gp.stats = stats_dev; gp.M = M; gp.P = P; gp.Nc = Nc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc = 0;
+  Timer t(st, ms_out, repeat);
+  for (int r = 0; r < repeat && rc == 0; ++r) {
+    if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
+    else launch_gemm_simt(gp, bf, st);
+  }
+  t.stop();
+  int rc2 = finish(st);
+  cudaFree(wbuf);
+  return rc ? LCM_ERR_INVALID : rc2;
+}
+
+int lcm_op_conv3x3(const void* in_dev, const float* w_dev, const float* bias_dev, void* out_dev, double* stats_dev,
+                   int N, int Hin, int Win, int Ci, int Co, int mode, int precision, int impl, int repeat,
+                   float* ms_out, void* stream) {
+  if (!in_dev || !w_dev || !bias_dev || !out_dev || repeat < 1 || mode < 0 || mode > 2) return LCM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = precision == LCM_PREC_BF16, tc = bf && impl == 1;
+  const int Cpad = (Ci + 63) / 64 * 64;
+  const int block_n = tc ? gemm_tc_pick_block_n(Co) : 0;
+  const size_t wbytes = tc ? (size_t)Co * 9 * Cpad * 2 : (size_t)Co * 9 * Ci * (bf ? 2 : 4);
+  void* wbuf = nullptr;
+  if (cudaMalloc(&wbuf, wbytes) != cudaSuccess) return LCM_ERR_CUDA;
+  cudaMemsetAsync(wbuf, 0, wbytes, st);
+  PackJob j{};
+  j.kind = PACK_CONV3; j.bf16 = bf; j.R = Co; j.Ci = Ci; j.dst = wbuf;
+  if (tc) { j.layout = WL_UMMA; j.ld = 9 * Cpad; j.tap_stride = Cpad; j.block_n = block_n; }
+  else { j.layout = WL_ROWMAJOR; j.ld = 9 * Ci; j.tap_stride = Ci; }
+  launch_pack(j, w_dev, st);
+  const int Ho = mode == CONV_S2 ? Hin / 2 : (mode == CONV_UP2 ? Hin * 2 : Hin);
+  const int Wo = mode == CONV_S2 ? Win / 2 : (mode == CONV_UP2 ? Win * 2 : Win);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc = 0;
+  Timer t(st, ms_out, repeat);
+  for (int r = 0; r < repeat && rc == 0; ++r) {
+    if (tc) {
+      GemmParams gp{};
+      gp.nseg = 1; gp.seg[0].A = in_dev; gp.seg[0].K = 9 * Ci; gp.seg[0].ld = Ci; gp.seg[0].mode = XF_NONE;
+      gp.Ktot = 9 * Ci; gp.W = wbuf; gp.out = out_dev; gp.stats = stats_dev; gp.P = Ho * Wo; gp.M = (long long)N * Ho * Wo; gp.Nc = Co;
+      ConvGeom cg{mode, Hin, Win, Ho, Wo, Ci, bias_dev};
+      rc = launch_gemm_tc(gp, cg, block_n, sms, st);
+    } else {
+      launch_conv3x3_simt(in_dev, wbuf, bias_dev, out_dev, stats_dev, N, Hin, Win, Ci, Co, mode, bf, st);
+    }
+  }
+  t.stop();
+  int rc2 = finish(st);
+  cudaFree(wbuf);
+  return rc ? LCM_ERR_INVALID : rc2;
+}
+
+int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, float* pool_dev, int N,
+                  int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream) {
+  if (!in_dev || !coef_dev || !w_dev || !out_dev || !pool_dev || repeat < 1 || C % 32) return LCM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = precision == LCM_PREC_BF16;
+  float* wbuf = nullptr;
+  if (cudaMalloc((void**)&wbuf, (size_t)9 * C * 4) != cudaSuccess) return LCM_ERR_CUDA;
+  PackJob j{}; j.kind = PACK_DW; j.dst = wbuf; j.R = C;
+  launch_pack(j, w_dev, st);
+  Timer t(st, ms_out, repeat);
+  for (int r = 0; r < repeat; ++r)
+    launch_dwconv(in_dev, (const float2*)coef_dev, wbuf, out_dev, pool_dev, N, H, W, C, bf, impl, st);
+  t.stop();
+  int rc = finish(st);
+  cudaFree(wbuf);
+  return rc;
+}
+
+}  // extern "C"

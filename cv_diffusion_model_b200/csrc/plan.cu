@@ -1,0 +1,832 @@
+// Execution plan of EfficientUNet.forward + the LCM loop, and the C ABI (include/lcm_unet.h).
+//
+// The plan is the static op list of one forward for fixed (config, B, H, W): every tensor lives at a
+// fixed offset of a caller-provided workspace, so a forward is a pure sequence of kernel launches
+// on the caller's stream (no allocation, no host sync).  Op order follows
+// /root/reference/src/models/efficient_unet.py:532-606; each block is cut into
+//   gn_coef | expand GEMM | gn_coef(+FiLM) | depthwise(+SE pool) | se_gate | project GEMM(+residual)
+// so that GroupNorm / FiLM / ReLU6 / SE-scale / residual never touch HBM on their own.
+//
+// Workspace regions: Z (zeroed at the start of every forward: channel statistics, SE pools, attention
+// state), F (small fixed buffers: prologue coefficients, FiLM table, time embedding), A (activations,
+// NHWC, offsets assigned by a plan-time first-fit allocator with lifetime-based reuse).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lcm_unet.h"
+#include "kernels.h"
+
+using namespace lcm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (x);                                                                   \
+    if (e_ != cudaSuccess) return fail(LCM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+struct Tensor {
+  size_t off = 0;        // byte offset in region A
+  size_t bytes = 0;
+  int C = 0, H = 0, W = 0;
+  size_t stats_off = 0;  // byte offset of double[N][C][2] in region Z
+  int refs = 0;
+};
+typedef std::shared_ptr<Tensor> TensorP;
+
+struct RunCtx {
+  char* z; char* f; char* a;   // region bases
+  const float* xa; int ca; long long sa;
+  const float* xb; int cb; long long sb;
+  const long long* t_dev; long long t_scalar;
+  float* eps;
+  FinalStep step;
+};
+
+typedef std::function<void(const RunCtx&, cudaStream_t)> RunFn;
+struct Op {
+  std::string name, kernel;
+  double bytes = 0, flops = 0;
+  RunFn run;
+};
+
+struct WeightSlot {
+  int64_t numel = 0;
+  std::vector<PackJob> jobs;
+  bool set = false;
+};
+
+// first-fit free-list allocator over region A (plan-time only)
+struct PoolAlloc {
+  struct Blk { size_t off, size; };
+  std::vector<Blk> free_list;
+  size_t top = 0;
+  bool reuse = true;
+  size_t alloc(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    if (reuse) {
+      for (size_t i = 0; i < free_list.size(); ++i) {
+        if (free_list[i].size >= bytes) {
+          size_t off = free_list[i].off;
+          if (free_list[i].size == bytes) free_list.erase(free_list.begin() + i);
+          else { free_list[i].off += bytes; free_list[i].size -= bytes; }
+          return off;
+        }
+      }
+      if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+        size_t off = free_list.back().off;   // grow the trailing free block
+        top = off + bytes;
+        free_list.pop_back();
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    if (!reuse) return;
+    bytes = align_up(bytes, 1024);
+    size_t i = 0;
+    while (i < free_list.size() && free_list[i].off < off) ++i;
+    free_list.insert(free_list.begin() + i, Blk{off, bytes});
+    for (size_t j = 0; j + 1 < free_list.size();) {
+      if (free_list[j].off + free_list[j].size == free_list[j + 1].off) {
+        free_list[j].size += free_list[j + 1].size;
+        free_list.erase(free_list.begin() + j + 1);
+      } else ++j;
+    }
+  }
+};
+
+}  // namespace
+
+struct lcm_plan {
+  lcm_unet_config cfg;
+  int N = 0, H = 0, W = 0, prec = 0, device = 0;
+  uint32_t flags = 0;
+  bool bf16 = false, tc = false, taps = false;
+  int num_sms = 148;
+  size_t esz = 4;  // activation element size
+
+  size_t z_bytes = 0, f_bytes = 0;
+  PoolAlloc pool;
+  size_t ws_bytes = 0;
+
+  char* wbase = nullptr;   // packed weights (owned)
+  size_t wbytes = 0;
+  std::vector<PackJob> identity_jobs;
+  std::map<std::string, WeightSlot> weights;
+  std::vector<std::string> weight_order;
+
+  int film_rows = 0;
+  size_t film_f_off = 0, silu_f_off = 0;
+
+  std::vector<Op> ops;
+  std::map<std::string, TensorP> tap_map;
+  std::vector<std::string> tap_order;
+  double total_bytes = 0, total_flops = 0;
+
+  size_t walloc(size_t bytes) { size_t o = wbytes; wbytes += align_up(bytes, 256); return o; }
+  size_t zalloc(size_t bytes) { size_t o = z_bytes; z_bytes += align_up(bytes, 256); return o; }
+  size_t falloc(size_t bytes) { size_t o = f_bytes; f_bytes += align_up(bytes, 256); return o; }
+
+  int groups(int C) const {
+    int g = C < 32 ? C : 32;
+    if (C % g == 0) return g;
+    return cfg.groupnorm_gcd ? gcd_i(32, C) : -1;
+  }
+  TensorP new_tensor(int C, int h, int w, bool stats, const std::string& tap) {
+    TensorP t = std::make_shared<Tensor>();
+    t->C = C; t->H = h; t->W = w;
+    t->bytes = (size_t)N * h * w * C * esz;
+    t->off = pool.alloc(t->bytes);
+    t->refs = 1;
+    if (stats) t->stats_off = zalloc((size_t)N * C * 2 * sizeof(double));
+    if (taps && !tap.empty()) { tap_map[tap] = t; tap_order.push_back(tap); }
+    return t;
+  }
+  void release(const TensorP& t) { if (--t->refs == 0) pool.release(t->off, t->bytes); }
+
+  void add_weight(const std::string& name, int64_t numel, const PackJob& job) {
+    if (weights.find(name) == weights.end()) { weight_order.push_back(name); weights[name].numel = numel; }
+    weights[name].jobs.push_back(job);
+  }
+  size_t add_copy(const std::string& name, int64_t numel) {   // verbatim fp32 copy; returns weight-arena offset
+    size_t off = walloc(numel * sizeof(float));
+    PackJob j{}; j.kind = PACK_COPY; j.dst = (void*)off; j.R = 1; j.Cc = (int)numel;
+    add_weight(name, numel, j);
+    return off;
+  }
+  const float* wf(size_t off) const { return (const float*)(wbase + off); }
+};
+
+namespace {
+
+// A GEMM weight: logical [Nc][sum K_s]; in the tcgen05 image every segment is padded to 64-wide chunks.
+struct GemmW {
+  size_t off = 0;
+  int Nc = 0, Ktot = 0, Kpad = 0, block_n = 0;
+  std::vector<int> seg_off, seg_pad_off;
+};
+
+struct View {
+  TensorP part[2];
+  int n = 0;
+  int C() const { return (n > 0 ? part[0]->C : 0) + (n > 1 ? part[1]->C : 0); }
+  static View of(const TensorP& t) { View v; v.part[0] = t; v.n = 1; return v; }
+};
+
+struct Builder {
+  lcm_plan* p;
+  int N;
+  struct FilmBlock { std::string wname; int row0, rows; };
+  std::vector<FilmBlock> film_blocks;
+  explicit Builder(lcm_plan* plan) : p(plan), N(plan->N) {}
+
+  void push(const std::string& name, const char* kernel, double bytes, double flops, RunFn fn) {
+    Op o; o.name = name; o.kernel = kernel; o.bytes = bytes; o.flops = flops; o.run = std::move(fn);
+    p->total_bytes += bytes; p->total_flops += flops;
+    p->ops.push_back(std::move(o));
+  }
+
+  GemmW make_w(int Nc, const std::vector<int>& segK) {
+    GemmW g;
+    g.Nc = Nc;
+    for (int k : segK) {
+      g.seg_off.push_back(g.Ktot);
+      g.seg_pad_off.push_back(g.Kpad);
+      g.Ktot += k;
+      g.Kpad += (k + 63) / 64 * 64;
+    }
+    if (p->tc) { g.block_n = gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
+    else g.off = p->walloc((size_t)Nc * g.Ktot * p->esz);
+    return g;
+  }
+  // job that writes columns [src_col0, src_col0+Cc) of a [R][src_ld] source into segment `seg`
+  PackJob mat_job(const GemmW& g, int seg, int kind, int R, int Cc, int src_ld, int src_col0) {
+    PackJob j{};
+    j.kind = kind;
+    j.layout = p->tc ? WL_UMMA : WL_ROWMAJOR;
+    j.bf16 = p->bf16 ? 1 : 0;
+    j.dst = (void*)g.off;
+    j.R = R; j.Cc = Cc; j.src_ld = src_ld; j.src_col0 = src_col0;
+    j.ld = p->tc ? g.Kpad : g.Ktot;
+    j.off = p->tc ? g.seg_pad_off[seg] : g.seg_off[seg];
+    j.block_n = g.block_n;
+    return j;
+  }
+
+  // GroupNorm finalise -> coef buffer [N][C] in region F
+  size_t gn_coef(const std::string& name, const View& x, const std::string& wname, int film_row0) {
+    const int C = x.C(), G = p->groups(C);
+    const size_t coef = p->falloc((size_t)N * C * sizeof(float2));
+    const size_t g_off = p->add_copy(wname + ".weight", C), b_off = p->add_copy(wname + ".bias", C);
+    const size_t s0 = x.part[0]->stats_off; const int C0 = x.part[0]->C;
+    const size_t s1 = x.n > 1 ? x.part[1]->stats_off : 0; const int C1 = x.n > 1 ? x.part[1]->C : 0;
+    const double count = (double)x.part[0]->H * x.part[0]->W * (C / G);
+    lcm_plan* pl = p; const int n = N;
+    push(name, "gn_coef", 0, 0, [=](const RunCtx& c, cudaStream_t st) {
+      const float* film = film_row0 >= 0 ? (const float*)(c.f + pl->film_f_off) + film_row0 : nullptr;
+      launch_gn_coef((const double*)(c.z + s0), C0, C1 ? (const double*)(c.z + s1) : nullptr, C1, G, count,
+                     pl->wf(g_off), pl->wf(b_off), film, pl->film_rows, (float2*)(c.f + coef), n, st);
+    });
+    return coef;
+  }
+
+  struct SegSpec { TensorP t; size_t coef; int coef_ld, coef_off, mode; };
+
+  void gemm(const std::string& name, const std::vector<SegSpec>& segs, const GemmW& w, const TensorP& out, bool stats,
+            double bytes, double flops) {
+    lcm_plan* pl = p; const int n = N;
+    std::vector<SegSpec> sg = segs;
+    push(name, pl->tc ? "gemm_tc" : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
+      GemmParams gp{};
+      gp.nseg = (int)sg.size();
+      for (int i = 0; i < gp.nseg; ++i) {
+        gp.seg[i].A = c.a + sg[i].t->off;
+        gp.seg[i].K = sg[i].t->C;
+        gp.seg[i].ld = sg[i].t->C;
+        gp.seg[i].coef = sg[i].mode == XF_NONE ? nullptr : (const float2*)(c.f + sg[i].coef);
+        gp.seg[i].coef_ld = sg[i].coef_ld;
+        gp.seg[i].coef_off = sg[i].coef_off;
+        gp.seg[i].mode = sg[i].mode;
+      }
+      gp.Ktot = w.Ktot;
+      gp.W = pl->wbase + w.off;
+      gp.out = c.a + out->off;
+      gp.stats = stats ? (double*)(c.z + out->stats_off) : nullptr;
+      gp.P = out->H * out->W;
+      gp.M = (long long)n * gp.P;
+      gp.Nc = w.Nc;
+      if (pl->tc) { ConvGeom g{}; g.mode = -1; launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st); }
+      else launch_gemm_simt(gp, pl->bf16, st);
+    });
+  }
+
+  // ---- InvertedResidualBlock (efficient_unet.py:203-236) -------------------------------------
+  TensorP block(const std::string& name, const View& x, int Co) {
+    const int Ci = x.C(), Ch = Ci * p->cfg.expansion_ratio;
+    int SQ = (int)(Ch * p->cfg.se_ratio);
+    if (SQ < 1) SQ = 1;
+    const int h = x.part[0]->H, w = x.part[0]->W;
+    const double P = (double)h * w, es = (double)p->esz;
+    const int row0 = p->film_rows;   // this block's [scale | shift] rows in the fused FiLM GEMV
+    p->film_rows += 2 * Ch;
+    film_blocks.push_back({name + ".time_mlp.1", row0, 2 * Ch});
+
+    // norm1 -> ReLU6 -> expand (:207-209)
+    const size_t coef1 = gn_coef(name + ".norm1", x, name + ".norm1", -1);
+    TensorP h1 = p->new_tensor(Ch, h, w, true, name + ".expand");
+    {
+      std::vector<int> segK;
+      for (int i = 0; i < x.n; ++i) segK.push_back(x.part[i]->C);
+      GemmW we = make_w(Ch, segK);
+      std::vector<SegSpec> segs;
+      int col = 0;
+      for (int i = 0; i < x.n; ++i) {
+        segs.push_back({x.part[i], coef1, Ci, col, XF_AFFINE_RELU6});
+        p->add_weight(name + ".expand.weight", (int64_t)Ch * Ci, mat_job(we, i, PACK_MAT, Ch, x.part[i]->C, Ci, col));
+        col += x.part[i]->C;
+      }
+      gemm(name + ".expand", segs, we, h1, true, (Ci + Ch) * N * P * es + (double)Ci * Ch * es, 2.0 * N * P * Ci * Ch);
+    }
+    // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
+    const size_t coef2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
+    TensorP h2 = p->new_tensor(Ch, h, w, false, name + ".depthwise");
+    const size_t pool = p->zalloc((size_t)N * Ch * sizeof(float));
+    const size_t dw_off = p->walloc((size_t)9 * Ch * sizeof(float));
+    { PackJob j{}; j.kind = PACK_DW; j.dst = (void*)dw_off; j.R = Ch; p->add_weight(name + ".depthwise.weight", (int64_t)Ch * 9, j); }
+    {
+      lcm_plan* pl = p; const int n = N;
+      push(name + ".depthwise", "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
+           [=](const RunCtx& c, cudaStream_t st) {
+             launch_dwconv(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
+                           (float*)(c.z + pool), n, h, w, Ch, pl->bf16, pl->bf16 && pl->tc, st);
+           });
+    }
+    p->release(h1);
+    // SE gate (:98-99)
+    const size_t gate = p->falloc((size_t)N * Ch * sizeof(float2));
+    const size_t w1 = p->add_copy(name + ".se.fc1.weight", (int64_t)SQ * Ch), b1 = p->add_copy(name + ".se.fc1.bias", SQ);
+    const size_t w2 = p->add_copy(name + ".se.fc2.weight", (int64_t)Ch * SQ), b2 = p->add_copy(name + ".se.fc2.bias", Ch);
+    {
+      lcm_plan* pl = p; const int n = N;
+      push(name + ".se", "se_gate", 2.0 * Ch * SQ * 4 + 8.0 * N * Ch, 4.0 * N * Ch * SQ,
+           [=](const RunCtx& c, cudaStream_t st) {
+             launch_se_gate((const float*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2), pl->wf(b2),
+                            (float2*)(c.f + gate), n, Ch, SQ, st);
+           });
+    }
+    // SE scale -> project -> + (skip conv | identity)(x)  (:100,226,230-234) as ONE GEMM over [h2 | x]
+    TensorP out = p->new_tensor(Co, h, w, true, name + ".out");
+    {
+      std::vector<int> pk;
+      pk.push_back(Ch);
+      for (int i = 0; i < x.n; ++i) pk.push_back(x.part[i]->C);
+      GemmW wp = make_w(Co, pk);
+      p->add_weight(name + ".project.weight", (int64_t)Co * Ch, mat_job(wp, 0, PACK_MAT, Co, Ch, Ch, 0));
+      std::vector<SegSpec> segs;
+      segs.push_back({h2, gate, Ch, 0, XF_AFFINE});
+      int col = 0;
+      for (int i = 0; i < x.n; ++i) {
+        segs.push_back({x.part[i], 0, 0, 0, XF_NONE});
+        if (Ci != Co) p->add_weight(name + ".skip.weight", (int64_t)Co * Ci, mat_job(wp, 1 + i, PACK_MAT, Co, x.part[i]->C, Ci, col));
+        else p->identity_jobs.push_back(mat_job(wp, 1 + i, PACK_IDENTITY, Co, x.part[i]->C, Ci, col));
+        col += x.part[i]->C;
+      }
+      const double bytes = (Ch + Ci + Co) * N * P * es + (double)Ch * Co * es + (Ci != Co ? (double)Ci * Co * es : 0.0);
+      const double flops = 2.0 * N * P * Ch * Co + (Ci != Co ? 2.0 * N * P * Ci * Co : 0.0);
+      gemm(name + ".project", segs, wp, out, true, bytes, flops);
+    }
+    p->release(h2);
+    for (int i = 0; i < x.n; ++i) p->release(x.part[i]);
+    return out;
+  }
+
+  // ---- LinearAttention (efficient_unet.py:273-308) ---------------------------------------------
+  TensorP attention(const std::string& name, const TensorP& x) {
+    const int C = x->C, heads = p->cfg.num_attention_heads, inner = heads * 32;
+    const int h = x->H, w = x->W, P = h * w;
+    const double es = (double)p->esz;
+    const size_t coefn = gn_coef(name + ".norm", View::of(x), name + ".norm", -1);
+    TensorP qkv = p->new_tensor(3 * inner, h, w, false, name + ".qkv");
+    GemmW wq = make_w(3 * inner, {C});
+    p->add_weight(name + ".to_qkv.weight", (int64_t)3 * inner * C, mat_job(wq, 0, PACK_MAT, 3 * inner, C, C, 0));
+    gemm(name + ".to_qkv", {{x, coefn, C, 0, XF_AFFINE}}, wq, qkv, false,
+         (C + 3.0 * inner) * N * P * es + 3.0 * inner * C * es, 2.0 * N * P * C * 3 * inner);
+    const size_t state = p->zalloc((size_t)N * heads * 32 * 33 * sizeof(float));
+    TensorP o = p->new_tensor(inner, h, w, false, name + ".attn");
+    {
+      lcm_plan* pl = p; const int n = N;
+      push(name + ".kv", "attn_kv", 2.0 * inner * N * P * es, 2.0 * N * heads * P * 32 * 33,
+           [=](const RunCtx& c, cudaStream_t st) { launch_attn_kv(c.a + qkv->off, (float*)(c.z + state), n, P, heads, pl->bf16, st); });
+      push(name + ".apply", "attn_apply", 2.0 * inner * N * P * es, 2.0 * N * heads * P * 32 * 33,
+           [=](const RunCtx& c, cudaStream_t st) {
+             launch_attn_apply(c.a + qkv->off, (const float*)(c.z + state), c.a + o->off, n, P, heads, pl->bf16, st);
+           });
+    }
+    p->release(qkv);
+    TensorP u = p->new_tensor(C, h, w, true, "");
+    GemmW wo = make_w(C, {inner});
+    p->add_weight(name + ".to_out.0.weight", (int64_t)C * inner, mat_job(wo, 0, PACK_MAT, C, inner, inner, 0));
+    gemm(name + ".to_out", {{o, 0, 0, 0, XF_NONE}}, wo, u, true, (C + (double)inner) * N * P * es + (double)inner * C * es,
+         2.0 * N * P * C * inner);
+    p->release(o);
+    const size_t coefo = gn_coef(name + ".to_out.1", View::of(u), name + ".to_out.1", -1);
+    TensorP y = p->new_tensor(C, h, w, true, name + ".out");
+    {
+      lcm_plan* pl = p; const int n = N;
+      push(name + ".gn_residual", "affine_residual", 3.0 * C * N * P * es, 3.0 * N * P * C,
+           [=](const RunCtx& c, cudaStream_t st) {
+             launch_affine_residual(c.a + u->off, (const float2*)(c.f + coefo), c.a + x->off, c.a + y->off,
+                                    (double*)(c.z + y->stats_off), n, P, C, pl->bf16, st);
+           });
+    }
+    p->release(u);
+    p->release(x);
+    return y;
+  }
+
+  // ---- Downsample / Upsample (efficient_unet.py:360-384) -------------------------------------
+  TensorP conv3(const std::string& name, const std::string& wname, const TensorP& x, int mode) {
+    const int C = x->C;
+    const int Ho = mode == CONV_S2 ? x->H / 2 : (mode == CONV_UP2 ? x->H * 2 : x->H);
+    const int Wo = mode == CONV_S2 ? x->W / 2 : (mode == CONV_UP2 ? x->W * 2 : x->W);
+    TensorP out = p->new_tensor(C, Ho, Wo, true, name);
+    const int Cpad = (C + 63) / 64 * 64;
+    PackJob j{};
+    j.kind = PACK_CONV3; j.bf16 = p->bf16 ? 1 : 0; j.R = C; j.Ci = C;
+    int block_n = 0;
+    size_t w_off;
+    if (p->tc) {
+      block_n = gemm_tc_pick_block_n(C);
+      w_off = p->walloc((size_t)C * 9 * Cpad * sizeof(bf16));
+      j.layout = WL_UMMA; j.ld = 9 * Cpad; j.tap_stride = Cpad; j.block_n = block_n;
+    } else {
+      w_off = p->walloc((size_t)C * 9 * C * p->esz);
+      j.layout = WL_ROWMAJOR; j.ld = 9 * C; j.tap_stride = C;
+    }
+    j.dst = (void*)w_off;
+    p->add_weight(wname + ".weight", (int64_t)C * C * 9, j);
+    const size_t b_off = p->add_copy(wname + ".bias", C);
+    lcm_plan* pl = p; const int n = N;
+    const int Hin = x->H, Win = x->W;
+    const double es = (double)p->esz;
+    push(name, pl->tc ? "conv3x3_tc" : "conv3x3_simt",
+         ((double)C * Hin * Win + (double)C * Ho * Wo) * N * es + 9.0 * C * C * es, 18.0 * N * Ho * Wo * C * C,
+         [=](const RunCtx& c, cudaStream_t st) {
+           if (pl->tc) {
+             GemmParams gp{};
+             gp.nseg = 1; gp.seg[0].A = c.a + x->off; gp.seg[0].K = 9 * C; gp.seg[0].ld = C; gp.seg[0].mode = XF_NONE;
+             gp.Ktot = 9 * C; gp.W = pl->wbase + w_off; gp.out = c.a + out->off;
+             gp.stats = (double*)(c.z + out->stats_off); gp.P = Ho * Wo; gp.M = (long long)n * Ho * Wo; gp.Nc = C;
+             ConvGeom cg{mode, Hin, Win, Ho, Wo, C, pl->wf(b_off)};
+             launch_gemm_tc(gp, cg, block_n, pl->num_sms, st);
+           } else {
+             launch_conv3x3_simt(c.a + x->off, pl->wbase + w_off, pl->wf(b_off), c.a + out->off,
+                                 (double*)(c.z + out->stats_off), n, Hin, Win, C, C, mode, pl->bf16, st);
+           }
+         });
+    p->release(x);
+    return out;
+  }
+};
+
+int build_plan(lcm_plan* p) {
+  const lcm_unet_config& c = p->cfg;
+  Builder b(p);
+  const int N = p->N, H = p->H, W = p->W;
+  std::vector<int> widths;
+  for (int i = 0; i < c.num_levels; ++i) widths.push_back(c.base_channels * c.channel_multipliers[i]);
+  auto has_attn = [&](int res) {
+    for (int i = 0; i < c.num_attention_resolutions; ++i)
+      if (c.attention_resolutions[i] == res) return true;
+    return false;
+  };
+  const int ted = c.time_embed_dim, base = c.base_channels;
+
+  // a2: time embedding (efficient_unet.py:550)
+  {
+    const size_t w1 = p->add_copy("time_mlp.1.weight", (int64_t)ted * base), b1 = p->add_copy("time_mlp.1.bias", ted);
+    const size_t w3 = p->add_copy("time_mlp.3.weight", (int64_t)ted * ted), b3 = p->add_copy("time_mlp.3.bias", ted);
+    p->silu_f_off = p->falloc((size_t)N * ted * sizeof(float));
+    b.push("time_mlp", "time_embed", 0, 0, [=](const RunCtx& cx, cudaStream_t st) {
+      launch_time_embed(cx.t_dev, cx.t_scalar, N, base, ted, p->wf(w1), p->wf(b1), p->wf(w3), p->wf(b3), nullptr,
+                        (float*)(cx.f + p->silu_f_off), st);
+    });
+  }
+  const size_t film_op_index = p->ops.size();   // filled in once all blocks are enumerated
+  b.push("film", "film", 0, 0, nullptr);
+
+  // a3: init conv fused with the conditioning concat (:553, low_light_diffusion.py:222)
+  TensorP h = p->new_tensor(widths[0], H, W, true, "init_conv");
+  {
+    const int Cin = c.in_channels, Co = widths[0];
+    const size_t w_off = p->walloc((size_t)9 * Cin * Co * sizeof(float));
+    PackJob j{}; j.kind = PACK_CONV3_KN; j.dst = (void*)w_off; j.R = Co; j.Ci = Cin;
+    p->add_weight("init_conv.weight", (int64_t)Co * Cin * 9, j);
+    const size_t b_off = p->add_copy("init_conv.bias", Co);
+    TensorP out = h;
+    b.push("init_conv", "init_conv", (double)N * H * W * (Cin * 4.0 + Co * (double)p->esz), 18.0 * N * H * W * Cin * Co,
+           [=](const RunCtx& cx, cudaStream_t st) {
+             launch_init_conv(cx.xa, cx.ca, cx.sa, cx.xb, cx.cb, cx.sb, p->wf(w_off), p->wf(b_off), cx.a + out->off,
+                              (double*)(cx.z + out->stats_off), N, H, W, Co, p->bf16, st);
+           });
+  }
+
+  auto run_level = [&](const std::string& prefix, int nblocks, int res, View x, int Co) -> TensorP {
+    int idx = 0;
+    TensorP cur;
+    for (int i = 0; i < nblocks; ++i) {
+      cur = b.block(prefix + "." + std::to_string(idx++), x, Co);
+      if (has_attn(res)) cur = b.attention(prefix + "." + std::to_string(idx++), cur);
+      x = View::of(cur);
+    }
+    return cur;
+  };
+
+  // encoder (:558-570); the level output is kept for the decoder (refs+1)
+  std::vector<TensorP> skips;
+  int res = c.image_size;
+  for (int li = 0; li < c.num_levels; ++li) {
+    h = run_level("encoder_blocks." + std::to_string(li), c.num_res_blocks, res, View::of(h), widths[li]);
+    h->refs++;
+    skips.push_back(h);
+    if (li < c.num_levels - 1) {
+      const std::string nm = "downsamplers." + std::to_string(li);
+      h = b.conv3(nm, nm + ".down", h, CONV_S2);
+      res /= 2;
+    }
+  }
+  // middle (:573-575)
+  h = b.block("mid_block1", View::of(h), widths.back());
+  h = b.attention("mid_attn", h);
+  h = b.block("mid_block2", View::of(h), widths.back());
+  // decoder (:580-597)
+  for (int li = 0; li < c.num_levels; ++li) {
+    const int Co = widths[c.num_levels - 1 - li];
+    if (li > 0) {
+      const std::string nm = "upsamplers." + std::to_string(li - 1);
+      h = b.conv3(nm, nm + ".conv", h, CONV_UP2);
+      res *= 2;
+    }
+    View x;
+    x.part[0] = h; x.part[1] = skips.back(); x.n = 2;
+    skips.pop_back();
+    h = run_level("decoder_blocks." + std::to_string(li), c.num_res_blocks + 1, res, x, Co);
+  }
+  // a8 + a11: final norm + SiLU + conv, LCM step fused (:600-602, lcm_scheduler.py:214-242)
+  {
+    const size_t coef = b.gn_coef("final_norm", View::of(h), "final_norm", -1);
+    const int Ci = widths[0], Co = c.out_channels;
+    const size_t w_off = p->walloc((size_t)9 * Ci * Co * sizeof(float));
+    PackJob j{}; j.kind = PACK_CONV3_KN; j.dst = (void*)w_off; j.R = Co; j.Ci = Ci;
+    p->add_weight("final_conv.weight", (int64_t)Co * Ci * 9, j);
+    const size_t b_off = p->add_copy("final_conv.bias", Co);
+    TensorP in = h;
+    b.push("final_conv", "final_conv", (double)N * H * W * (Ci * (double)p->esz + Co * 4.0 * 3), 18.0 * N * H * W * Ci * Co,
+           [=](const RunCtx& cx, cudaStream_t st) {
+             launch_final_conv(cx.a + in->off, (const float2*)(cx.f + coef), p->wf(w_off), p->wf(b_off), cx.eps, cx.step,
+                               N, H, W, Ci, Co, p->bf16, st);
+           });
+  }
+  // a4.3: one fused GEMV over all blocks' time_mlp.1 (:189-192,215)
+  {
+    const int rows = p->film_rows;
+    const size_t fw = p->walloc((size_t)rows * ted * sizeof(float)), fb = p->walloc((size_t)rows * sizeof(float));
+    p->film_f_off = p->falloc((size_t)N * rows * sizeof(float));
+    for (auto& blk : b.film_blocks) {
+      PackJob jw{}; jw.kind = PACK_COPY; jw.dst = (void*)(fw + (size_t)blk.row0 * ted * sizeof(float)); jw.R = 1; jw.Cc = blk.rows * ted;
+      p->add_weight(blk.wname + ".weight", (int64_t)blk.rows * ted, jw);
+      PackJob jb{}; jb.kind = PACK_COPY; jb.dst = (void*)(fb + (size_t)blk.row0 * sizeof(float)); jb.R = 1; jb.Cc = blk.rows;
+      p->add_weight(blk.wname + ".bias", blk.rows, jb);
+    }
+    Op& f = p->ops[film_op_index];
+    f.bytes = (double)rows * ted * 4; f.flops = 2.0 * N * rows * ted;
+    p->total_bytes += f.bytes; p->total_flops += f.flops;
+    f.run = [=](const RunCtx& cx, cudaStream_t st) {
+      launch_film((const float*)(cx.f + p->silu_f_off), p->wf(fw), p->wf(fb), (float*)(cx.f + p->film_f_off), N, rows, ted, st);
+    };
+  }
+  return 0;
+}
+
+int check_ready(const lcm_plan* p) {
+  for (auto& kv : p->weights)
+    if (!kv.second.set) return fail(LCM_ERR_MISSING_WEIGHT, "weight '%s' has not been set", kv.first.c_str());
+  return 0;
+}
+
+RunCtx make_ctx(const lcm_plan* p, void* workspace) {
+  RunCtx c{};
+  c.z = (char*)workspace;
+  c.f = c.z + align_up(p->z_bytes, 1024);
+  c.a = c.f + align_up(p->f_bytes, 1024);
+  return c;
+}
+
+int run_forward(lcm_plan* p, const RunCtx& c, cudaStream_t st, lcm_op_profile* rec, int cap) {
+  CUDA_TRY(cudaMemsetAsync(c.z, 0, p->z_bytes, st));
+  std::vector<cudaEvent_t> ev;
+  if (rec) {
+    ev.resize(p->ops.size() + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+  }
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    p->ops[i].run(c, st);
+    if (rec) CUDA_TRY(cudaEventRecord(ev[i + 1], st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (rec) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < p->ops.size() && (int)i < cap; ++i) {
+      lcm_op_profile& r = rec[i];
+      memset(&r, 0, sizeof(r));
+      snprintf(r.name, sizeof(r.name), "%s", p->ops[i].name.c_str());
+      snprintf(r.kernel, sizeof(r.kernel), "%s", p->ops[i].kernel.c_str());
+      cudaEventElapsedTime(&r.ms, ev[i], ev[i + 1]);
+      r.bytes = p->ops[i].bytes; r.flops = p->ops[i].flops;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
+int fill_inputs(lcm_plan* plan, RunCtx& c, const float* xa, int ca, int64_t sa, const float* xb, int cb, int64_t sb) {
+  if (!xa || ca < 1 || cb < 0 || ca + cb != plan->cfg.in_channels || (cb > 0 && !xb))
+    return fail(LCM_ERR_INVALID, "input channels %d+%d do not match in_channels=%d", ca, cb, plan->cfg.in_channels);
+  c.xa = xa; c.ca = ca; c.sa = sa; c.xb = xb; c.cb = cb; c.sb = sb;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* lcm_last_error(void) { return g_err.c_str(); }
+int lcm_version(void) { return 1; }
+
+int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width, int precision, uint32_t flags,
+                    int device, lcm_plan** out) {
+  if (!cfg || !out) return fail(LCM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (batch < 1 || height < 1 || width < 1) return fail(LCM_ERR_INVALID, "bad batch/size");
+  if (cfg->num_levels < 1 || cfg->num_levels > LCM_MAX_LEVELS) return fail(LCM_ERR_INVALID, "bad num_levels");
+  const int div = 1 << (cfg->num_levels - 1);
+  if (height % div || width % div) return fail(LCM_ERR_INVALID, "height/width must be divisible by %d", div);
+  if (precision != LCM_PREC_FP32 && precision != LCM_PREC_BF16) return fail(LCM_ERR_INVALID, "Unknown precision: %d", precision);
+  if (cfg->out_channels < 1 || cfg->out_channels > 4) return fail(LCM_ERR_INVALID, "out_channels must be 1..4");
+  if (cfg->base_channels % 16 || cfg->base_channels < 16 || cfg->base_channels > 64)
+    return fail(LCM_ERR_INVALID, "base_channels must be 16/32/48/64");
+  if (cfg->in_channels < 1 || cfg->in_channels > 8) return fail(LCM_ERR_INVALID, "in_channels must be 1..8");
+  if (cfg->time_embed_dim < 1 || cfg->time_embed_dim > 512) return fail(LCM_ERR_INVALID, "time_embed_dim must be 1..512");
+  if (cfg->expansion_ratio < 1 || cfg->num_res_blocks < 1 || cfg->num_attention_heads < 1)
+    return fail(LCM_ERR_INVALID, "bad block configuration");
+  std::unique_ptr<lcm_plan> p(new lcm_plan());
+  p->cfg = *cfg; p->N = batch; p->H = height; p->W = width; p->prec = precision; p->device = device; p->flags = flags;
+  p->bf16 = precision == LCM_PREC_BF16;
+  p->tc = p->bf16 && !(flags & LCM_FLAG_SIMT_GEMM);
+  p->taps = (flags & LCM_FLAG_TAPS) != 0;
+  p->pool.reuse = !p->taps;
+  p->esz = p->bf16 ? 2 : 4;
+  // GroupNorm validity: the reference raises ValueError at construction when C % min(32,C) != 0 (F1)
+  {
+    std::vector<int> widths, cs;
+    for (int i = 0; i < cfg->num_levels; ++i) widths.push_back(cfg->base_channels * cfg->channel_multipliers[i]);
+    int ci = widths[0];
+    for (int i = 0; i < cfg->num_levels; ++i) { cs.push_back(ci); cs.push_back(widths[i]); ci = widths[i]; }
+    for (int i = 0; i < cfg->num_levels; ++i) { int co = widths[cfg->num_levels - 1 - i]; cs.push_back(ci + co); cs.push_back(co); ci = co; }
+    for (int C : cs) {
+      if (C % 16) return fail(LCM_ERR_INVALID, "channel count %d is not a multiple of 16", C);
+      if (p->groups(C) < 0 || p->groups(C * cfg->expansion_ratio) < 0)
+        return fail(LCM_ERR_INVALID, "num_channels (%d) must be divisible by num_groups (32)", p->groups(C) < 0 ? C : C * cfg->expansion_ratio);
+      if ((C * cfg->expansion_ratio) % 32) return fail(LCM_ERR_INVALID, "hidden width %d is not a multiple of 32", C * cfg->expansion_ratio);
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(LCM_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(LCM_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  p->num_sms = prop.multiProcessorCount;
+
+  int rc = build_plan(p.get());
+  if (rc) return rc;
+  p->ws_bytes = align_up(p->z_bytes, 1024) + align_up(p->f_bytes, 1024) + align_up(p->pool.top, 1024);
+  CUDA_TRY(cudaMalloc((void**)&p->wbase, p->wbytes ? p->wbytes : 256));
+  CUDA_TRY(cudaMemset(p->wbase, 0, p->wbytes ? p->wbytes : 256));
+  for (PackJob j : p->identity_jobs) {   // residual identities of the project GEMMs
+    j.dst = p->wbase + (size_t)j.dst;
+    launch_pack(j, nullptr, 0);
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = p.release();
+  return 0;
+}
+
+void lcm_plan_destroy(lcm_plan* plan) {
+  if (!plan) return;
+  if (plan->wbase) cudaFree(plan->wbase);
+  delete plan;
+}
+
+size_t lcm_plan_workspace_bytes(const lcm_plan* plan) { return plan ? plan->ws_bytes : 0; }
+int lcm_plan_num_weights(const lcm_plan* plan) { return plan ? (int)plan->weight_order.size() : 0; }
+
+int lcm_plan_weight_info(const lcm_plan* plan, int index, const char** name, int64_t* numel) {
+  if (!plan || index < 0 || index >= (int)plan->weight_order.size()) return fail(LCM_ERR_INVALID, "bad weight index");
+  const std::string& n = plan->weight_order[index];
+  if (name) *name = n.c_str();
+  if (numel) *numel = plan->weights.at(n).numel;
+  return 0;
+}
+
+int lcm_plan_set_weight(lcm_plan* plan, const char* name, const float* dev_values, int64_t numel, void* stream) {
+  if (!plan || !name || !dev_values) return fail(LCM_ERR_INVALID, "null argument");
+  auto it = plan->weights.find(name);
+  if (it == plan->weights.end()) return fail(LCM_ERR_UNKNOWN_WEIGHT, "unknown weight '%s'", name);
+  if (it->second.numel != numel)
+    return fail(LCM_ERR_INVALID, "weight '%s': expected %lld elements, got %lld", name, (long long)it->second.numel, (long long)numel);
+  for (PackJob j : it->second.jobs) {
+    j.dst = plan->wbase + (size_t)j.dst;
+    launch_pack(j, dev_values, (cudaStream_t)stream);
+  }
+  CUDA_TRY(cudaGetLastError());
+  it->second.set = true;
+  return 0;
+}
+
+int lcm_unet_forward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride, const float* xb_dev, int cb,
+                     int64_t xb_batch_stride, const int64_t* t_dev, float* eps_dev, void* workspace, void* stream) {
+  if (!plan || !t_dev || !eps_dev || !workspace) return fail(LCM_ERR_INVALID, "null argument");
+  int rc = check_ready(plan);
+  if (rc) return rc;
+  RunCtx c = make_ctx(plan, workspace);
+  rc = fill_inputs(plan, c, xa_dev, ca, xa_batch_stride, xb_dev, cb, xb_batch_stride);
+  if (rc) return rc;
+  c.t_dev = (const long long*)t_dev;
+  c.eps = eps_dev;
+  c.step.enabled = 0;
+  return run_forward(plan, c, (cudaStream_t)stream, nullptr, 0);
+}
+
+int lcm_plan_profile_forward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride, const float* xb_dev,
+                             int cb, int64_t xb_batch_stride, const int64_t* t_dev, float* eps_dev, void* workspace,
+                             void* stream, lcm_op_profile* records, int cap) {
+  if (!plan || !t_dev || !eps_dev || !workspace || !records) return fail(LCM_ERR_INVALID, "null argument");
+  int rc = check_ready(plan);
+  if (rc) return rc;
+  RunCtx c = make_ctx(plan, workspace);
+  rc = fill_inputs(plan, c, xa_dev, ca, xa_batch_stride, xb_dev, cb, xb_batch_stride);
+  if (rc) return rc;
+  c.t_dev = (const long long*)t_dev;
+  c.eps = eps_dev;
+  c.step.enabled = 0;
+  rc = run_forward(plan, c, (cudaStream_t)stream, records, cap);
+  return rc ? rc : (int)plan->ops.size();
+}
+
+int lcm_enhance(lcm_plan* plan, const float* cond_dev, float* latents_dev, const float* noises_dev, int steps,
+                const int64_t* timesteps, const float* coef, float* out_dev, float* trace_dev, void* workspace,
+                void* stream) {
+  if (!plan || !cond_dev || !latents_dev || !timesteps || !coef || !out_dev || !workspace)
+    return fail(LCM_ERR_INVALID, "null argument");
+  if (steps < 1) return fail(LCM_ERR_INVALID, "steps must be >= 1");
+  if (steps > 1 && !noises_dev) return fail(LCM_ERR_INVALID, "noises_dev is required for steps > 1");
+  if (plan->cfg.in_channels != 2 * plan->cfg.out_channels)
+    return fail(LCM_ERR_INVALID, "enhance needs concat conditioning: in_channels == 2*out_channels");
+  int rc = check_ready(plan);
+  if (rc) return rc;
+  const int C = plan->cfg.out_channels;
+  const long long per = (long long)C * plan->H * plan->W, all = per * plan->N;
+  RunCtx c = make_ctx(plan, workspace);
+  rc = fill_inputs(plan, c, latents_dev, C, per, cond_dev, C, per);
+  if (rc) return rc;
+  for (int i = 0; i < steps; ++i) {
+    const bool last = i == steps - 1;
+    c.t_dev = nullptr;
+    c.t_scalar = timesteps[i];
+    c.eps = nullptr;
+    c.step.enabled = 1;
+    c.step.noise = last ? nullptr : noises_dev + (long long)i * all;
+    c.step.latents = latents_dev;
+    c.step.clamped = last ? out_dev : nullptr;
+    c.step.trace = trace_dev ? trace_dev + (long long)i * all : nullptr;
+    c.step.sb_t = coef[4 * i + 0]; c.step.sa_t = coef[4 * i + 1]; c.step.sa_p = coef[4 * i + 2]; c.step.sb_p = coef[4 * i + 3];
+    rc = run_forward(plan, c, (cudaStream_t)stream, nullptr, 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int lcm_scheduler_step(const float* model_out_dev, const float* sample_dev, const float* noise_dev, float* prev_dev,
+                       float* x0_dev, int64_t numel, int prediction, float sqrt_beta_t, float sqrt_alpha_t,
+                       float sqrt_alpha_prev, float sqrt_beta_prev, void* stream) {
+  if (!model_out_dev || !sample_dev || !prev_dev) return fail(LCM_ERR_INVALID, "null argument");
+  if (prediction != 0 && prediction != 1) return fail(LCM_ERR_INVALID, "Unknown prediction type: %d", prediction);
+  launch_lcm_step(model_out_dev, sample_dev, noise_dev, prev_dev, x0_dev, numel, prediction, sqrt_beta_t, sqrt_alpha_t,
+                  sqrt_alpha_prev, sqrt_beta_prev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_dev, const float* abar_dev, float* out_dev,
+                      int batch, int64_t per_sample, int velocity, void* stream) {
+  if (!a_dev || !b_dev || !t_dev || !abar_dev || !out_dev) return fail(LCM_ERR_INVALID, "null argument");
+  launch_lcm_mix(a_dev, b_dev, (const long long*)t_dev, abar_dev, out_dev, batch, per_sample, velocity, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_plan_num_taps(const lcm_plan* plan) { return plan ? (int)plan->tap_order.size() : 0; }
+int lcm_plan_tap_info(const lcm_plan* plan, int index, const char** name, int* channels, int* height, int* width) {
+  if (!plan || index < 0 || index >= (int)plan->tap_order.size()) return fail(LCM_ERR_INVALID, "bad tap index");
+  const std::string& n = plan->tap_order[index];
+  const TensorP& t = plan->tap_map.at(n);
+  if (name) *name = n.c_str();
+  if (channels) *channels = t->C;
+  if (height) *height = t->H;
+  if (width) *width = t->W;
+  return 0;
+}
+int lcm_plan_read_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, void* workspace, void* stream) {
+  if (!plan || !name || !out_nchw_dev || !workspace) return fail(LCM_ERR_INVALID, "null argument");
+  auto it = plan->tap_map.find(name);
+  if (it == plan->tap_map.end()) return fail(LCM_ERR_INVALID, "unknown tap '%s' (plan created without LCM_FLAG_TAPS?)", name);
+  RunCtx c = make_ctx(plan, workspace);
+  const TensorP& t = it->second;
+  launch_nhwc_to_nchw(c.a + t->off, out_nchw_dev, plan->N, t->H, t->W, t->C, plan->bf16, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_plan_launches_per_forward(const lcm_plan* plan) { return plan ? (int)plan->ops.size() + 1 : 0; }
+double lcm_plan_algorithmic_bytes(const lcm_plan* plan) { return plan ? plan->total_bytes : 0; }
+double lcm_plan_algorithmic_flops(const lcm_plan* plan) { return plan ? plan->total_flops : 0; }
+
+}  // extern "C"

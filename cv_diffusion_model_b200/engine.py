@@ -1,0 +1,238 @@
+"""Host side of the native path: plan handles, weight upload and the calls behind the reference API.
+
+PyTorch is plumbing here — it owns tensors, the caching allocator and the current stream; every
+FLOP of the hot path is executed by ``liblcmunet.so`` through the C ABI (include/lcm_unet.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native
+
+_PREC = {"fp32": native.PREC_FP32, "bf16": native.PREC_BF16}
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the B200 path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{what} must be float32 (got {t.dtype})")
+
+
+class Engine:
+    """One native plan = (weights of one EfficientUNet, batch, height, width, precision, device)."""
+
+    def __init__(self, unet, batch: int, height: int, width: int, precision: str = "bf16", simt_gemm: bool = False,
+                 taps: bool = False, device: Optional[torch.device] = None):
+        if precision not in _PREC:
+            raise ValueError(f"Unknown precision: {precision}")
+        self.lib = native.lib()
+        self.unet = unet
+        self.shape = (batch, height, width)
+        self.precision = precision
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("the B200 path has no CPU fallback")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        cfg = native.config_struct(unet.config, unet.groupnorm)
+        flags = (native.FLAG_SIMT_GEMM if simt_gemm else 0) | (native.FLAG_TAPS if taps else 0)
+        handle = C.c_void_p()
+        native.check(self.lib.lcm_plan_create(C.byref(cfg), batch, height, width, _PREC[precision], flags, dev_index,
+                                              C.byref(handle)))
+        self.handle = handle
+        self.workspace = torch.empty(self.lib.lcm_plan_workspace_bytes(handle), dtype=torch.uint8, device=self.device)
+        self._weight_version = None
+        self.upload_weights()
+
+    # ---- weights --------------------------------------------------------------------------------
+    def _version(self) -> Tuple[int, ...]:
+        return tuple(p._version for p in self.unet.parameters())
+
+    def upload_weights(self) -> None:
+        sd = self.unet.state_dict()
+        n = self.lib.lcm_plan_num_weights(self.handle)
+        name, numel = C.c_char_p(), C.c_int64()
+        expected = set()
+        with torch.cuda.device(self.device):
+            for i in range(n):
+                native.check(self.lib.lcm_plan_weight_info(self.handle, i, C.byref(name), C.byref(numel)))
+                key = name.value.decode()
+                expected.add(key)
+                if key not in sd:
+                    raise ValueError(f"state_dict has no entry '{key}'")
+                w = sd[key].detach().to(device=self.device, dtype=torch.float32).contiguous()
+                native.check(self.lib.lcm_plan_set_weight(self.handle, key.encode(), C.c_void_p(w.data_ptr()), w.numel(),
+                                                          _stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+        extra = set(sd.keys()) - expected
+        if extra:
+            raise ValueError(f"state_dict entries unknown to the native plan: {sorted(extra)[:4]}")
+        self._weight_version = self._version()
+
+    def refresh(self) -> None:
+        if self._weight_version != self._version():
+            self.upload_weights()
+
+    # ---- EfficientUNet.forward --------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
+        b, h, w = self.shape
+        _require_cuda(x, "x")
+        if tuple(x.shape) != (b, self.unet.config.in_channels, h, w):
+            raise ValueError(f"x has shape {tuple(x.shape)}, plan expects {(b, self.unet.config.in_channels, h, w)}")
+        x = x.contiguous()
+        t = timestep.to(device=x.device, dtype=torch.long).contiguous()
+        if t.numel() != b:
+            raise ValueError("timestep must have one entry per sample")
+        self.refresh()
+        eps = torch.empty(b, self.unet.config.out_channels, h, w, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.lcm_unet_forward(self.handle, C.c_void_p(x.data_ptr()), x.shape[1], x.stride(0), None, 0, 0,
+                                                   C.c_void_p(t.data_ptr()), C.c_void_p(eps.data_ptr()),
+                                                   C.c_void_p(self.workspace.data_ptr()), _stream_ptr()))
+        return eps
+
+    # ---- LowLightDiffusion.enhance loop -------------------------------------------------------------
+    def enhance(self, cond: torch.Tensor, latents: torch.Tensor, noises: Optional[torch.Tensor],
+                timesteps: Sequence[int], coefs: Sequence[Sequence[float]], trace: bool = False):
+        """`latents` is updated in place and holds the pre-clamp result afterwards."""
+        b, h, w = self.shape
+        for t_, nm in ((cond, "low_light"), (latents, "latents")):
+            _require_cuda(t_, nm)
+            if tuple(t_.shape) != (b, 3, h, w) or not t_.is_contiguous():
+                raise ValueError(f"{nm} must be a contiguous [{b},3,{h},{w}] tensor, got {tuple(t_.shape)}")
+        steps = len(timesteps)
+        if steps > 1:
+            _require_cuda(noises, "noises")
+            if tuple(noises.shape) != (steps - 1, b, 3, h, w) or not noises.is_contiguous():
+                raise ValueError(f"noises must be [{steps - 1},{b},3,{h},{w}]")
+        self.refresh()
+        out = torch.empty_like(latents)
+        tr = torch.empty(steps, b, 3, h, w, dtype=torch.float32, device=latents.device) if trace else None
+        ts = (C.c_int64 * steps)(*[int(t) for t in timesteps])
+        flat = [float(v) for row in coefs for v in row[:4]]
+        cf = (C.c_float * (4 * steps))(*flat)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.lcm_enhance(self.handle, C.c_void_p(cond.data_ptr()), C.c_void_p(latents.data_ptr()),
+                                              C.c_void_p(noises.data_ptr()) if steps > 1 else None, steps, ts, cf,
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(tr.data_ptr()) if trace else None,
+                                              C.c_void_p(self.workspace.data_ptr()), _stream_ptr()))
+        return (out, tr) if trace else out
+
+    # ---- introspection ----------------------------------------------------------------------------------
+    def taps(self) -> Dict[str, Tuple[int, int, int]]:
+        out = {}
+        name, c, h, w = C.c_char_p(), C.c_int(), C.c_int(), C.c_int()
+        for i in range(self.lib.lcm_plan_num_taps(self.handle)):
+            native.check(self.lib.lcm_plan_tap_info(self.handle, i, C.byref(name), C.byref(c), C.byref(h), C.byref(w)))
+            out[name.value.decode()] = (c.value, h.value, w.value)
+        return out
+
+    def read_tap(self, name: str) -> torch.Tensor:
+        c, h, w = self.taps()[name]
+        out = torch.empty(self.shape[0], c, h, w, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.lcm_plan_read_tap(self.handle, name.encode(), C.c_void_p(out.data_ptr()),
+                                                    C.c_void_p(self.workspace.data_ptr()), _stream_ptr()))
+        return out
+
+    @property
+    def launches_per_forward(self) -> int:
+        return self.lib.lcm_plan_launches_per_forward(self.handle)
+
+    @property
+    def algorithmic_bytes(self) -> float:
+        return self.lib.lcm_plan_algorithmic_bytes(self.handle)
+
+    @property
+    def algorithmic_flops(self) -> float:
+        return self.lib.lcm_plan_algorithmic_flops(self.handle)
+
+    def profile(self, x: torch.Tensor, timestep: torch.Tensor) -> List[dict]:
+        """Per-op device times of one forward (CUDA events around every launch)."""
+        b, h, w = self.shape
+        x = x.contiguous()
+        t = timestep.to(device=x.device, dtype=torch.long).contiguous()
+        eps = torch.empty(b, self.unet.config.out_channels, h, w, dtype=torch.float32, device=x.device)
+        cap = self.launches_per_forward
+        recs = (native.OpProfileC * cap)()
+        with torch.cuda.device(self.device):
+            n = native.check(self.lib.lcm_plan_profile_forward(
+                self.handle, C.c_void_p(x.data_ptr()), x.shape[1], x.stride(0), None, 0, 0, C.c_void_p(t.data_ptr()),
+                C.c_void_p(eps.data_ptr()), C.c_void_p(self.workspace.data_ptr()), _stream_ptr(), recs, cap))
+        return [dict(name=recs[i].name.decode(), kernel=recs[i].kernel.decode(), ms=recs[i].ms, bytes=recs[i].bytes,
+                     flops=recs[i].flops) for i in range(min(n, cap))]
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.lcm_plan_destroy(self.handle)
+            self.handle = None
+        self.workspace = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def get_engine(unet, batch: int, height: int, width: int, device, precision: Optional[str] = None, **kw) -> Engine:
+    precision = precision or unet.precision
+    dev = torch.device(device)
+    key = (batch, height, width, precision, dev.index if dev.index is not None else torch.cuda.current_device(),
+           tuple(sorted(kw.items())))
+    eng = unet._engines.get(key)
+    if eng is None:
+        eng = Engine(unet, batch, height, width, precision, device=dev, **kw)
+        unet._engines[key] = eng
+    return eng
+
+
+# ---- functions behind the reference surface -----------------------------------------------------------------
+def unet_forward(unet, x: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be [B, C, H, W]")
+    return get_engine(unet, x.shape[0], x.shape[2], x.shape[3], x.device).forward(x, timestep)
+
+
+def lcm_step(model_output: torch.Tensor, sample: torch.Tensor, noise: Optional[torch.Tensor], prediction_type: str,
+             sb_t: float, sa_t: float, sa_p: float, sb_p: float):
+    """LCMScheduler.step arithmetic (lcm_scheduler.py:214-242) as one kernel."""
+    for t_, nm in ((model_output, "model_output"), (sample, "sample")):
+        _require_cuda(t_, nm)
+    pred = {"epsilon": 0, "v_prediction": 1}.get(prediction_type)
+    if pred is None:
+        raise ValueError(f"Unknown prediction type: {prediction_type}")
+    e, s = model_output.contiguous(), sample.contiguous()
+    nz = noise.contiguous() if noise is not None else None
+    prev, x0 = torch.empty_like(s), torch.empty_like(s)
+    with torch.cuda.device(s.device):
+        native.check(native.lib().lcm_scheduler_step(
+            C.c_void_p(e.data_ptr()), C.c_void_p(s.data_ptr()), C.c_void_p(nz.data_ptr()) if nz is not None else None,
+            C.c_void_p(prev.data_ptr()), C.c_void_p(x0.data_ptr()), s.numel(), pred, sb_t, sa_t, sa_p, sb_p,
+            _stream_ptr()))
+    return prev, x0
+
+
+def lcm_mix(a: torch.Tensor, b: torch.Tensor, timesteps: torch.Tensor, alphas_cumprod: torch.Tensor,
+            velocity: bool) -> torch.Tensor:
+    """add_noise / get_velocity (lcm_scheduler.py:255-305)."""
+    _require_cuda(a, "samples")
+    _require_cuda(b, "noise")
+    a, b = a.contiguous(), b.contiguous()
+    t = timesteps.to(device=a.device, dtype=torch.long).contiguous()
+    abar = alphas_cumprod.to(device=a.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        native.check(native.lib().lcm_scheduler_mix(
+            C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(t.data_ptr()), C.c_void_p(abar.data_ptr()),
+            C.c_void_p(out.data_ptr()), a.shape[0], a.numel() // a.shape[0], 1 if velocity else 0, _stream_ptr()))
+    return out

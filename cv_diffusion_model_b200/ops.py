@@ -1,0 +1,90 @@
+"""Python wrappers of the single-kernel C entry points (unit parity tests, micro-benchmarks).
+
+Activations are NHWC tensors in the plan precision (torch.float32 or torch.bfloat16); weights are
+given in the reference's fp32 layouts.  ``impl=1`` selects the tcgen05 / tuned kernel (bf16 only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native
+from .engine import _stream_ptr
+
+NONE, AFFINE, AFFINE_RELU6, AFFINE_SILU = 0, 1, 2, 3
+
+
+def _prec(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return native.PREC_FP32
+    if t.dtype == torch.bfloat16:
+        return native.PREC_BF16
+    raise ValueError(f"unsupported activation dtype {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def gemm(segs: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], int]], weight: torch.Tensor, pixels_per_image: int,
+         impl: int = 0, want_stats: bool = True, repeat: int = 1, timing: bool = False):
+    """segs: [(A [M,K] activations, coef [images,K,2] fp32 or None, mode)], weight fp32 [Nc, sum K].
+    Returns (out [M,Nc], stats [images,Nc,2] float64 or None[, ms])."""
+    a0 = segs[0][0]
+    M, Nc = a0.shape[0], weight.shape[0]
+    images = M // pixels_per_image
+    arr = (native.GemmSegC * len(segs))()
+    keep = []
+    for i, (a, coef, mode) in enumerate(segs):
+        a = a.contiguous()
+        keep.append(a)
+        arr[i].A = a.data_ptr()
+        if coef is not None:
+            coef = coef.to(torch.float32).contiguous()
+            keep.append(coef)
+            arr[i].coef = coef.data_ptr()
+        else:
+            arr[i].coef = None
+        arr[i].K = a.shape[1]
+        arr[i].mode = mode
+    w = weight.to(torch.float32).contiguous()
+    out = torch.empty(M, Nc, dtype=a0.dtype, device=a0.device)
+    stats = torch.zeros(images, Nc, 2, dtype=torch.float64, device=a0.device) if want_stats else None
+    ms = C.c_float(0)
+    with torch.cuda.device(a0.device):
+        native.check(native.lib().lcm_op_gemm(arr, len(segs), _p(w), _p(out), _p(stats), M, pixels_per_image, Nc,
+                                              _prec(a0), impl, repeat, C.byref(ms) if timing else None, _stream_ptr()))
+    return (out, stats, ms.value) if timing else (out, stats)
+
+
+def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, mode: int, impl: int = 0, repeat: int = 1,
+            timing: bool = False):
+    """x NHWC [N,H,W,Ci]; weight fp32 [Co,Ci,3,3]; mode 0 s1, 1 s2, 2 bilinear-x2 + s1."""
+    n, h, w_, ci = x.shape
+    co = weight.shape[0]
+    ho, wo = (h // 2, w_ // 2) if mode == 1 else ((2 * h, 2 * w_) if mode == 2 else (h, w_))
+    x = x.contiguous()
+    wt, bs = weight.to(torch.float32).contiguous(), bias.to(torch.float32).contiguous()
+    out = torch.empty(n, ho, wo, co, dtype=x.dtype, device=x.device)
+    stats = torch.zeros(n, co, 2, dtype=torch.float64, device=x.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        native.check(native.lib().lcm_op_conv3x3(_p(x), _p(wt), _p(bs), _p(out), _p(stats), n, h, w_, ci, co, mode,
+                                                 _prec(x), impl, repeat, C.byref(ms) if timing else None, _stream_ptr()))
+    return (out, stats, ms.value) if timing else (out, stats)
+
+
+def dwconv(x: torch.Tensor, coef: torch.Tensor, weight: torch.Tensor, impl: int = 0, repeat: int = 1,
+           timing: bool = False):
+    """x NHWC [N,H,W,C]; coef fp32 [N,C,2]; weight fp32 [C,1,3,3].  Returns (out, pooled sums [N,C])."""
+    n, h, w_, c = x.shape
+    x, coef, wt = x.contiguous(), coef.to(torch.float32).contiguous(), weight.to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    pool = torch.zeros(n, c, dtype=torch.float32, device=x.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        native.check(native.lib().lcm_op_dwconv(_p(x), _p(coef), _p(wt), _p(out), _p(pool), n, h, w_, c, _prec(x), impl,
+                                                repeat, C.byref(ms) if timing else None, _stream_ptr()))
+    return (out, pool, ms.value) if timing else (out, pool)

@@ -1,0 +1,120 @@
+"""``LowLightDiffusion`` with the reference's public surface, running on the B200 library.
+
+Reference: src/models/low_light_diffusion.py:31-281.  ``enhance`` keeps the reference semantics —
+schedule from ``LCMScheduler.set_timesteps``, initial latents ``torch.randn(..., generator=generator)``,
+per-step noise from the *global* RNG (``randn_like``; the reference ignores ``generator`` there),
+final ``clamp(-1, 1)`` — but the whole 4-8 step loop is ONE native call: concat, UNet forward and
+scheduler step of every iteration are fused kernels on the caller's stream, with no host sync.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from .modules import EfficientUNet, create_efficient_unet
+from .scheduler import LCMScheduler
+
+
+@dataclass
+class LowLightDiffusionOutput:
+    enhanced: torch.Tensor
+    intermediate: Optional[list] = None
+
+
+class LowLightDiffusion(nn.Module):
+    def __init__(self, unet: Optional[EfficientUNet] = None, scheduler: Optional[LCMScheduler] = None,
+                 unet_variant: str = "small", image_size: int = 256, num_inference_steps: int = 4,
+                 condition_mode: str = "concat", groupnorm: str = "strict", precision: str = "bf16"):
+        super().__init__()
+        if condition_mode != "concat":
+            raise ValueError('only condition_mode="concat" is supported by the B200 path '
+                             '("add" is a non-default mode outside the hot path, SURVEY §2)')
+        self.image_size = image_size
+        self.num_inference_steps = num_inference_steps
+        self.condition_mode = condition_mode
+        self.unet = unet if unet is not None else create_efficient_unet(
+            variant=unet_variant, image_size=image_size, groupnorm=groupnorm, in_channels=6)
+        self.unet.precision = precision
+        self.scheduler = scheduler if scheduler is not None else LCMScheduler(
+            num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+            num_inference_steps=num_inference_steps, rescale_betas_zero_snr=True)
+
+    # ---- inference -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def enhance(self, low_light: torch.Tensor, num_inference_steps: Optional[int] = None,
+                generator: Optional[torch.Generator] = None, return_intermediate: bool = False,
+                latents: Optional[torch.Tensor] = None, noises: Optional[torch.Tensor] = None
+                ) -> Union[torch.Tensor, LowLightDiffusionOutput]:
+        """Reference signature plus two optional injection points (``latents`` [B,3,S,S], ``noises``
+        [steps-1,B,3,S,S]) used for parity testing and for sharding one global noise draw over GPUs."""
+        from .engine import get_engine
+        if not low_light.is_cuda:
+            raise RuntimeError("low_light must be a CUDA tensor: the B200 path has no CPU fallback")
+        if self.scheduler.config.prediction_type != "epsilon":
+            raise ValueError("the fused enhance loop implements epsilon prediction (the pipeline default)")
+        device, b = low_light.device, low_light.shape[0]
+        s = self.image_size
+        if tuple(low_light.shape) != (b, 3, s, s):
+            raise ValueError(f"low_light must be [B,3,{s},{s}] (image_size), got {tuple(low_light.shape)}")
+        steps = num_inference_steps if num_inference_steps is not None else self.num_inference_steps
+        self.scheduler.set_timesteps(steps, device=device)
+        ts = list(self.scheduler._host_timesteps)
+        if latents is None:
+            latents = torch.randn(b, 3, s, s, device=device, generator=generator)
+        else:
+            latents = latents.to(device=device, dtype=torch.float32).clone()
+        if noises is None and steps > 1:
+            noises = torch.stack([torch.randn_like(latents) for _ in range(steps - 1)])
+        coefs = [self.scheduler.step_coefficients(t) for t in ts]
+        eng = get_engine(self.unet, b, s, s, device)
+        low = low_light.to(torch.float32).contiguous()
+        res = eng.enhance(low, latents.contiguous(), noises, ts, coefs, trace=return_intermediate)
+        self.scheduler._step_index = steps
+        if return_intermediate:
+            out, tr = res
+            return LowLightDiffusionOutput(enhanced=out, intermediate=[tr[i] for i in range(steps)])
+        return res
+
+    def forward(self, low_light: torch.Tensor, normal_light: Optional[torch.Tensor] = None,
+                timesteps: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                return_dict: bool = True):
+        """Training-style forward (reference :115-171), inference-only here: noise prediction without autograd."""
+        if normal_light is None:
+            return self.enhance(low_light)
+        b, device = low_light.shape[0], low_light.device
+        if timesteps is None:
+            timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (b,), device=device)
+        if noise is None:
+            noise = torch.randn_like(normal_light)
+        noisy = self.scheduler.add_noise(normal_light, noise, timesteps)
+        with torch.no_grad():
+            noise_pred = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
+        if return_dict:
+            return {"noise_pred": noise_pred, "noise": noise, "timesteps": timesteps}
+        return noise_pred
+
+    def compute_loss(self, low_light: torch.Tensor, normal_light: torch.Tensor, loss_type: str = "mse") -> torch.Tensor:
+        """Loss value of the reference (:250-277).  NOTE: forward-only — the backward kernels of the
+        data-parallel training config are not part of this round ('out of scope')."""
+        import torch.nn.functional as F
+        if loss_type not in ("mse", "huber", "l1"):
+            raise ValueError(f"Unknown loss type: {loss_type}")
+        out = self.forward(low_light, normal_light)
+        fn = {"mse": F.mse_loss, "huber": F.huber_loss, "l1": F.l1_loss}[loss_type]
+        return fn(out["noise_pred"], out["noise"])
+
+    def get_model_size(self) -> Dict[str, float]:
+        return self.unet.get_memory_footprint()
+
+
+def normalize_image(image: torch.Tensor) -> torch.Tensor:
+    """[0,1] -> [-1,1] (reference :412-414)."""
+    return image * 2 - 1
+
+
+def denormalize_image(image: torch.Tensor) -> torch.Tensor:
+    """[-1,1] -> [0,1] (reference :417-419)."""
+    return (image + 1) / 2

@@ -1,0 +1,167 @@
+/*
+ * lcm_unet.h — C ABI of the B200 (sm_100a) LCM denoising hot path.
+ *
+ * The reference (zamazincode/cv-diffusion-model) is pure Python and has no FFI of its own; the
+ * drop-in boundary is its Python class surface.  Every entry point below replaces the
+ * *execution* of one reference function and is what a binding for that function would call.
+ * Reference citations are relative to /root/reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative lcm_status otherwise; the message of the
+ *     last failure on the calling thread is returned by lcm_last_error().
+ *   - all pointers named *dev* / workspace are DEVICE pointers owned by the caller (PyTorch in the
+ *     Python binding); the library owns only the opaque plan and its packed-weight copies.
+ *   - calls enqueue work on `stream` (a cudaStream_t passed as void*) and never synchronise.
+ *   - a plan is bound to (device, config, batch, height, width, precision); it is not thread-safe.
+ *   - images/latents cross the boundary as fp32 NCHW (the reference's tensors); activations inside
+ *     the plan are NHWC in the plan's precision.
+ *   - there is no CPU path: every call fails with LCM_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef LCM_UNET_H_
+#define LCM_UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCM_MAX_LEVELS 8
+
+typedef enum {
+  LCM_OK = 0,
+  LCM_ERR_INVALID = -1,     /* bad argument / unsupported configuration (Python: ValueError)  */
+  LCM_ERR_CUDA = -2,        /* CUDA runtime failure (Python: RuntimeError)                    */
+  LCM_ERR_UNKNOWN_WEIGHT = -3,
+  LCM_ERR_MISSING_WEIGHT = -4,
+  LCM_ERR_WORKSPACE = -5
+} lcm_status;
+
+typedef enum { LCM_PREC_FP32 = 0, LCM_PREC_BF16 = 1 } lcm_precision;
+
+/* plan flags */
+#define LCM_FLAG_SIMT_GEMM 1u     /* bf16 plans: use the CUDA-core GEMM/conv kernels instead of tcgen05 (cross-check) */
+#define LCM_FLAG_TAPS 2u          /* keep every intermediate alive (no buffer reuse) so lcm_plan_read_tap works */
+
+/* Mirrors EfficientUNetConfig (src/models/efficient_unet.py:24-57). */
+typedef struct {
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t base_channels;
+  int32_t num_levels;
+  int32_t channel_multipliers[LCM_MAX_LEVELS];
+  int32_t num_attention_resolutions;
+  int32_t attention_resolutions[LCM_MAX_LEVELS];
+  int32_t num_attention_heads;
+  int32_t num_res_blocks;
+  int32_t expansion_ratio;
+  float se_ratio;
+  int32_t time_embed_dim;
+  int32_t image_size;       /* config.image_size: decides where attention modules exist (:426,447) */
+  int32_t groupnorm_gcd;    /* 0: min(32,C) groups like the reference; 1: gcd(32,C) (tiny/base patch) */
+} lcm_unet_config;
+
+typedef struct lcm_plan lcm_plan;
+
+const char* lcm_last_error(void);
+int lcm_version(void);
+
+/* ---- plan life cycle ------------------------------------------------------------------------
+ * Replaces EfficientUNet.__init__'s role of fixing the op sequence (efficient_unet.py:403-530). */
+int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width, int precision,
+                    uint32_t flags, int device, lcm_plan** out);
+void lcm_plan_destroy(lcm_plan* plan);
+size_t lcm_plan_workspace_bytes(const lcm_plan* plan);
+
+/* Weights: state_dict entries without the "unet." prefix, fp32, device memory.
+ * Replaces model.load_state_dict() for the native path; packs into the plan's own layouts. */
+int lcm_plan_num_weights(const lcm_plan* plan);
+int lcm_plan_weight_info(const lcm_plan* plan, int index, const char** name, int64_t* numel);
+int lcm_plan_set_weight(lcm_plan* plan, const char* name, const float* dev_values, int64_t numel, void* stream);
+
+/* ---- EfficientUNet.forward (efficient_unet.py:532-606) ----------------------------------------
+ * x = cat([xa, xb], dim=1): xa has ca channels, xb has cb channels (cb may be 0), ca+cb == in_channels;
+ * each is fp32 NCHW with the given batch stride in elements.  t_dev: int64[batch].  eps_dev: fp32 NCHW. */
+int lcm_unet_forward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride,
+                     const float* xb_dev, int cb, int64_t xb_batch_stride, const int64_t* t_dev,
+                     float* eps_dev, void* workspace, void* stream);
+
+/* ---- LowLightDiffusion.enhance loop (low_light_diffusion.py:204-240) with LCMScheduler.step
+ * (lcm_scheduler.py:204-242) fused into the last kernel of every forward.
+ *   cond_dev      fp32 [B,3,H,W]   low-light image in [-1,1]
+ *   latents_dev   fp32 [B,3,H,W]   in: initial noise; out: pre-clamp final latents (updated in place)
+ *   noises_dev    fp32 [steps-1,B,3,H,W] per-step noise (the reference draws randn_like, :237)
+ *   timesteps     host int64[steps]  (e.g. 739,499,259,19)
+ *   coef          host float[steps*4]: sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), sqrt(1-abar_prev)
+ *   out_dev       fp32 [B,3,H,W]   clamp(latents,-1,1)
+ *   trace_dev     optional fp32 [steps,B,3,H,W]: post-step latents (return_intermediate), may be NULL */
+int lcm_enhance(lcm_plan* plan, const float* cond_dev, float* latents_dev, const float* noises_dev,
+                int steps, const int64_t* timesteps, const float* coef, float* out_dev, float* trace_dev,
+                void* workspace, void* stream);
+
+/* ---- LCMScheduler.step (lcm_scheduler.py:204-242), stand-alone.  prediction: 0 epsilon, 1 v_prediction.
+ * noise_dev == NULL means last step (prev = x0). */
+int lcm_scheduler_step(const float* model_out_dev, const float* sample_dev, const float* noise_dev,
+                       float* prev_dev, float* x0_dev, int64_t numel, int prediction, float sqrt_beta_t,
+                       float sqrt_alpha_t, float sqrt_alpha_prev, float sqrt_beta_prev, void* stream);
+
+/* ---- LCMScheduler.add_noise / get_velocity (lcm_scheduler.py:255-305).
+ * out = sa[t]*a + sb[t]*b (add_noise: a=x0,b=noise) or sa[t]*b - sb[t]*a (velocity: a=sample,b=noise). */
+int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_dev, const float* abar_dev,
+                      float* out_dev, int batch, int64_t per_sample, int velocity, void* stream);
+
+/* ---- debugging / unit parity --------------------------------------------------------------------
+ * Copy a named intermediate of the most recent forward (e.g. "encoder_blocks.0.0.expand",
+ * "mid_attn.out", see lcm_plan_tap_info) into fp32 NCHW.  Only valid when the plan was created with
+ * LCM_FLAG_TAPS (which disables buffer reuse). */
+int lcm_plan_num_taps(const lcm_plan* plan);
+int lcm_plan_tap_info(const lcm_plan* plan, int index, const char** name, int* channels, int* height, int* width);
+int lcm_plan_read_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, void* workspace, void* stream);
+
+/* Number of kernels the plan launches per UNet forward (for bench.py's gpu_launches). */
+int lcm_plan_launches_per_forward(const lcm_plan* plan);
+/* Algorithmic HBM bytes / FLOPs of one UNet forward under SURVEY §8(d) accounting. */
+double lcm_plan_algorithmic_bytes(const lcm_plan* plan);
+double lcm_plan_algorithmic_flops(const lcm_plan* plan);
+
+/* Per-kernel profile of one forward: runs the forward with a cudaEvent pair around every op and
+ * fills up to `cap` records.  Returns the number of ops. */
+typedef struct {
+  char name[96];
+  char kernel[32];
+  float ms;
+  double bytes;   /* algorithmic */
+  double flops;
+} lcm_op_profile;
+int lcm_plan_profile_forward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride,
+                             const float* xb_dev, int cb, int64_t xb_batch_stride, const int64_t* t_dev,
+                             float* eps_dev, void* workspace, void* stream, lcm_op_profile* records, int cap);
+
+/* ---- single-kernel entry points (unit parity tests, micro-benchmarks, ncu) --------------------------
+ * Raw device pointers; activations NHWC in `precision`; weights are given in the reference's fp32
+ * layouts and packed internally.  impl: 0 = CUDA-core kernel, 1 = tcgen05 / tuned kernel (bf16 only).
+ * The kernel is launched `repeat` times (>=1); when ms_out != NULL the average device time per launch
+ * (CUDA events on `stream`) is stored there. */
+typedef struct {
+  const void* A;      /* [M][K] activation slice source, channel stride == K                      */
+  const void* coef;   /* float2 [images][K] prologue coefficients for this segment, or NULL        */
+  int32_t K;
+  int32_t mode;       /* 0 none, 1 a*x+b, 2 relu6(a*x+b), 3 silu(a*x+b)                           */
+} lcm_gemm_seg;
+/* out[m][n] = sum_s sum_k xform_s(A_s[m][k]) * W[n][koff_s + k]   (1x1 convs, efficient_unet.py:174,186,199,265,267) */
+int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
+                int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream);
+/* dense 3x3 conv, mode 0: stride 1, 1: stride 2, 2: bilinear x2 then stride 1 (efficient_unet.py:367,380-384);
+ * w_dev [Co][Ci][3][3], bias [Co] */
+int lcm_op_conv3x3(const void* in_dev, const float* w_dev, const float* bias_dev, void* out_dev, double* stats_dev,
+                   int N, int Hin, int Win, int Ci, int Co, int mode, int precision, int impl, int repeat,
+                   float* ms_out, void* stream);
+/* depthwise 3x3 with relu6(a*x+b) prologue and pooled-sum epilogue (efficient_unet.py:212-223); w_dev [C][1][3][3] */
+int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, float* pool_dev, int N,
+                  int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCM_UNET_H_ */

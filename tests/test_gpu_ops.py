@@ -1,0 +1,134 @@
+"""-m gpu: single-kernel parity through the C ABI against plain torch fp32 ops on the same inputs."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _xform(x, coef, mode):
+    if coef is None or mode == 0:
+        return x
+    y = x * coef[..., 0] + coef[..., 1]
+    if mode == 2:
+        y = y.clamp(0, 6)
+    elif mode == 3:
+        y = F.silu(y)
+    return y
+
+
+def _gemm_ref(segs, weight, P):
+    cols = []
+    for a, coef, mode in segs:
+        M, K = a.shape
+        af = a.float().view(M // P, P, K)
+        cols.append(_xform(af, None if coef is None else coef[:, None], mode).reshape(M, K))
+    A = torch.cat(cols, dim=1)
+    return A @ weight.t()
+
+
+def _stats_ref(out, P):
+    o = out.double().view(out.shape[0] // P, P, out.shape[1])
+    return torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+
+
+GEMM_CASES = [  # (images, P, [K...], Nc, modes)
+    (2, 256, [32], 128, [2]),            # expand, level 0
+    (2, 256, [128, 32], 32, [1, 0]),     # project + identity/skip
+    (3, 64, [64, 32], 384, [2, 2]),      # concat expand (dec L3 b0)
+    (2, 64, [384, 64, 32], 32, [1, 0, 0]),
+    (1, 16, [512], 2048, [2]),           # deep level, N tiling
+    (2, 16, [2048, 512], 256, [1, 0]),
+    (2, 100, [48], 192, [2]),            # base-variant widths, ragged M
+    (1, 16, [16], 32, [2]),              # tiny
+    (2, 64, [256], 384, [1]),            # to_qkv
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("images,P,Ks,Nc,modes", GEMM_CASES)
+def test_gemm(images, P, Ks, Nc, modes, dtype, impl):
+    from cv_diffusion_model_b200 import ops
+    if impl == 1 and os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    if impl == 1 and dtype != torch.bfloat16:
+        pytest.skip("tcgen05 kernel is bf16 only")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M = images * P
+    segs = []
+    for K, mode in zip(Ks, modes):
+        a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+        coef = None
+        if mode != 0:
+            coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
+                                torch.randn(images, K, device="cuda", generator=g) * 0.3], dim=-1)
+        segs.append((a, coef, mode))
+    w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / (sum(Ks) ** 0.5)
+    if dtype == torch.bfloat16:
+        w = w.bfloat16().float()   # the kernels round weights to bf16; compare like with like
+    out, stats = ops.gemm(segs, w, P, impl=impl)
+    ref = _gemm_ref(segs, w, P)
+    if dtype == torch.float32:
+        assert (out - ref).abs().max().item() < 2e-4
+    else:
+        # bf16: the A operand is rounded to bf16 after the prologue (tensor-core input) and the output to bf16
+        assert (out.float() - ref).abs().max().item() < 0.06 * ref.abs().max().item() + 0.02
+        rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        assert rel < 8e-3, rel
+    sref = _stats_ref(out.float(), P)   # statistics are defined on the stored values
+    assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3), (stats - sref).abs().max()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(2, 16, 16, 32, 32), (1, 8, 12, 64, 64), (2, 8, 8, 128, 128), (1, 8, 8, 48, 48),
+                                        (1, 4, 4, 256, 256)])
+def test_conv3x3(N, H, W, Ci, Co, mode, dtype, impl):
+    from cv_diffusion_model_b200 import ops
+    if impl == 1 and os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    if impl == 1 and dtype != torch.bfloat16:
+        pytest.skip("tcgen05 kernel is bf16 only")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).to(dtype)
+    w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (9 * Ci) ** 0.5
+    b = torch.randn(Co, device="cuda", generator=g) * 0.1
+    if dtype == torch.bfloat16:
+        w = w.bfloat16().float()
+    out, stats = ops.conv3x3(x, w, b, mode, impl=impl)
+    xin = x.float().permute(0, 3, 1, 2)
+    if mode == 2:
+        xin = F.interpolate(xin, scale_factor=2, mode="bilinear", align_corners=False)
+    ref = F.conv2d(xin, w, b, stride=2 if mode == 1 else 1, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    tol = 2e-4 if dtype == torch.float32 else 0.03
+    assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    o = out.float().double().reshape(N, -1, Co)
+    sref = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+    assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 128), (1, 32, 32, 64), (2, 8, 8, 512), (1, 20, 12, 96), (3, 4, 4, 2048)])
+def test_dwconv(N, H, W, C, dtype, impl):
+    from cv_diffusion_model_b200 import ops
+    if impl == 1 and os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    if impl == 1 and dtype != torch.bfloat16:
+        pytest.skip("tuned depthwise kernel is bf16 only")
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).to(dtype)
+    coef = torch.stack([torch.rand(N, C, device="cuda", generator=g) + 0.5, torch.randn(N, C, device="cuda", generator=g)], dim=-1)
+    w = torch.randn(C, 1, 3, 3, device="cuda", generator=g) / 3
+    out, pool = ops.dwconv(x, coef, w, impl=impl)
+    a = (x.float() * coef[:, None, None, :, 0] + coef[:, None, None, :, 1]).clamp(0, 6).permute(0, 3, 1, 2)
+    ref = F.conv2d(a, w, padding=1, groups=C).permute(0, 2, 3, 1)
+    tol = 1e-4 if dtype == torch.float32 else 0.05
+    assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    pref = ref.sum(dim=(1, 2))
+    assert torch.allclose(pool, pref, rtol=2e-3 if dtype == torch.float32 else 2e-2, atol=0.05 * H * W ** 0.5)
