@@ -1,6 +1,589 @@
-// placeholder, replaced by the tcgen05 kernel
+// tcgen05 / TMEM / TMA GEMM for the 1x1 convolutions and (as implicit GEMM) the dense 3x3
+// convolutions of the EfficientUNet (efficient_unet.py:174,186,199,265,267 and :367,380-384).
+//
+//   out[m][n] = sum_k xform(A[m][k]) * W[n][k]  (+ bias[n]),   bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, warp-specialised (448 threads):
+//   warps 0-3   epilogue   : tcgen05.ld accumulator -> (+bias) -> bf16 -> padded smem staging -> coalesced
+//                            16-byte global stores + per-(image, channel) sum / sum-of-squares for the next
+//                            GroupNorm (kept in smem across tiles, flushed with fp64 atomics on image change)
+//   warp  4     MMA issuer : one thread issues tcgen05.mma (M=128, N=block_n, K=16) per 32-byte K step,
+//                            tcgen05.commit releases smem stages / publishes the accumulator
+//   warp  5     weights    : TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of pre-swizzled weight
+//                            chunks — resident in smem for the whole N tile when they fit, else streamed
+//   warps 6-13  A producers: two groups of 128 threads alternate over K chunks; each loads 16-byte vectors
+//                            of NHWC activations, applies the fused prologue (GroupNorm/FiLM affine + ReLU6,
+//                            SE gate, identity for residual / skip operands; for 3x3 convs: tap gather with
+//                            zero padding, stride 2, or bilinear x2 upsampling on load), and stores them into
+//                            the 128B-swizzled K-major layout the UMMA descriptor expects.
+// The A operand cannot come straight from TMA because ReLU6 sits between the normalisation and the
+// contraction; weights are static, so they are swizzled once at load time (PackJob / WL_UMMA).
+//
+// Tiles are ordered N-tile-major so that a CTA's contiguous tile range walks along M with a fixed weight
+// tile (weights stay in smem, statistics stay in one image for many tiles).
+#include <cstdio>
+
 #include "kernels.h"
+
 namespace lcm {
-int gemm_tc_pick_block_n(int Nc) { return Nc; }
-int launch_gemm_tc(const GemmParams&, const ConvGeom&, int, int, cudaStream_t) { return -1; }
+
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kEpiThreads = 128;
+constexpr int kProdThreads = 256;
+constexpr int kProdBase = 192;       // first producer thread
+constexpr uint32_t kStageA = 16384;  // 128 rows x 128 bytes
+constexpr int kMaxChunks = 160;
+constexpr uint32_t kSmemLimit = 232448;
+
+struct TcParams {
+  GemmSeg seg[LCM_MAX_SEGS];
+  int coef_base[LCM_MAX_SEGS];  // float2 index of the segment's coefficients in the smem table
+  int nseg, ncoef;
+  const bf16* W;
+  bf16* out;
+  double* stats;
+  const float* bias;
+  long long M, m_tiles;
+  int P, Nc, block_n, n_tiles, nchunks;
+  int resident, stages, fast;
+  int conv_mode, Hin, Win, Hout, Wout, Ci;
+  uint32_t stage_bytes, bres_off, stg_off, stg_stride, coef_off, misc_off;
+  uint32_t chunk[kMaxChunks];  // seg/tap | kvalid << 8 | c0 << 16
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("gemm_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void unpack8(uint4 u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// 16 bytes of activations through the prologue: coef = 8 x (a, b)
+__device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mode) {
+  float f[8];
+  unpack8(raw, f);
+  const float4* c4 = reinterpret_cast<const float4*>(ab);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 c = c4[j];
+    f[2 * j] = fmaf(c.x, f[2 * j], c.y);
+    f[2 * j + 1] = fmaf(c.z, f[2 * j + 1], c.w);
+  }
+  if (mode == XF_AFFINE_RELU6) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], 0.f), 6.f);
+  } else if (mode == XF_AFFINE_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+  }
+  return pack8(f);
+}
+
+__device__ __forceinline__ int div_upr(int u, int upr) {
+  return upr == 8 ? (u >> 3) : (upr == 4 ? (u >> 2) : (upr == 2 ? (u >> 1) : u / upr));
+}
+
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;   // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (sbase - sraw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // misc region: barriers, TMEM pointer, statistics accumulators, bias
+  uint8_t* misc = smem + p.misc_off;
+  const uint32_t bar0 = sbase + p.misc_off;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (34 + a); };
+  const uint32_t bres_bar = bar0 + 8u * 36;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * 40);
+  float* s_sum = reinterpret_cast<float*>(misc + 512);
+  float* s_sq = s_sum + 256;
+  float* s_bias = s_sq + 256;
+  float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_off);
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 128 + (p.resident ? 0 : 1));
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads); }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid < 256) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long total_tiles = p.m_tiles * p.n_tiles;
+  const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+  const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const uint32_t b_chunk_bytes = (uint32_t)p.block_n * 128u;
+
+  if (warp >= 6) {
+    // ================================ A producers ================================================
+    const int ptid = tid - kProdBase;
+    const int group = ptid >> 7, gt = ptid & 127;
+    int cur_img = -1;
+    long long gc = 0;  // chunk counter across tiles
+    for (long long t = t_begin; t < t_end; ++t) {
+      const long long m_tile = t % p.m_tiles;
+      const long long m0 = m_tile * 128;
+      if (p.ncoef > 0 && p.fast) {
+        const int img = (int)(m0 / p.P);
+        if (img != cur_img) {
+          bar_sync(1, kProdThreads);
+          for (int s = 0; s < p.nseg; ++s) {
+            if (p.seg[s].mode == XF_NONE) continue;
+            const float2* src = p.seg[s].coef + (size_t)img * p.seg[s].coef_ld + p.seg[s].coef_off;
+            for (int k = ptid; k < p.seg[s].K; k += kProdThreads) s_coef[p.coef_base[s] + k] = src[k];
+          }
+          bar_sync(1, kProdThreads);
+          cur_img = img;
+        }
+      }
+      // conv: this thread's output pixel
+      int cy = 0, cx = 0;
+      long long cn = 0;
+      const long long cm = m0 + gt;
+      if (p.conv_mode >= 0) {
+        cx = (int)(cm % p.Wout);
+        const long long q = cm / p.Wout;
+        cy = (int)(q % p.Hout);
+        cn = q / p.Hout;
+      }
+      for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
+        if ((gc & 1) != group) continue;
+        const int stage = (int)(gc % p.stages);
+        const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
+        const uint32_t cd = p.chunk[ci];
+        const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
+        const int upr = kvalid >> 3;
+        const uint32_t a_smem = sbase + stage * p.stage_bytes;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (p.conv_mode < 0) {
+          // ---- 1x1: 16-byte units interleaved over threads (8 lanes cover one 128-byte row) ----------
+          const GemmSeg& sg = p.seg[sidx];
+          const bf16* A = reinterpret_cast<const bf16*>(sg.A);
+          const int total = 128 * upr;
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int u = gt + i * 128;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (u < total) {
+              const int row = div_upr(u, upr), cu = u - row * upr;
+              const long long m = m0 + row;
+              if (m < p.M) v[i] = ldg_stream(A + m * sg.ld + c0 + cu * 8);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int u = gt + i * 128;
+            if (u < total) {
+              const int row = div_upr(u, upr), cu = u - row * upr;
+              uint4 o = v[i];
+              if (sg.mode != XF_NONE && m0 + row < p.M) {
+                if (p.fast) {
+                  o = apply_xform(o, s_coef + p.coef_base[sidx] + c0 + cu * 8, sg.mode);
+                } else {
+                  const int img = (int)((m0 + row) / p.P);
+                  __align__(16) float2 ab[8];
+                  const float2* src = sg.coef + (size_t)img * sg.coef_ld + sg.coef_off + c0 + cu * 8;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) ab[j] = src[j];
+                  o = apply_xform(o, ab, sg.mode);
+                }
+              }
+              sts128(a_smem + row * 128 + ((cu ^ (row & 7)) << 4), o);
+            }
+          }
+        } else {
+          // ---- 3x3 tap gather: one output pixel (row) per thread -----------------------------------
+          const int tap = sidx, ky = tap / 3, kx = tap - ky * 3;
+          const bf16* in = reinterpret_cast<const bf16*>(p.seg[0].A);
+          const uint32_t rbase = a_smem + gt * 128;
+          const int sw = gt & 7;
+          if (p.conv_mode == CONV_UP2) {
+            const int uy = cy + ky - 1, ux = cx + kx - 1;
+            const bool ok = cm < p.M && uy >= 0 && uy < p.Hout && ux >= 0 && ux < p.Wout;
+            if (ok) {
+              // F.interpolate(scale_factor=2, bilinear, align_corners=False): src = max(dst/2 - 0.25, 0)
+              const float sy = fmaxf(uy * 0.5f - 0.25f, 0.f), sx = fmaxf(ux * 0.5f - 0.25f, 0.f);
+              const int y0 = (int)sy, x0 = (int)sx;
+              const int y1 = min(y0 + 1, p.Hin - 1), x1 = min(x0 + 1, p.Win - 1);
+              const float ly = sy - y0, lx = sx - x0;
+              const bf16* b0 = in + ((cn * p.Hin + y0) * p.Win) * p.Ci + c0;
+              const bf16* b1 = in + ((cn * p.Hin + y1) * p.Win) * p.Ci + c0;
+              for (int cu = 0; cu < upr; ++cu) {
+                float a[8], b[8], c[8], d[8], o[8];
+                unpack8(ldg_cached(b0 + (long long)x0 * p.Ci + cu * 8), a);
+                unpack8(ldg_cached(b0 + (long long)x1 * p.Ci + cu * 8), b);
+                unpack8(ldg_cached(b1 + (long long)x0 * p.Ci + cu * 8), c);
+                unpack8(ldg_cached(b1 + (long long)x1 * p.Ci + cu * 8), d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+                sts128(rbase + ((cu ^ sw) << 4), pack8(o));
+              }
+            } else {
+              for (int cu = 0; cu < upr; ++cu) sts128(rbase + ((cu ^ sw) << 4), make_uint4(0u, 0u, 0u, 0u));
+            }
+          } else {
+            const int st = p.conv_mode == CONV_S2 ? 2 : 1;
+            const int iy = cy * st + ky - 1, ix = cx * st + kx - 1;
+            const bool ok = cm < p.M && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+            const bf16* src = in + ((cn * p.Hin + iy) * p.Win + ix) * p.Ci + c0;
+            uint4 v[8];
+#pragma unroll
+            for (int cu = 0; cu < 8; ++cu) v[cu] = (ok && cu < upr) ? ldg_cached(src + cu * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int cu = 0; cu < 8; ++cu)
+              if (cu < upr) sts128(rbase + ((cu ^ sw) << 4), v[cu]);
+          }
+        }
+        fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(stage));
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ weight loader (TMA bulk copies) =============================
+    if (lane == 0) {
+      int cur_nt = -1;
+      long long gc = 0, it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const int n_tile = (int)(t / p.m_tiles);
+        const bf16* wt = p.W + (size_t)n_tile * p.nchunks * p.block_n * 64;
+        if (p.resident) {
+          if (n_tile != cur_nt) {
+            if (it > 0) mbar_wait(tfull_bar((int)((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));  // old weights no longer read
+            mbar_expect_tx(bres_bar, (uint32_t)p.nchunks * b_chunk_bytes);
+            for (int ci = 0; ci < p.nchunks; ++ci)
+              bulk_g2s(sbase + p.bres_off + ci * b_chunk_bytes, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, bres_bar);
+            cur_nt = n_tile;
+          }
+        } else {
+          for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
+            const int stage = (int)(gc % p.stages);
+            const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), b_chunk_bytes);
+            bulk_g2s(sbase + stage * p.stage_bytes + kStageA, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, full_bar(stage));
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================================ MMA issuer ================================================
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = block_n, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
+    int cur_nt = -1;
+    uint32_t bres_phase = 0;
+    long long gc = 0, it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int n_tile = (int)(t / p.m_tiles);
+      const int acc = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      if (p.resident && n_tile != cur_nt) {
+        mbar_wait(bres_bar, bres_phase);
+        bres_phase ^= 1;
+        cur_nt = n_tile;
+      }
+      mbar_wait(tempty_bar(acc), aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
+        const int stage = (int)(gc % p.stages);
+        const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const int kvalid = (p.chunk[ci] >> 8) & 0xff;
+          const uint32_t a_addr = sbase + stage * p.stage_bytes;
+          const uint32_t b_addr = p.resident ? sbase + p.bres_off + ci * b_chunk_bytes : a_addr + kStageA;
+          const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+          for (int k = 0; k < (kvalid >> 4); ++k)
+            umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (ci == p.nchunks - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 0-3) ==========================================
+    const int upr = p.block_n >> 3;
+    const int RG = 128 / upr;
+    const bool active = tid < upr * RG;
+    const int cu = tid % upr, rg = tid / upr;
+    const uint32_t stg = sbase + p.stg_off;
+    int cur_img = -1, cur_nt = -1;
+    auto flush = [&]() {   // all statistics of (cur_img, cur_nt) -> global, fp64 atomics
+      if (tid < p.block_n) {
+        double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + tid) * 2;
+        atomicAdd(d, (double)s_sum[tid]);
+        atomicAdd(d + 1, (double)s_sq[tid]);
+        s_sum[tid] = 0.f;
+        s_sq[tid] = 0.f;
+      }
+    };
+    long long it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int n_tile = (int)(t / p.m_tiles);
+      const long long m0 = (t % p.m_tiles) * 128;
+      const int n0 = n_tile * p.block_n;
+      const int acc = (int)(it & 1);
+      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
+      const int img = (int)(m0 / p.P);
+      if (p.stats && p.fast && (img != cur_img || n_tile != cur_nt)) {
+        if (cur_img >= 0) flush();   // previous tile's trailing bar_sync ordered all smem atomics before this
+        cur_img = img;
+      }
+      if (p.bias && n_tile != cur_nt) {
+        for (int c = tid; c < p.block_n; c += kEpiThreads) s_bias[c] = p.bias[n0 + c];
+        bar_sync(2, kEpiThreads);
+      }
+      cur_nt = n_tile;
+
+      mbar_wait(tfull_bar(acc), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t my_row = stg + (uint32_t)tid * p.stg_stride;
+      for (int cb = 0; cb < p.block_n; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + cb, r);
+        tmem_wait_ld();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += s_bias[cb + j];
+        }
+        sts128(my_row + cb * 2, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+        sts128(my_row + cb * 2 + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));   // accumulator drained: the MMA warp may start the tile after next
+      bar_sync(2, kEpiThreads);       // staging complete
+      if (active) {
+        float cs[8], cq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+        for (int r = rg; r < 128; r += RG) {
+          const long long m = m0 + r;
+          if (m >= p.M) break;
+          const uint4 v = lds128(stg + (uint32_t)r * p.stg_stride + cu * 16);
+          *reinterpret_cast<uint4*>(p.out + m * p.Nc + n0 + cu * 8) = v;
+          if (p.stats) {
+            float f[8];
+            unpack8(v, f);
+            if (p.fast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+            } else {
+              double* d = p.stats + ((size_t)(m / p.P) * p.Nc + n0 + cu * 8) * 2;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { atomicAdd(d + 2 * j, (double)f[j]); atomicAdd(d + 2 * j + 1, (double)f[j] * f[j]); }
+            }
+          }
+        }
+        if (p.stats && p.fast) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cu * 8 + j], cs[j]); atomicAdd(&s_sq[cu * 8 + j], cq[j]); }
+        }
+      }
+      bar_sync(2, kEpiThreads);       // staging free, smem statistics complete
+    }
+    if (p.stats && p.fast && cur_img >= 0) flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+int gemm_tc_pick_block_n(int Nc) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (Nc % bn == 0) return bn;
+  return 0;
+}
+
+int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st) {
+  TcParams p{};
+  if (block_n < 16 || block_n > 256 || block_n % 16 || g.Nc % block_n) return -1;
+  p.nseg = g.nseg;
+  p.W = reinterpret_cast<const bf16*>(g.W);
+  p.out = reinterpret_cast<bf16*>(g.out);
+  p.stats = g.stats;
+  p.M = g.M; p.P = g.P; p.Nc = g.Nc; p.block_n = block_n;
+  p.n_tiles = g.Nc / block_n;
+  p.m_tiles = (g.M + 127) / 128;
+  p.fast = (g.P % 128 == 0) ? 1 : 0;
+  p.conv_mode = cg.mode;
+  int nch = 0, ncoef = 0;
+  if (cg.mode < 0) {
+    p.bias = nullptr;
+    for (int s = 0; s < g.nseg; ++s) {
+      p.seg[s] = g.seg[s];
+      if (g.seg[s].K % 16) return -1;
+      p.coef_base[s] = -1;
+      if (g.seg[s].mode != XF_NONE) { p.coef_base[s] = ncoef; ncoef += g.seg[s].K; }
+      for (int c0 = 0; c0 < g.seg[s].K; c0 += 64) {
+        if (nch >= kMaxChunks) return -1;
+        const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;
+        p.chunk[nch++] = (uint32_t)s | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
+      }
+    }
+  } else {
+    p.bias = cg.bias;
+    p.seg[0] = g.seg[0];
+    p.Hin = cg.Hin; p.Win = cg.Win; p.Hout = cg.Hout; p.Wout = cg.Wout; p.Ci = cg.Ci;
+    if (cg.Ci % 16) return -1;
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c0 = 0; c0 < cg.Ci; c0 += 64) {
+        if (nch >= kMaxChunks) return -1;
+        const int kv = cg.Ci - c0 < 64 ? cg.Ci - c0 : 64;
+        p.chunk[nch++] = (uint32_t)tap | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
+      }
+  }
+  p.nchunks = nch;
+  p.ncoef = ncoef;
+  // shared-memory layout
+  const uint32_t b_chunk = (uint32_t)block_n * 128u;
+  const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
+  const uint32_t stg_bytes = (128u * stg_stride + 1023u) & ~1023u;
+  const uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
+  const uint32_t misc_bytes = 4096;
+  const uint32_t fixed = stg_bytes + coef_bytes + misc_bytes + 1024;  // +1024: base alignment slack
+  const uint32_t bres = (uint32_t)nch * b_chunk;
+  p.resident = 0;
+  if (bres <= 98304 && fixed + bres + 3 * kStageA <= kSmemLimit) p.resident = 1;
+  p.stage_bytes = kStageA + (p.resident ? 0u : b_chunk);
+  const uint32_t avail = kSmemLimit - fixed - (p.resident ? bres : 0u);
+  int stages = (int)(avail / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -1;
+  p.stages = stages;
+  uint32_t off = (uint32_t)stages * p.stage_bytes;
+  p.bres_off = off; off += p.resident ? bres : 0u;
+  p.stg_off = off; off += stg_bytes;
+  p.stg_stride = stg_stride;
+  p.coef_off = off; off += coef_bytes;
+  p.misc_off = off; off += misc_bytes;
+  const uint32_t smem_bytes = off + 1024;
+  if (smem_bytes > kSmemLimit) return -1;
+  if (!g_attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) != cudaSuccess) return -2;
+    g_attr_set = true;
+  }
+  const long long tiles = p.m_tiles * p.n_tiles;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  gemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
+  return 0;
+}
+
+}  // namespace lcm

@@ -61,6 +61,7 @@ struct RunCtx {
   const long long* t_dev; long long t_scalar;
   float* eps;
   FinalStep step;
+  int* launch_err;   // set by ops whose launch wrapper rejects the shape
 };
 
 typedef std::function<void(const RunCtx&, cudaStream_t)> RunFn;
@@ -279,7 +280,7 @@ struct Builder {
       gp.P = out->H * out->W;
       gp.M = (long long)n * gp.P;
       gp.Nc = w.Nc;
-      if (pl->tc) { ConvGeom g{}; g.mode = -1; launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st); }
+      if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });
   }
@@ -442,7 +443,7 @@ struct Builder {
              gp.Ktot = 9 * C; gp.W = pl->wbase + w_off; gp.out = c.a + out->off;
              gp.stats = (double*)(c.z + out->stats_off); gp.P = Ho * Wo; gp.M = (long long)n * Ho * Wo; gp.Nc = C;
              ConvGeom cg{mode, Hin, Win, Ho, Wo, C, pl->wf(b_off)};
-             launch_gemm_tc(gp, cg, block_n, pl->num_sms, st);
+             if (launch_gemm_tc(gp, cg, block_n, pl->num_sms, st)) *c.launch_err = 1;
            } else {
              launch_conv3x3_simt(c.a + x->off, pl->wbase + w_off, pl->wf(b_off), c.a + out->off,
                                  (double*)(c.z + out->stats_off), n, Hin, Win, C, C, mode, pl->bf16, st);
@@ -586,7 +587,9 @@ RunCtx make_ctx(const lcm_plan* p, void* workspace) {
   return c;
 }
 
-int run_forward(lcm_plan* p, const RunCtx& c, cudaStream_t st, lcm_op_profile* rec, int cap) {
+int run_forward(lcm_plan* p, RunCtx& c, cudaStream_t st, lcm_op_profile* rec, int cap) {
+  int launch_err = 0;
+  c.launch_err = &launch_err;
   CUDA_TRY(cudaMemsetAsync(c.z, 0, p->z_bytes, st));
   std::vector<cudaEvent_t> ev;
   if (rec) {
@@ -599,6 +602,7 @@ int run_forward(lcm_plan* p, const RunCtx& c, cudaStream_t st, lcm_op_profile* r
     if (rec) CUDA_TRY(cudaEventRecord(ev[i + 1], st));
   }
   CUDA_TRY(cudaGetLastError());
+  if (launch_err) return fail(LCM_ERR_INVALID, "a tcgen05 kernel rejected its shape (unsupported configuration)");
   if (rec) {
     CUDA_TRY(cudaStreamSynchronize(st));
     for (size_t i = 0; i < p->ops.size() && (int)i < cap; ++i) {

@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    try:  # fp32 torch comparators on the GPU must be true fp32 (TF32 silently changes the reference)
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
