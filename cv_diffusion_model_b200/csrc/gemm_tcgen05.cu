@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   float* s_sum = reinterpret_cast<float*>(misc + 512);
   float* s_sq = s_sum + 256;
   float* s_bias = s_sq + 256;
+  float* s_psum = reinterpret_cast<float*>(misc + 4096);   // per-row-group partial column sums [RG][block_n]
+  float* s_psq = s_psum + 1024;
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_off);
 
   if (warp == 5 && lane == 0) {
@@ -415,12 +417,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t stg = sbase + p.stg_off;
     int cur_img = -1, cur_nt = -1;
     auto flush = [&]() {   // all statistics of (cur_img, cur_nt) -> global, fp64 atomics
-      if (tid < p.block_n) {
-        double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + tid) * 2;
-        atomicAdd(d, (double)s_sum[tid]);
-        atomicAdd(d + 1, (double)s_sq[tid]);
-        s_sum[tid] = 0.f;
-        s_sq[tid] = 0.f;
+      for (int c = tid; c < p.block_n; c += kEpiThreads) {
+        double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + c) * 2;
+        atomicAdd(d, (double)s_sum[c]);
+        atomicAdd(d + 1, (double)s_sq[c]);
+        s_sum[c] = 0.f;
+        s_sq[c] = 0.f;
       }
     };
     long long it = 0;
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int img = (int)(m0 / p.P);
       if (p.stats && p.fast && (img != cur_img || n_tile != cur_nt)) {
-        if (cur_img >= 0) flush();   // previous tile's trailing bar_sync ordered all smem atomics before this
+        if (cur_img >= 0) flush();   // columns are thread-owned: program order suffices
         cur_img = img;
       }
       if (p.bias && n_tile != cur_nt) {
@@ -484,12 +486,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
           }
         }
-        if (p.stats && p.fast) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cu * 8 + j], cs[j]); atomicAdd(&s_sq[cu * 8 + j], cq[j]); }
+        if (p.stats && p.fast) {   // partial sums of this thread's rows; folded (without atomics) after the barrier
+          float4* ps = reinterpret_cast<float4*>(s_psum + rg * p.block_n + cu * 8);
+          float4* pq = reinterpret_cast<float4*>(s_psq + rg * p.block_n + cu * 8);
+          ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+          pq[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); pq[1] = make_float4(cq[4], cq[5], cq[6], cq[7]);
         }
       }
-      bar_sync(2, kEpiThreads);       // staging free, smem statistics complete
+      bar_sync(2, kEpiThreads);       // staging free, partial statistics visible
+      if (p.stats && p.fast) {
+        for (int c = tid; c < p.block_n; c += kEpiThreads) {   // column c is owned by thread c % 128
+          float a = 0.f, b = 0.f;
+          for (int g = 0; g < RG; ++g) { a += s_psum[g * p.block_n + c]; b += s_psq[g * p.block_n + c]; }
+          s_sum[c] += a;
+          s_sq[c] += b;
+        }
+      }
     }
     if (p.stats && p.fast && cur_img >= 0) flush();
   }
@@ -557,7 +569,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
   const uint32_t stg_bytes = (128u * stg_stride + 1023u) & ~1023u;
   const uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
-  const uint32_t misc_bytes = 4096;
+  const uint32_t misc_bytes = 4096 + 8192;
   const uint32_t fixed = stg_bytes + coef_bytes + misc_bytes + 1024;  // +1024: base alignment slack
   const uint32_t bres = (uint32_t)nch * b_chunk;
   p.resident = 0;

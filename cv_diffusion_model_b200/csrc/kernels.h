@@ -28,12 +28,12 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 void launch_gemm_simt(const GemmParams& p, int bf16act, cudaStream_t st);
 
 // ---- a4.4 + SE pool: depthwise 3x3 with affine+ReLU6 prologue, pooled sums epilogue ---------------
-// in/out NHWC [N][H][W][C]; coef [N][C]; w [9][C] fp32; pool [N][C] fp32 sums (atomically accumulated).
-void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, float* pool, int N, int H, int W,
+// in/out NHWC [N][H][W][C]; coef [N][C]; w [9][C] fp32; pool [N][C] fp64 sums (atomically accumulated).
+void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                    int C, int bf16act, int fast, cudaStream_t st);
 
 // ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0) -------------------------------
-void launch_se_gate(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                     const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st);
 
 // ---- a3/a6/a7: dense 3x3 convs ------------------------------------------------------------------
@@ -59,9 +59,10 @@ void launch_final_conv(const void* in, const float2* coef, const float* w, const
                        const FinalStep& step, int N, int H, int W, int Ci, int Co, int bf16act, cudaStream_t st);
 
 // ---- a5: linear attention --------------------------------------------------------------------------
-// qkv NHWC [N][P][3*inner] (q | k | v, each heads*32); state [N][heads][32][33] fp32 (col 32 = k_sum), zeroed.
-void launch_attn_kv(const void* qkv, float* state, int N, int P, int heads, int bf16act, cudaStream_t st);
-void launch_attn_apply(const void* qkv, const float* state, void* out, int N, int P, int heads, int bf16act,
+// qkv NHWC [N][P][3*inner] (q | k | v, each heads*32); state [N][heads][32][33] fp64 (col 32 = k_sum), zeroed.
+// (fp64 accumulators make the atomic reductions order-insensitive to ~1e-16, i.e. run-to-run reproducible)
+void launch_attn_kv(const void* qkv, double* state, int N, int P, int heads, int bf16act, cudaStream_t st);
+void launch_attn_apply(const void* qkv, const double* state, void* out, int N, int P, int heads, int bf16act,
                        cudaStream_t st);
 // y = a*u + b + x (to_out GroupNorm + residual), channel statistics of y.
 void launch_affine_residual(const void* u, const float2* coef, const void* x, void* y, double* stats, int N, int P,

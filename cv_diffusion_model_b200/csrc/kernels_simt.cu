@@ -197,7 +197,7 @@ void launch_conv3x3_simt(const void* in, const void* Wt, const float* bias, void
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const float2* __restrict__ coef,
                                                      const float* __restrict__ w, T* __restrict__ out,
-                                                     float* __restrict__ pool, int H, int W, int C, int tilesX) {
+                                                     double* __restrict__ pool, int H, int W, int C, int tilesX) {
   constexpr int TS = 16, HS = TS + 2, CB = 32;
   __shared__ __align__(16) float tile[HS * HS * CB];
   __shared__ float s_pool[CB];
@@ -275,10 +275,10 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
     if ((tid & 31) < 4) atomicAdd(&s_pool[cg * 8 + j], v);
   }
   __syncthreads();
-  if (tid < CB) atomicAdd(&pool[(size_t)n * C + c0 + tid], s_pool[tid]);
+  if (tid < CB) atomicAdd(&pool[(size_t)n * C + c0 + tid], (double)s_pool[tid]);
 }
 
-void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, float* pool, int N, int H, int W,
+void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                    int C, int bf16act, int fast, cudaStream_t st) {
   (void)fast;
   const int tilesX = (W + 15) / 16, tilesY = (H + 15) / 16;
@@ -449,7 +449,7 @@ void launch_final_conv(const void* in, const float2* coef, const float* w, const
 __device__ __forceinline__ float phi(float x) { return x > 0.f ? x + 1.f : expf(x); }  // elu(x)+1
 
 template <typename T>
-__global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv, float* __restrict__ state, int P,
+__global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv, double* __restrict__ state, int P,
                                                       int heads) {
   __shared__ float ks[64][33], vs[64][33];
   const int n = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * 64;
@@ -476,23 +476,23 @@ __global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv,
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = fmaf(k, vs[pp][e0 + j], acc[j]);
   }
-  float* s = state + (((size_t)n * heads + h) * 32 + d) * 33;
+  double* s = state + (((size_t)n * heads + h) * 32 + d) * 33;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) atomicAdd(&s[e0 + j], acc[j]);
-  if (e0 == 0) atomicAdd(&s[32], ksum);
+  for (int j = 0; j < 4; ++j) atomicAdd(&s[e0 + j], (double)acc[j]);
+  if (e0 == 0) atomicAdd(&s[32], (double)ksum);
 }
 
 // Pass 2: out[p][e] = sum_d phi(q[p][d]) KV[d][e] / (sum_d phi(q[p][d]) ksum[d] + 1e-6)
 template <typename T>
-__global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ qkv, const float* __restrict__ state,
+__global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ qkv, const double* __restrict__ state,
                                                          T* __restrict__ out, int P, int heads) {
   __shared__ float kv[32][33];
   __shared__ float qs[64][33];
   const int n = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * 64;
   const int inner = heads * 32, ld = 3 * inner;
   const int tid = threadIdx.x;
-  const float* s = state + ((size_t)n * heads + h) * 32 * 33;
-  for (int i = tid; i < 32 * 33; i += 256) kv[i / 33][i % 33] = s[i];
+  const double* s = state + ((size_t)n * heads + h) * 32 * 33;
+  for (int i = tid; i < 32 * 33; i += 256) kv[i / 33][i % 33] = (float)s[i];
   for (int i = tid; i < 64 * 32; i += 256) {
     const int pp = i >> 5, d = i & 31, p = p0 + pp;
     qs[pp][d] = p < P ? phi(to_f<T>(qkv[((size_t)n * P + p) * ld + h * 32 + d])) : 0.f;
@@ -512,12 +512,12 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ q
   }
 }
 
-void launch_attn_kv(const void* qkv, float* state, int N, int P, int heads, int bf16act, cudaStream_t st) {
+void launch_attn_kv(const void* qkv, double* state, int N, int P, int heads, int bf16act, cudaStream_t st) {
   dim3 grid((P + 63) / 64, heads, N);
   if (bf16act) attn_kv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, state, P, heads);
   else attn_kv_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, state, P, heads);
 }
-void launch_attn_apply(const void* qkv, const float* state, void* out, int N, int P, int heads, int bf16act,
+void launch_attn_apply(const void* qkv, const double* state, void* out, int N, int P, int heads, int bf16act,
                        cudaStream_t st) {
   dim3 grid((P + 63) / 64, heads, N);
   if (bf16act) attn_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, state, (bf16*)out, P, heads);

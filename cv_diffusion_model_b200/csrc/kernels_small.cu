@@ -125,7 +125,7 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 // ------------------------------------------------------------------------------------------------
 // Squeeze-and-Excitation gate (efficient_unet.py:96-100).  One block per image; fc weights fp32
 // [SQ][C] and [C][SQ].  Output is a prologue coefficient (gate, 0) for the project GEMM.
-__global__ void se_gate_kernel(const float* __restrict__ pool, float inv_count, const float* __restrict__ w1,
+__global__ void se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2,
                                const float* __restrict__ b2, float2* __restrict__ coef, int C, int SQ) {
   extern __shared__ float sm[];
@@ -133,7 +133,7 @@ __global__ void se_gate_kernel(const float* __restrict__ pool, float inv_count, 
   float* hid = sm + C;    // [SQ]
   const int n = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(size_t)n * C + c] * inv_count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = (float)pool[(size_t)n * C + c] * inv_count;
   __syncthreads();
   for (int j = warp; j < SQ; j += nw) {
     float acc = 0.f;
@@ -152,7 +152,7 @@ __global__ void se_gate_kernel(const float* __restrict__ pool, float inv_count, 
   }
 }
 
-void launch_se_gate(const float* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                     const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st) {
   se_gate_kernel<<<N, 512, (C + SQ) * sizeof(float), st>>>(pool, inv_count, w1, b1, w2, b2, coef, C, SQ);
 }
@@ -165,9 +165,11 @@ __global__ void lcm_step_kernel(const float* __restrict__ eps, const float* __re
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
        i += (long long)gridDim.x * blockDim.x) {
     const float e = eps[i], x = sample[i];
-    float x0 = prediction == 0 ? (x - sb_t * e) / sa_t : sa_t * x - sb_t * e;
+    // same fp32 operation order as the reference (mul, sub, div / mul, mul, add), no FMA contraction
+    float x0 = prediction == 0 ? __fdiv_rn(__fsub_rn(x, __fmul_rn(sb_t, e)), sa_t)
+                               : __fsub_rn(__fmul_rn(sa_t, x), __fmul_rn(sb_t, e));
     if (x0o) x0o[i] = x0;
-    prev[i] = noise ? sa_p * x0 + sb_p * noise[i] : x0;
+    prev[i] = noise ? __fadd_rn(__fmul_rn(sa_p, x0), __fmul_rn(sb_p, noise[i])) : x0;
   }
 }
 

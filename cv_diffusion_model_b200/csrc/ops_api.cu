@@ -110,7 +110,7 @@ int lcm_op_conv3x3(const void* in_dev, const float* w_dev, const float* bias_dev
   return rc ? LCM_ERR_INVALID : rc2;
 }
 
-int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, float* pool_dev, int N,
+int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, double* pool_dev, int N,
                   int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream) {
   if (!in_dev || !coef_dev || !w_dev || !out_dev || !pool_dev || repeat < 1 || C % 32) return LCM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;

@@ -315,7 +315,7 @@ struct Builder {
     // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
     const size_t coef2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
     TensorP h2 = p->new_tensor(Ch, h, w, false, name + ".depthwise");
-    const size_t pool = p->zalloc((size_t)N * Ch * sizeof(float));
+    const size_t pool = p->zalloc((size_t)N * Ch * sizeof(double));
     const size_t dw_off = p->walloc((size_t)9 * Ch * sizeof(float));
     { PackJob j{}; j.kind = PACK_DW; j.dst = (void*)dw_off; j.R = Ch; p->add_weight(name + ".depthwise.weight", (int64_t)Ch * 9, j); }
     {
@@ -323,7 +323,7 @@ struct Builder {
       push(name + ".depthwise", "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
            [=](const RunCtx& c, cudaStream_t st) {
              launch_dwconv(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
-                           (float*)(c.z + pool), n, h, w, Ch, pl->bf16, pl->bf16 && pl->tc, st);
+                           (double*)(c.z + pool), n, h, w, Ch, pl->bf16, pl->bf16 && pl->tc, st);
            });
     }
     p->release(h1);
@@ -335,7 +335,7 @@ struct Builder {
       lcm_plan* pl = p; const int n = N;
       push(name + ".se", "se_gate", 2.0 * Ch * SQ * 4 + 8.0 * N * Ch, 4.0 * N * Ch * SQ,
            [=](const RunCtx& c, cudaStream_t st) {
-             launch_se_gate((const float*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2), pl->wf(b2),
+             launch_se_gate((const double*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2), pl->wf(b2),
                             (float2*)(c.f + gate), n, Ch, SQ, st);
            });
     }
@@ -376,15 +376,15 @@ struct Builder {
     p->add_weight(name + ".to_qkv.weight", (int64_t)3 * inner * C, mat_job(wq, 0, PACK_MAT, 3 * inner, C, C, 0));
     gemm(name + ".to_qkv", {{x, coefn, C, 0, XF_AFFINE}}, wq, qkv, false,
          (C + 3.0 * inner) * N * P * es + 3.0 * inner * C * es, 2.0 * N * P * C * 3 * inner);
-    const size_t state = p->zalloc((size_t)N * heads * 32 * 33 * sizeof(float));
+    const size_t state = p->zalloc((size_t)N * heads * 32 * 33 * sizeof(double));
     TensorP o = p->new_tensor(inner, h, w, false, name + ".attn");
     {
       lcm_plan* pl = p; const int n = N;
       push(name + ".kv", "attn_kv", 2.0 * inner * N * P * es, 2.0 * N * heads * P * 32 * 33,
-           [=](const RunCtx& c, cudaStream_t st) { launch_attn_kv(c.a + qkv->off, (float*)(c.z + state), n, P, heads, pl->bf16, st); });
+           [=](const RunCtx& c, cudaStream_t st) { launch_attn_kv(c.a + qkv->off, (double*)(c.z + state), n, P, heads, pl->bf16, st); });
       push(name + ".apply", "attn_apply", 2.0 * inner * N * P * es, 2.0 * N * heads * P * 32 * 33,
            [=](const RunCtx& c, cudaStream_t st) {
-             launch_attn_apply(c.a + qkv->off, (const float*)(c.z + state), c.a + o->off, n, P, heads, pl->bf16, st);
+             launch_attn_apply(c.a + qkv->off, (const double*)(c.z + state), c.a + o->off, n, P, heads, pl->bf16, st);
            });
     }
     p->release(qkv);

@@ -82,7 +82,7 @@ def dwconv(x: torch.Tensor, coef: torch.Tensor, weight: torch.Tensor, impl: int 
     n, h, w_, c = x.shape
     x, coef, wt = x.contiguous(), coef.to(torch.float32).contiguous(), weight.to(torch.float32).contiguous()
     out = torch.empty_like(x)
-    pool = torch.zeros(n, c, dtype=torch.float32, device=x.device)
+    pool = torch.zeros(n, c, dtype=torch.float64, device=x.device)
     ms = C.c_float(0)
     with torch.cuda.device(x.device):
         native.check(native.lib().lcm_op_dwconv(_p(x), _p(coef), _p(wt), _p(out), _p(pool), n, h, w_, c, _prec(x), impl,

@@ -44,6 +44,9 @@ GEMM_CASES = [  # (images, P, [K...], Nc, modes)
     (2, 100, [48], 192, [2]),            # base-variant widths, ragged M
     (1, 16, [16], 32, [2]),              # tiny
     (2, 64, [256], 384, [1]),            # to_qkv
+    (2, 1024, [64], 256, [2]),           # block_n 256 with per-image statistics kept in smem
+    (3, 256, [256, 64], 64, [1, 0]),
+    (2, 384, [96], 384, [2]),            # block_n 192, P multiple of 128
 ]
 
 
@@ -131,4 +134,4 @@ def test_dwconv(N, H, W, C, dtype, impl):
     tol = 1e-4 if dtype == torch.float32 else 0.05
     assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
     pref = ref.sum(dim=(1, 2))
-    assert torch.allclose(pool, pref, rtol=2e-3 if dtype == torch.float32 else 2e-2, atol=0.05 * H * W ** 0.5)
+    assert torch.allclose(pool.float(), pref, rtol=2e-3 if dtype == torch.float32 else 2e-2, atol=0.05 * H * W ** 0.5)
