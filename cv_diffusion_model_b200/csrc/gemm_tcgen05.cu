@@ -22,6 +22,7 @@
 // Tiles are ordered N-tile-major so that a CTA's contiguous tile range walks along M with a fixed weight
 // tile (weights stay in smem, statistics stay in one image for many tiles).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -51,6 +52,7 @@ struct TcParams {
   int conv_mode, Hin, Win, Hout, Wout, Ci;
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, coef_off, misc_off;
   uint32_t chunk[kMaxChunks];  // seg/tap | kvalid << 8 | c0 << 16
+  int debug;  // LCM_TC_DEBUG bit mask (bottleneck experiments only): 1 no A loads, 2 no stores, 4 no copy-out, 8 no stats
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -82,9 +84,9 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 6000000000LL) mbar_timeout(bar, parity);
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);   // try_wait itself sleeps in hardware between probes
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -171,6 +173,29 @@ __device__ __forceinline__ int div_upr(int u, int upr) {
 }
 
 // =====================================================================================================
+// Loop bookkeeping is strictly incremental and 32-bit: a 64-bit divide or modulo costs hundreds of
+// dependent cycles and every role is a single warp (or thread) on the critical path of the pipeline.
+struct TileIter {
+  int n_tile, m_tile, m0, img, rem;   // m0 = m_tile*128 ; img = m0 / P ; rem = m0 % P
+  __device__ __forceinline__ void init(long long t, int m_tiles, int P) {
+    n_tile = (int)(t / m_tiles);
+    m_tile = (int)(t - (long long)n_tile * m_tiles);
+    m0 = m_tile * 128;
+    img = m0 / P;
+    rem = m0 - img * P;
+  }
+  __device__ __forceinline__ void next(int m_tiles, int P) {
+    if (++m_tile == m_tiles) { m_tile = 0; ++n_tile; m0 = 0; img = 0; rem = 0; return; }
+    m0 += 128;
+    rem += 128;
+    while (rem >= P) { rem -= P; ++img; }
+  }
+};
+struct Ring {
+  int stage; uint32_t phase; int stages;
+  __device__ __forceinline__ void advance() { if (++stage == stages) { stage = 0; phase ^= 1u; } }
+};
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sraw = smem_u32(smem_raw);
@@ -213,84 +238,85 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const int m_tiles = (int)p.m_tiles;
   const long long total_tiles = p.m_tiles * p.n_tiles;
   const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-  const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
   const uint32_t b_chunk_bytes = (uint32_t)p.block_n * 128u;
+  const int M = (int)p.M;
 
   if (warp >= 6) {
     // ================================ A producers ================================================
     const int ptid = tid - kProdBase;
     const int group = ptid >> 7, gt = ptid & 127;
     int cur_img = -1;
-    long long gc = 0;  // chunk counter across tiles
-    for (long long t = t_begin; t < t_end; ++t) {
-      const long long m_tile = t % p.m_tiles;
-      const long long m0 = m_tile * 128;
-      if (p.ncoef > 0 && p.fast) {
-        const int img = (int)(m0 / p.P);
-        if (img != cur_img) {
-          bar_sync(1, kProdThreads);
-          for (int s = 0; s < p.nseg; ++s) {
-            if (p.seg[s].mode == XF_NONE) continue;
-            const float2* src = p.seg[s].coef + (size_t)img * p.seg[s].coef_ld + p.seg[s].coef_off;
-            for (int k = ptid; k < p.seg[s].K; k += kProdThreads) s_coef[p.coef_base[s] + k] = src[k];
-          }
-          bar_sync(1, kProdThreads);
-          cur_img = img;
+    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    Ring ring{0, 0u, p.stages};
+    int par = 0;   // chunk parity: group g fills the chunks with par == g
+    for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+      const int m0 = ti.m0;
+      if (p.ncoef > 0 && p.fast && ti.img != cur_img) {
+        bar_sync(1, kProdThreads);
+        for (int s = 0; s < p.nseg; ++s) {
+          if (p.seg[s].mode == XF_NONE) continue;
+          const float2* src = p.seg[s].coef + (size_t)ti.img * p.seg[s].coef_ld + p.seg[s].coef_off;
+          for (int k = ptid; k < p.seg[s].K; k += kProdThreads) s_coef[p.coef_base[s] + k] = src[k];
         }
+        bar_sync(1, kProdThreads);
+        cur_img = ti.img;
       }
       // conv: this thread's output pixel
-      int cy = 0, cx = 0;
-      long long cn = 0;
-      const long long cm = m0 + gt;
+      int cy = 0, cx = 0, cn = 0;
+      const int cm = m0 + gt;
       if (p.conv_mode >= 0) {
-        cx = (int)(cm % p.Wout);
-        const long long q = cm / p.Wout;
-        cy = (int)(q % p.Hout);
+        const int q = cm / p.Wout;
+        cx = cm - q * p.Wout;
         cn = q / p.Hout;
+        cy = q - cn * p.Hout;
       }
-      for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
-        if ((gc & 1) != group) continue;
-        const int stage = (int)(gc % p.stages);
-        const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
+      for (int ci = 0; ci < p.nchunks; ++ci, ring.advance(), par ^= 1) {
+        if (par != group) continue;
+        const int stage = ring.stage;
         const uint32_t cd = p.chunk[ci];
         const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
         const int upr = kvalid >> 3;
         const uint32_t a_smem = sbase + stage * p.stage_bytes;
-        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_wait(empty_bar(stage), ring.phase ^ 1u);
         if (p.conv_mode < 0) {
           // ---- 1x1: 16-byte units interleaved over threads (8 lanes cover one 128-byte row) ----------
           const GemmSeg& sg = p.seg[sidx];
           const bf16* A = reinterpret_cast<const bf16*>(sg.A);
           const int total = 128 * upr;
+          const int mode = sg.mode;
           uint4 v[8];
+          int rows[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int u = gt + i * 128;
             v[i] = make_uint4(0u, 0u, 0u, 0u);
+            rows[i] = div_upr(u, upr);
             if (u < total) {
-              const int row = div_upr(u, upr), cu = u - row * upr;
-              const long long m = m0 + row;
-              if (m < p.M) v[i] = ldg_stream(A + m * sg.ld + c0 + cu * 8);
+              const int cu = u - rows[i] * upr;
+              const int m = m0 + rows[i];
+              if (m < M && !(p.debug & 1)) v[i] = ldg_stream(A + (long long)m * sg.ld + c0 + cu * 8);
             }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int u = gt + i * 128;
-            if (u < total) {
-              const int row = div_upr(u, upr), cu = u - row * upr;
+            if (u < total && !(p.debug & 16)) {
+              const int row = rows[i], cu = u - row * upr;
               uint4 o = v[i];
-              if (sg.mode != XF_NONE && m0 + row < p.M) {
+              if (mode != XF_NONE && m0 + row < M) {
                 if (p.fast) {
-                  o = apply_xform(o, s_coef + p.coef_base[sidx] + c0 + cu * 8, sg.mode);
+                  o = apply_xform(o, s_coef + p.coef_base[sidx] + c0 + cu * 8, mode);
                 } else {
-                  const int img = (int)((m0 + row) / p.P);
+                  const int img = (m0 + row) / p.P;
                   __align__(16) float2 ab[8];
                   const float2* src = sg.coef + (size_t)img * sg.coef_ld + sg.coef_off + c0 + cu * 8;
 #pragma unroll
                   for (int j = 0; j < 8; ++j) ab[j] = src[j];
-                  o = apply_xform(o, ab, sg.mode);
+                  o = apply_xform(o, ab, mode);
                 }
               }
               sts128(a_smem + row * 128 + ((cu ^ (row & 7)) << 4), o);
@@ -304,15 +330,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int sw = gt & 7;
           if (p.conv_mode == CONV_UP2) {
             const int uy = cy + ky - 1, ux = cx + kx - 1;
-            const bool ok = cm < p.M && uy >= 0 && uy < p.Hout && ux >= 0 && ux < p.Wout;
+            const bool ok = cm < M && uy >= 0 && uy < p.Hout && ux >= 0 && ux < p.Wout;
             if (ok) {
               // F.interpolate(scale_factor=2, bilinear, align_corners=False): src = max(dst/2 - 0.25, 0)
               const float sy = fmaxf(uy * 0.5f - 0.25f, 0.f), sx = fmaxf(ux * 0.5f - 0.25f, 0.f);
               const int y0 = (int)sy, x0 = (int)sx;
               const int y1 = min(y0 + 1, p.Hin - 1), x1 = min(x0 + 1, p.Win - 1);
               const float ly = sy - y0, lx = sx - x0;
-              const bf16* b0 = in + ((cn * p.Hin + y0) * p.Win) * p.Ci + c0;
-              const bf16* b1 = in + ((cn * p.Hin + y1) * p.Win) * p.Ci + c0;
+              const bf16* b0 = in + ((long long)(cn * p.Hin + y0) * p.Win) * p.Ci + c0;
+              const bf16* b1 = in + ((long long)(cn * p.Hin + y1) * p.Win) * p.Ci + c0;
               for (int cu = 0; cu < upr; ++cu) {
                 float a[8], b[8], c[8], d[8], o[8];
                 unpack8(ldg_cached(b0 + (long long)x0 * p.Ci + cu * 8), a);
@@ -330,8 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           } else {
             const int st = p.conv_mode == CONV_S2 ? 2 : 1;
             const int iy = cy * st + ky - 1, ix = cx * st + kx - 1;
-            const bool ok = cm < p.M && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-            const bf16* src = in + ((cn * p.Hin + iy) * p.Win + ix) * p.Ci + c0;
+            const bool ok = cm < M && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+            const bf16* src = in + ((long long)(cn * p.Hin + iy) * p.Win + ix) * p.Ci + c0;
             uint4 v[8];
 #pragma unroll
             for (int cu = 0; cu < 8; ++cu) v[cu] = (ok && cu < upr) ? ldg_cached(src + cu * 8) : make_uint4(0u, 0u, 0u, 0u);
@@ -345,67 +371,67 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 5) {
-    // ================================ weight loader (TMA bulk copies) =============================
+    // ================================ weight loader (TMA bulk copies), one thread =====================
     if (lane == 0) {
       int cur_nt = -1;
-      long long gc = 0, it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const int n_tile = (int)(t / p.m_tiles);
-        const bf16* wt = p.W + (size_t)n_tile * p.nchunks * p.block_n * 64;
+      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      Ring ring{0, 0u, p.stages};
+      int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
+      for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+        const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
         if (p.resident) {
-          if (n_tile != cur_nt) {
-            if (it > 0) mbar_wait(tfull_bar((int)((it - 1) & 1)), (uint32_t)(((it - 1) >> 1) & 1));  // old weights no longer read
+          if (ti.n_tile != cur_nt) {
+            if (it > 0) mbar_wait(tfull_bar(acc), aphase);   // MMAs of the previous tile done: old weights dead
             mbar_expect_tx(bres_bar, (uint32_t)p.nchunks * b_chunk_bytes);
             for (int ci = 0; ci < p.nchunks; ++ci)
               bulk_g2s(sbase + p.bres_off + ci * b_chunk_bytes, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, bres_bar);
-            cur_nt = n_tile;
+            cur_nt = ti.n_tile;
           }
+          if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }   // now describes tile `it`
         } else {
-          for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
-            const int stage = (int)(gc % p.stages);
-            const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), b_chunk_bytes);
-            bulk_g2s(sbase + stage * p.stage_bytes + kStageA, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, full_bar(stage));
+          for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1u);
+            mbar_expect_tx(full_bar(ring.stage), b_chunk_bytes);
+            bulk_g2s(sbase + ring.stage * p.stage_bytes + kStageA, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes,
+                     full_bar(ring.stage));
           }
         }
       }
     }
   } else if (warp == 4) {
-    // ================================ MMA issuer ================================================
-    // instruction descriptor: D fp32, A/B bf16, both K-major, N = block_n, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
-    int cur_nt = -1;
-    uint32_t bres_phase = 0;
-    long long gc = 0, it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      const int n_tile = (int)(t / p.m_tiles);
-      const int acc = (int)(it & 1);
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      if (p.resident && n_tile != cur_nt) {
-        mbar_wait(bres_bar, bres_phase);
-        bres_phase ^= 1;
-        cur_nt = n_tile;
-      }
-      mbar_wait(tempty_bar(acc), aphase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-      for (int ci = 0; ci < p.nchunks; ++ci, ++gc) {
-        const int stage = (int)(gc % p.stages);
-        const uint32_t phase = (uint32_t)((gc / p.stages) & 1);
-        mbar_wait(full_bar(stage), phase);
+    // ================================ MMA issuer, one thread ==========================================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = block_n, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
+      int cur_nt = -1;
+      uint32_t bres_phase = 0;
+      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      Ring ring{0, 0u, p.stages};
+      int acc = 0; uint32_t aphase = 0;
+      for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+        if (p.resident && ti.n_tile != cur_nt) {
+          mbar_wait(bres_bar, bres_phase);
+          bres_phase ^= 1u;
+          cur_nt = ti.n_tile;
+        }
+        mbar_wait(tempty_bar(acc), aphase ^ 1u);
         tc_fence_after();
-        if (lane == 0) {
-          const int kvalid = (p.chunk[ci] >> 8) & 0xff;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+          const int stage = ring.stage;
+          mbar_wait(full_bar(stage), ring.phase);
+          tc_fence_after();
+          const int ksteps = (p.chunk[ci] >> 12) & 0xf;   // kvalid / 16
           const uint32_t a_addr = sbase + stage * p.stage_bytes;
           const uint32_t b_addr = p.resident ? sbase + p.bres_off + ci * b_chunk_bytes : a_addr + kStageA;
           const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
-          for (int k = 0; k < (kvalid >> 4); ++k)
+          for (int k = 0; k < ksteps; ++k)
             umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
           if (ci == p.nchunks - 1) umma_commit(tfull_bar(acc));
         }
-        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) aphase ^= 1u;
       }
     }
   } else {
@@ -415,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool active = tid < upr * RG;
     const int cu = tid % upr, rg = tid / upr;
     const uint32_t stg = sbase + p.stg_off;
+    const bool do_stats = p.stats != nullptr && !(p.debug & 8);
     int cur_img = -1, cur_nt = -1;
     auto flush = [&]() {   // all statistics of (cur_img, cur_nt) -> global, fp64 atomics
       for (int c = tid; c < p.block_n; c += kEpiThreads) {
@@ -425,17 +452,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         s_sq[c] = 0.f;
       }
     };
-    long long it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      const int n_tile = (int)(t / p.m_tiles);
-      const long long m0 = (t % p.m_tiles) * 128;
-      const int n0 = n_tile * p.block_n;
-      const int acc = (int)(it & 1);
-      const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      const int img = (int)(m0 / p.P);
-      if (p.stats && p.fast && (img != cur_img || n_tile != cur_nt)) {
+    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    int acc = 0; uint32_t aphase = 0;
+    for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+      const int n_tile = ti.n_tile, m0 = ti.m0, n0 = n_tile * p.block_n;
+      if (do_stats && p.fast && (ti.img != cur_img || n_tile != cur_nt)) {
         if (cur_img >= 0) flush();   // columns are thread-owned: program order suffices
-        cur_img = img;
+        cur_img = ti.img;
       }
       if (p.bias && n_tile != cur_nt) {
         for (int c = tid; c < p.block_n; c += kEpiThreads) s_bias[c] = p.bias[n0 + c];
@@ -447,46 +470,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 256u;
       const uint32_t my_row = stg + (uint32_t)tid * p.stg_stride;
-      for (int cb = 0; cb < p.block_n; cb += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + cb, r);
+      for (int cb = 0; cb < ((p.debug & 32) ? 0 : p.block_n); cb += 32) {
+        // two 16-column TMEM loads in flight per wait
+        uint32_t r0[16], r1[16];
+        const bool two = cb + 16 < p.block_n;
+        tmem_ld16(taddr + cb, r0);
+        if (two) tmem_ld16(taddr + cb + 16, r1);
         tmem_wait_ld();
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += s_bias[cb + j];
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(h == 0 ? r0[j] : r1[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += s_bias[cb + h * 16 + j];
+          }
+          const uint32_t dst = my_row + (cb + h * 16) * 2;
+          sts128(dst, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+          sts128(dst + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
         }
-        sts128(my_row + cb * 2, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
-        sts128(my_row + cb * 2 + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));   // accumulator drained: the MMA warp may start the tile after next
       bar_sync(2, kEpiThreads);       // staging complete
-      if (active) {
+      if (active && !(p.debug & 4)) {
         float cs[8], cq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-        for (int r = rg; r < 128; r += RG) {
-          const long long m = m0 + r;
-          if (m >= p.M) break;
-          const uint4 v = lds128(stg + (uint32_t)r * p.stg_stride + cu * 16);
-          *reinterpret_cast<uint4*>(p.out + m * p.Nc + n0 + cu * 8) = v;
-          if (p.stats) {
+        const int rows_valid = min(128, M - m0);
+        uint32_t src = stg + (uint32_t)rg * p.stg_stride + cu * 16;
+        bf16* dst = p.out + (long long)(m0 + rg) * p.Nc + n0 + cu * 8;
+        const uint32_t src_step = (uint32_t)RG * p.stg_stride;
+        const long long dst_step = (long long)RG * p.Nc;
+#pragma unroll 4
+        for (int r = rg; r < rows_valid; r += RG, src += src_step, dst += dst_step) {
+          const uint4 v = lds128(src);
+          if (!(p.debug & 2)) *reinterpret_cast<uint4*>(dst) = v;
+          if (do_stats) {
             float f[8];
             unpack8(v, f);
             if (p.fast) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
             } else {
-              double* d = p.stats + ((size_t)(m / p.P) * p.Nc + n0 + cu * 8) * 2;
+              double* d = p.stats + ((size_t)((m0 + r) / p.P) * p.Nc + n0 + cu * 8) * 2;
 #pragma unroll
               for (int j = 0; j < 8; ++j) { atomicAdd(d + 2 * j, (double)f[j]); atomicAdd(d + 2 * j + 1, (double)f[j] * f[j]); }
             }
           }
         }
-        if (p.stats && p.fast) {   // partial sums of this thread's rows; folded (without atomics) after the barrier
+        if (do_stats && p.fast) {   // partial sums of this thread's rows; folded (without atomics) after the barrier
           float4* ps = reinterpret_cast<float4*>(s_psum + rg * p.block_n + cu * 8);
           float4* pq = reinterpret_cast<float4*>(s_psq + rg * p.block_n + cu * 8);
           ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
@@ -494,16 +529,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
       bar_sync(2, kEpiThreads);       // staging free, partial statistics visible
-      if (p.stats && p.fast) {
+      if (do_stats && p.fast && !(p.debug & 4)) {
         for (int c = tid; c < p.block_n; c += kEpiThreads) {   // column c is owned by thread c % 128
           float a = 0.f, b = 0.f;
+#pragma unroll 4
           for (int g = 0; g < RG; ++g) { a += s_psum[g * p.block_n + c]; b += s_psq[g * p.block_n + c]; }
           s_sum[c] += a;
           s_sq[c] += b;
         }
       }
+      acc ^= 1;
+      if (acc == 0) aphase ^= 1u;
     }
-    if (p.stats && p.fast && cur_img >= 0) flush();
+    if (do_stats && p.fast && cur_img >= 0) flush();
   }
 
   tc_fence_before();
@@ -527,6 +565,7 @@ int gemm_tc_pick_block_n(int Nc) {
 int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st) {
   TcParams p{};
   if (block_n < 16 || block_n > 256 || block_n % 16 || g.Nc % block_n) return -1;
+  if (g.M <= 0 || g.M > 0x7fffff00LL || g.P <= 0) return -1;   // 32-bit row indices inside the kernel
   p.nseg = g.nseg;
   p.W = reinterpret_cast<const bf16*>(g.W);
   p.out = reinterpret_cast<bf16*>(g.out);
@@ -564,6 +603,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   }
   p.nchunks = nch;
   p.ncoef = ncoef;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
