@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Loader ld, const T* __re
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
   __shared__ float s_sum[64], s_sq[64];
+  __shared__ float s_ps[16][64], s_pq[16][64];   // per-row-group partial column sums (fixed-order fold)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long m0 = (long long)blockIdx.x * 64;
   const int n0 = blockIdx.y * 64;
@@ -126,8 +127,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Loader ld, const T* __re
   // epilogue: bias, store, channel statistics of the stored values
   const long long last = (m0 + 63 < M ? m0 + 63 : M - 1);
   const bool one_image = (m0 / P) == (last / P);
-  if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
-  __syncthreads();
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -153,7 +152,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Loader ld, const T* __re
   }
   if (stats && one_image) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { atomicAdd(&s_sum[tx * 4 + j], cs[j]); atomicAdd(&s_sq[tx * 4 + j], cq[j]); }
+    for (int j = 0; j < 4; ++j) { s_ps[ty][tx * 4 + j] = cs[j]; s_pq[ty][tx * 4 + j] = cq[j]; }
+    __syncthreads();
+    if (tid < 64) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) { a += s_ps[g][tid]; b += s_pq[g][tid]; }
+      s_sum[tid] = a; s_sq[tid] = b;
+    }
     __syncthreads();
     flush_stats(stats, (int)(m0 / P), Nc, n0, 64, s_sum, s_sq);
   }
@@ -200,12 +206,11 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
                                                      double* __restrict__ pool, int H, int W, int C, int tilesX) {
   constexpr int TS = 16, HS = TS + 2, CB = 32;
   __shared__ __align__(16) float tile[HS * HS * CB];
-  __shared__ float s_pool[CB];
+  __shared__ float s_part[8][CB];   // per-warp partial pooled sums (fixed-order reduction: reproducible)
   const int tid = threadIdx.x;
   const int n = blockIdx.z, c0 = blockIdx.y * CB;
   const int ty0 = (blockIdx.x / tilesX) * TS, tx0 = (blockIdx.x % tilesX) * TS;
   const int cg = tid & 3;  // this thread's 8-channel group (fixed for loads and compute: 256 % 4 == 0)
-  if (tid < CB) s_pool[tid] = 0.f;
 
   float2 ab[8];
 #pragma unroll
@@ -272,15 +277,23 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if ((tid & 31) < 4) atomicAdd(&s_pool[cg * 8 + j], v);
+    if ((tid & 31) < 4) s_part[tid >> 5][cg * 8 + j] = v;
   }
   __syncthreads();
-  if (tid < CB) atomicAdd(&pool[(size_t)n * C + c0 + tid], (double)s_pool[tid]);
+  if (tid < CB) {
+    float s = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) s += s_part[wi][tid];
+    atomicAdd(&pool[(size_t)n * C + c0 + tid], (double)s);
+  }
 }
+
+void launch_dwconv_fast(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
+                        int C, cudaStream_t st);   // dwconv_fast.cu (bf16 only)
 
 void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                    int C, int bf16act, int fast, cudaStream_t st) {
-  (void)fast;
+  if (fast && bf16act) { launch_dwconv_fast(in, coef, w, out, pool, N, H, W, C, st); return; }
   const int tilesX = (W + 15) / 16, tilesY = (H + 15) / 16;
   dim3 grid(tilesX * tilesY, C / 32, N);
   if (bf16act) dwconv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)in, coef, w, (bf16*)out, pool, H, W, C, tilesX);
@@ -296,12 +309,12 @@ __global__ void __launch_bounds__(128) init_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         T* __restrict__ out, double* __restrict__ stats, int H, int W,
                                                         int Co) {
-  extern __shared__ float sw[];  // [9*Cin][Co] then s_sum[Co], s_sq[Co]
+  extern __shared__ float sw[];  // [9*Cin][Co], then per-warp partials [4][2*Co], then s_sum[Co], s_sq[Co]
   const int Cin = ca + cb, K = 9 * Cin;
-  float* s_sum = sw + K * Co;
+  float* s_part = sw + K * Co;
+  float* s_sum = s_part + 4 * 2 * Co;
   float* s_sq = s_sum + Co;
   for (int i = threadIdx.x; i < K * Co; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < 2 * Co; i += blockDim.x) s_sum[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,9 +352,12 @@ __global__ void __launch_bounds__(128) init_conv_kernel(const float* __restrict_
       float v = valid ? rt<T>(acc[c]) : 0.f, q = v * v;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-      if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[c], v); atomicAdd(&s_sq[c], q); }
+      if ((threadIdx.x & 31) == 0) { s_part[(threadIdx.x >> 5) * 2 * Co + c] = v; s_part[(threadIdx.x >> 5) * 2 * Co + Co + c] = q; }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Co; i += blockDim.x)   // fixed-order reduction over the 4 warps
+    s_sum[i] = (s_part[i] + s_part[2 * Co + i]) + (s_part[4 * Co + i] + s_part[6 * Co + i]);
   __syncthreads();
   flush_stats(stats, n, Co, 0, Co, s_sum, s_sq);
 }
@@ -350,7 +366,7 @@ void launch_init_conv(const float* xa, int ca, long long sa, const float* xb, in
                       const float* bias, void* out, double* stats, int N, int H, int W, int Co, int bf16act,
                       cudaStream_t st) {
   dim3 grid((H * W + 127) / 128, N);
-  size_t smem = ((size_t)9 * (ca + cb) * Co + 2 * Co) * sizeof(float);
+  size_t smem = ((size_t)9 * (ca + cb) * Co + 10 * Co) * sizeof(float);
   if (bf16act)
     init_conv_kernel<bf16, 64><<<grid, 128, smem, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co);
   else
