@@ -1,0 +1,647 @@
+// tcgen05 GEMM, second generation: the kernel behind every 1x1 convolution (and, through a gather
+// producer, every dense 3x3 convolution) of the EfficientUNet in bf16 mode.
+//
+//   out[m][n] = sum_k xform(A[m][k]) * W[n][k] (+ bias[n]);  bf16 operands, fp32 accumulation in TMEM,
+//   epilogue: bf16 store + per-(image, channel) sum / sum-of-squares for the consumer's GroupNorm.
+//
+// Most of these GEMMs are HBM-bound (K, N <= 384 at 256^2 / 128^2), so the kernel is organised as a
+// deep streaming pipeline in which no role ever waits on global-memory latency with registers:
+//
+//   warp 5 (1 thread)  TMA      cp.async.bulk.tensor.2d (128-byte swizzle) brings 128 x 64 activation tiles of
+//                               each operand segment straight into the UMMA stage layout, up to `stages`
+//                               chunks ahead; weights arrive as pre-swizzled bulk copies (resident in smem
+//                               when they fit, else streamed with the A chunk).  Rows >= M and channels
+//                               >= K are zero-filled by the TMA unit.
+//   warps 14-21        XF       in-place prologue on the landed tile (smem -> registers -> smem): GroupNorm /
+//                               FiLM affine + ReLU6, or the SE gate; operands that need no transform (the
+//                               residual / skip-conv input) skip this stage entirely.  For 3x3 convolutions
+//                               these warps gather the taps instead (zero padding, stride 2, bilinear x2).
+//   warp 4 (1 thread)  MMA      tcgen05.mma M=128, N=block_n, K=16 per 32 bytes of K; tcgen05.commit frees
+//                               the stage and publishes the accumulator (two accumulators in TMEM).
+//   warps 0-3          E1       tcgen05.ld -> (+bias) -> bf16 -> padded smem staging tile (double-buffered)
+//   warps 6-13         E2       staging -> coalesced 16-byte global stores + column statistics; partial sums
+//                               are folded without atomics into CTA-resident accumulators that are flushed
+//                               with fp64 atomics only when the image (or N tile) changes.
+// All loop bookkeeping is incremental 32-bit arithmetic; every wait is a bounded mbarrier wait.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace lcm {
+
+int launch_gemm_tc_v1(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st);
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads2 = 704;
+constexpr int kE2Base = 192, kE2Threads = 256, kXfBase = 448, kXfThreads = 256;
+constexpr uint32_t kStageA2 = 16384;
+constexpr int kMaxChunks2 = 160;
+constexpr uint32_t kSmemLimit2 = 232448;
+constexpr uint32_t kMisc2 = 4096 + 16384;
+
+struct alignas(64) Tc2Params {
+  CUtensorMap tmap[LCM_MAX_SEGS];
+  GemmSeg seg[LCM_MAX_SEGS];
+  int coef_base[LCM_MAX_SEGS];
+  int nseg, ncoef;
+  const bf16* W;
+  bf16* out;
+  double* stats;
+  const float* bias;
+  long long M, m_tiles;
+  int P, Nc, block_n, n_tiles, nchunks;
+  int resident, stages, fast, nbuf;
+  int conv_mode, Hin, Win, Hout, Wout, Ci;
+  uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
+  int debug;
+  uint32_t chunk[kMaxChunks2];  // seg/tap | kvalid << 8 | c0 << 16
+};
+
+__device__ long long g_timeline[64 * 16];   // LCM_TC_DEBUG & 64: per-tile clock64 stamps of block 0
+#define TSTAMP(slot) do { if (kDebug && (p.debug & 64) && blockIdx.x == 0 && it < 64) g_timeline[it * 16 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// kConv: 3x3 gather producer instead of TMA + in-place prologue; kFast: every 128-row tile lies inside one image
+// (P % 128 == 0); kDebug: bottleneck-experiment switches and the timeline (never instantiated on the product path
+// unless LCM_TC_DEBUG is set).  Specialising keeps each instantiation's code small: the five roles run different
+// code concurrently and the instruction cache is a real constraint.
+template <bool kConv, bool kFast, bool kDebug>
+__global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - sraw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint8_t* misc = smem + p.misc_off;
+  const uint32_t bar0 = sbase + p.misc_off;
+  auto raw_bar = [&](int s) { return bar0 + 8u * s; };
+  auto xf_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (24 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (26 + a); };
+  auto sfull_bar = [&](int b) { return bar0 + 8u * (28 + b); };
+  auto sempty_bar = [&](int b) { return bar0 + 8u * (30 + b); };
+  const uint32_t bres_bar = bar0 + 8u * 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 320);
+  float* s_sum = reinterpret_cast<float*>(misc + 512);
+  float* s_sq = s_sum + 256;
+  float* s_bias = s_sq + 256;
+  float* s_scr = reinterpret_cast<float*>(misc + 4096);   // { psum[2048], psq[2048] }: statistics flush scratch
+  float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_off);
+
+  auto ld_s = [&](uint32_t saddr) { return *reinterpret_cast<const uint4*>(smem + (saddr - sbase)); };
+  auto st_s = [&](uint32_t saddr, uint4 v) { *reinterpret_cast<uint4*>(smem + (saddr - sbase)) = v; };
+
+  constexpr bool conv = kConv;
+  const int dbg = kDebug ? p.debug : 0;
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(raw_bar(s), 1);
+      mbar_init(xf_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+      mbar_init(sfull_bar(a), 128);
+      mbar_init(sempty_bar(a), kE2Threads);
+    }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (!conv)
+      for (int s = 0; s < p.nseg; ++s)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap[s])) : "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid < 256) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (int)p.m_tiles;
+  const long long total_tiles = p.m_tiles * p.n_tiles;
+  const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+  const int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
+  const uint32_t b_chunk_bytes = (uint32_t)p.block_n * 128u;
+  const int M = (int)p.M;
+
+  if (warp >= 14) {
+    // ================================ XF: prologue transform / conv gather ==========================
+    const int ptid = tid - kXfBase;
+    const int group = ptid >> 7, gt = ptid & 127;
+    int cur_img = -1;
+    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    Ring ring{0, 0u, p.stages};
+    int par = 0;
+    for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+      const int m0 = ti.m0;
+      if (p.ncoef > 0 && kFast && ti.img != cur_img) {
+        bar_sync(1, kXfThreads);
+        for (int s = 0; s < p.nseg; ++s) {
+          if (p.seg[s].mode == XF_NONE) continue;
+          const float2* src = p.seg[s].coef + (size_t)ti.img * p.seg[s].coef_ld + p.seg[s].coef_off;
+          for (int k = ptid; k < p.seg[s].K; k += kXfThreads) s_coef[p.coef_base[s] + k] = src[k];
+        }
+        bar_sync(1, kXfThreads);
+        cur_img = ti.img;
+      }
+      int cy = 0, cx = 0, cn = 0;
+      const int cm = m0 + gt;
+      if constexpr (conv) {
+        const int q = cm / p.Wout;
+        cx = cm - q * p.Wout;
+        cn = q / p.Hout;
+        cy = q - cn * p.Hout;
+      }
+      for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+        const uint32_t cd = p.chunk[ci];
+        const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
+        const int upr = kvalid >> 3;
+        const int stage = ring.stage;
+        const uint32_t a_smem = sbase + stage * p.stage_bytes;
+        if constexpr (!conv) {
+          const int mode = p.seg[sidx].mode;
+          par ^= 1;
+          if (par != (group ^ 1)) continue;       // chunks alternate between the two groups
+          // Every chunk passes through this stage so that xf_bar completes exactly one phase per use of the
+          // stage (an mbarrier must never run two phases ahead of its waiter); operands that need no
+          // transform (residual / skip input) are only handed on.
+          mbar_wait(raw_bar(stage), ring.phase);  // TMA bytes landed (swizzled: unit (row, cu) sits at slot cu ^ (row & 7))
+          if (ci == 0 && gt == 0) TSTAMP(1);
+          if (mode != XF_NONE && !(dbg & 16)) {
+            const GemmSeg& sg = p.seg[sidx];
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ld_s(a_smem + (uint32_t)(gt + i * 128) * 16u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int u = gt + i * 128;
+              const int row = u >> 3, cu = (u & 7) ^ (row & 7);
+              if (cu < upr) {
+                uint4 o;
+                if (dbg & 256) {
+                  o = v[i];
+                } else if (kFast) {
+                  o = apply_xform(v[i], s_coef + p.coef_base[sidx] + c0 + cu * 8, mode);
+                } else {
+                  const int mrow = min(m0 + row, M - 1);
+                  const int img = mrow / p.P;
+                  __align__(16) float2 ab[8];
+                  const float2* src = sg.coef + (size_t)img * sg.coef_ld + sg.coef_off + c0 + cu * 8;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) ab[j] = src[j];
+                  o = apply_xform(v[i], ab, mode);
+                }
+                st_s(a_smem + (uint32_t)u * 16u, o);
+              }
+            }
+            if (!(dbg & 128)) fence_proxy_async();
+          }
+          mbar_arrive(xf_bar(stage));
+          if (ci == 0 && gt == 0) TSTAMP(2);
+        } else {
+          par ^= 1;
+          if (par != (group ^ 1)) continue;
+          mbar_wait(empty_bar(stage), ring.phase ^ 1u);
+          // ---- 3x3 tap gather: one output pixel (row) per thread -------------------------------------
+          const int tap = sidx, ky = tap / 3, kx = tap - ky * 3;
+          const bf16* in = reinterpret_cast<const bf16*>(p.seg[0].A);
+          const uint32_t rbase = a_smem + gt * 128;
+          const int sw = gt & 7;
+          if (p.conv_mode == CONV_UP2) {
+            const int uy = cy + ky - 1, ux = cx + kx - 1;
+            const bool ok = cm < M && uy >= 0 && uy < p.Hout && ux >= 0 && ux < p.Wout;
+            if (ok) {
+              // F.interpolate(scale_factor=2, bilinear, align_corners=False): src = max(dst/2 - 0.25, 0)
+              const float sy = fmaxf(uy * 0.5f - 0.25f, 0.f), sx = fmaxf(ux * 0.5f - 0.25f, 0.f);
+              const int y0 = (int)sy, x0 = (int)sx;
+              const int y1 = min(y0 + 1, p.Hin - 1), x1 = min(x0 + 1, p.Win - 1);
+              const float ly = sy - y0, lx = sx - x0;
+              const bf16* b0 = in + ((long long)(cn * p.Hin + y0) * p.Win) * p.Ci + c0;
+              const bf16* b1 = in + ((long long)(cn * p.Hin + y1) * p.Win) * p.Ci + c0;
+              for (int cu = 0; cu < upr; ++cu) {
+                float a[8], b[8], c[8], d[8], o[8];
+                unpack8(ldg_cached(b0 + (long long)x0 * p.Ci + cu * 8), a);
+                unpack8(ldg_cached(b0 + (long long)x1 * p.Ci + cu * 8), b);
+                unpack8(ldg_cached(b1 + (long long)x0 * p.Ci + cu * 8), c);
+                unpack8(ldg_cached(b1 + (long long)x1 * p.Ci + cu * 8), d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+                sts128(rbase + ((cu ^ sw) << 4), pack8(o));
+              }
+            } else {
+              for (int cu = 0; cu < upr; ++cu) sts128(rbase + ((cu ^ sw) << 4), make_uint4(0u, 0u, 0u, 0u));
+            }
+          } else {
+            const int st = p.conv_mode == CONV_S2 ? 2 : 1;
+            const int iy = cy * st + ky - 1, ix = cx * st + kx - 1;
+            const bool ok = cm < M && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+            const bf16* src = in + ((long long)(cn * p.Hin + iy) * p.Win + ix) * p.Ci + c0;
+            uint4 v[8];
+#pragma unroll
+            for (int cu = 0; cu < 8; ++cu) v[cu] = (ok && cu < upr) ? ldg_cached(src + cu * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int cu = 0; cu < 8; ++cu)
+              if (cu < upr) sts128(rbase + ((cu ^ sw) << 4), v[cu]);
+          }
+          fence_proxy_async();
+          mbar_arrive(xf_bar(stage));
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ TMA: activations and weights ====================================
+    // The whole warp runs the (uniform) control flow so that addresses and barriers live in uniform
+    // registers; one elected lane issues the copies.
+    {
+      int cur_nt = -1;
+      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      Ring ring{0, 0u, p.stages};
+      int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
+      for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+        const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
+        if (p.resident) {
+          if (ti.n_tile != cur_nt) {
+            if (it > 0) mbar_wait(tfull_bar(acc), aphase);   // MMAs of the previous tile done: old weights dead
+            if (elect_one()) {
+              mbar_expect_tx(bres_bar, (uint32_t)p.nchunks * b_chunk_bytes);
+              for (int ci = 0; ci < p.nchunks; ++ci)
+                bulk_g2s(sbase + p.bres_off + ci * b_chunk_bytes, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, bres_bar);
+            }
+            __syncwarp();
+            cur_nt = ti.n_tile;
+          }
+          if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
+        }
+        if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
+        for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+          const int stage = ring.stage;
+          const uint32_t cd = p.chunk[ci];
+          const uint32_t a_smem = sbase + stage * p.stage_bytes;
+          mbar_wait(empty_bar(stage), ring.phase ^ 1u);
+          if (ci == 0) TSTAMP(0);
+          const bool load_a = !conv && !(dbg & 1);
+          if (elect_one()) {
+            mbar_expect_tx(raw_bar(stage), (load_a ? kStageA2 : 0u) + (p.resident ? 0u : b_chunk_bytes));
+            if (load_a) tma_load_2d(a_smem, &p.tmap[cd & 0xff], (int)(cd >> 16), ti.m0, raw_bar(stage));
+            if (!p.resident)
+              bulk_g2s(a_smem + kStageA2, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, raw_bar(stage));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================================ MMA issuer (warp-uniform control, one elected lane issues) =====
+    {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
+      int cur_nt = -1;
+      uint32_t bres_phase = 0;
+      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      Ring ring{0, 0u, p.stages};
+      int acc = 0; uint32_t aphase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+        if (p.resident && ti.n_tile != cur_nt) {
+          mbar_wait(bres_bar, bres_phase);
+          bres_phase ^= 1u;
+          cur_nt = ti.n_tile;
+        }
+        mbar_wait(tempty_bar(acc), aphase ^ 1u);
+        TSTAMP(3);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
+        for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+          const int stage = ring.stage;
+          const uint32_t cd = p.chunk[ci];
+          mbar_wait(xf_bar(stage), ring.phase);
+          if (ci == 0) TSTAMP(4);
+          if (conv && !p.resident) mbar_wait(raw_bar(stage), ring.phase);   // streamed weights of a 3x3 conv
+          tc_fence_after();
+          const int ksteps = (cd >> 12) & 0xf;
+          const uint32_t a_addr = sbase + stage * p.stage_bytes;
+          const uint32_t b_addr = p.resident ? sbase + p.bres_off + ci * b_chunk_bytes : a_addr + kStageA2;
+          const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (ci == p.nchunks - 1) umma_commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (ci == p.nchunks - 1) TSTAMP(5);
+        }
+        acc ^= 1;
+        if (acc == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ E1: TMEM -> bf16 staging ==========================================
+    int cur_nt = -1;
+    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    int acc = 0; uint32_t aphase = 0;
+    int sb = 0; uint32_t sphase = 0;
+    for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+      if (p.bias && ti.n_tile != cur_nt) {
+        bar_sync(3, 128);   // previous tile's bias reads are done
+        for (int c = tid; c < p.block_n; c += 128) s_bias[c] = p.bias[ti.n_tile * p.block_n + c];
+        bar_sync(3, 128);
+      }
+      cur_nt = ti.n_tile;
+      mbar_wait(tfull_bar(acc), aphase);
+      if (tid == 0) TSTAMP(6);
+      mbar_wait(sempty_bar(sb), sphase ^ 1u);
+      if (tid == 0) TSTAMP(7);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t my_row = sbase + p.stg_off + (uint32_t)sb * p.stg_bytes + (uint32_t)tid * p.stg_stride;
+      for (int cb = 0; cb < ((dbg & 32) ? 0 : p.block_n); cb += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = cb + 16 < p.block_n;
+        tmem_ld16(taddr + cb, r0);
+        if (two) tmem_ld16(taddr + cb + 16, r1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(h == 0 ? r0[j] : r1[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += s_bias[cb + h * 16 + j];
+          }
+          const uint32_t dst = my_row + (cb + h * 16) * 2;
+          st_s(dst, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+          st_s(dst + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));   // accumulator drained
+      mbar_arrive(sfull_bar(sb));     // staging tile complete (release)
+      if (tid == 0) TSTAMP(8);
+      acc ^= 1; if (acc == 0) aphase ^= 1u;
+      if (++sb == p.nbuf) { sb = 0; sphase ^= 1u; }
+    }
+  } else {
+    // ================================ E2: staging -> global + statistics (warps 6-13) ===================
+    const int et = tid - kE2Base;
+    const int upr = p.block_n >> 3;
+    const int RG = kE2Threads / upr;          // rows covered per pass
+    const bool active = et < upr * RG;
+    const int cu = et % upr, rg = et / upr;
+    const bool do_stats = p.stats != nullptr && !(dbg & 8);
+    int cur_img = -1, cur_nt = -1;
+    // Column statistics: every thread keeps the partial sums of its 8 columns in registers ACROSS tiles (the
+    // thread <-> column mapping is tile-invariant); they are combined over the row groups through shared
+    // memory in a fixed order, and added to the fp64 accumulators, only when the image or N tile changes.
+    float cs[8], cq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+    float* psum = s_scr;
+    float* psq = s_scr + 2048;
+    auto flush = [&]() {   // uniform across the 256 E2 threads
+      if (active) {
+        float4* ps = reinterpret_cast<float4*>(psum + rg * p.block_n + cu * 8);
+        float4* pq = reinterpret_cast<float4*>(psq + rg * p.block_n + cu * 8);
+        ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+        pq[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); pq[1] = make_float4(cq[4], cq[5], cq[6], cq[7]);
+      }
+      bar_sync(2, kE2Threads);
+      if (et < p.block_n) {
+        float a = 0.f, b = 0.f;
+#pragma unroll 4
+        for (int g = 0; g < RG; ++g) { a += psum[g * p.block_n + et]; b += psq[g * p.block_n + et]; }
+        double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + et) * 2;
+        atomicAdd(d, (double)a);
+        atomicAdd(d + 1, (double)b);
+      }
+      bar_sync(2, kE2Threads);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+    };
+    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    int sb = 0; uint32_t sphase = 0;
+    for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
+      const int n_tile = ti.n_tile, m0 = ti.m0, n0 = n_tile * p.block_n;
+      if (do_stats && kFast && (ti.img != cur_img || n_tile != cur_nt)) {
+        if (cur_img >= 0) flush();
+        cur_img = ti.img;
+      }
+      cur_nt = n_tile;
+      mbar_wait(sfull_bar(sb), sphase);
+      if (et == 0) TSTAMP(9);
+      if (active && !(dbg & 4)) {
+        const int rows_valid = min(128, M - m0);
+        const uint8_t* src = smem + p.stg_off + (uint32_t)sb * p.stg_bytes + (uint32_t)rg * p.stg_stride + cu * 16;
+        bf16* dst = p.out + (long long)(m0 + rg) * p.Nc + n0 + cu * 8;
+        const uint32_t src_step = (uint32_t)RG * p.stg_stride;
+        const long long dst_step = (long long)RG * p.Nc;
+#pragma unroll 4
+        for (int r = rg; r < rows_valid; r += RG, src += src_step, dst += dst_step) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src);
+          if (!(dbg & 2)) *reinterpret_cast<uint4*>(dst) = v;
+          if (do_stats) {
+            float f[8];
+            unpack8(v, f);
+            if (kFast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
+            } else {
+              double* d = p.stats + ((size_t)((m0 + r) / p.P) * p.Nc + n0 + cu * 8) * 2;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { atomicAdd(d + 2 * j, (double)f[j]); atomicAdd(d + 2 * j + 1, (double)f[j] * f[j]); }
+            }
+          }
+        }
+      }
+      mbar_arrive(sempty_bar(sb));    // staging tile consumed (release)
+      if (et == 0) TSTAMP(10);
+      if (++sb == p.nbuf) { sb = 0; sphase ^= 1u; }
+    }
+    if (do_stats && kFast && cur_img >= 0) flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---- host side: tensor maps ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; long long M; int K, ld;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && M == o.M && K == o.K && ld == o.ld; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<long long>()(k.M) * 1315423911u) ^ ((size_t)k.K << 20) ^ (size_t)k.ld;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// [M][K] bf16 activation slice with row stride ld: box = 64 channels x 128 rows, 128-byte swizzle, zero fill
+bool activation_map(const void* ptr, long long M, int K, int ld, CUtensorMap* out) {
+  MapKey key{ptr, M, K, ld};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return true;
+}
+
+}  // namespace
+
+int gemm_tc_read_timeline(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_timeline, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : -1;
+}
+
+int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st) {
+  static int use_v1 = -1;
+  if (use_v1 < 0) { const char* e = getenv("LCM_TC_V1"); use_v1 = (e && atoi(e)) ? 1 : 0; }
+  if (use_v1) return launch_gemm_tc_v1(g, cg, block_n, num_sms, st);
+
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  if (block_n < 16 || block_n > 256 || block_n % 16 || g.Nc % block_n) return -1;
+  if (g.M <= 0 || g.M > 0x7fffff00LL || g.P <= 0) return -1;
+  p.nseg = g.nseg;
+  p.W = reinterpret_cast<const bf16*>(g.W);
+  p.out = reinterpret_cast<bf16*>(g.out);
+  p.stats = g.stats;
+  p.M = g.M; p.P = g.P; p.Nc = g.Nc; p.block_n = block_n;
+  p.n_tiles = g.Nc / block_n;
+  p.m_tiles = (g.M + 127) / 128;
+  p.fast = (g.P % 128 == 0) ? 1 : 0;
+  p.conv_mode = cg.mode;
+  int nch = 0, ncoef = 0;
+  if (cg.mode < 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      p.seg[s] = g.seg[s];
+      if (g.seg[s].K % 16 || g.seg[s].ld % 8) return -1;
+      p.coef_base[s] = -1;
+      if (g.seg[s].mode != XF_NONE) { p.coef_base[s] = ncoef; ncoef += g.seg[s].K; }
+      if (!activation_map(g.seg[s].A, g.M, g.seg[s].K, g.seg[s].ld, &p.tmap[s])) return -3;
+      for (int c0 = 0; c0 < g.seg[s].K; c0 += 64) {
+        if (nch >= kMaxChunks2) return -1;
+        const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;
+        p.chunk[nch++] = (uint32_t)s | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
+      }
+    }
+  } else {
+    p.bias = cg.bias;
+    p.seg[0] = g.seg[0];
+    p.Hin = cg.Hin; p.Win = cg.Win; p.Hout = cg.Hout; p.Wout = cg.Wout; p.Ci = cg.Ci;
+    if (cg.Ci % 16) return -1;
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c0 = 0; c0 < cg.Ci; c0 += 64) {
+        if (nch >= kMaxChunks2) return -1;
+        const int kv = cg.Ci - c0 < 64 ? cg.Ci - c0 : 64;
+        p.chunk[nch++] = (uint32_t)tap | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
+      }
+  }
+  p.nchunks = nch;
+  p.ncoef = ncoef;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  // shared-memory layout
+  const uint32_t b_chunk = (uint32_t)block_n * 128u;
+  const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
+  const uint32_t stg_bytes = (128u * stg_stride + 1023u) & ~1023u;
+  const uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
+  const uint32_t base_fixed = coef_bytes + kMisc2 + 1024;
+  const uint32_t bres = (uint32_t)nch * b_chunk;
+  p.resident = (bres <= 98304 && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
+  p.stage_bytes = kStageA2 + (p.resident ? 0u : b_chunk);
+  const uint32_t used1 = base_fixed + stg_bytes + (p.resident ? bres : 0u);
+  p.nbuf = (used1 + stg_bytes + 4 * p.stage_bytes <= kSmemLimit2) ? 2 : 1;
+  const uint32_t used = used1 + (p.nbuf == 2 ? stg_bytes : 0u);
+  if (used >= kSmemLimit2) return -1;
+  int stages = (int)((kSmemLimit2 - used) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -1;
+  p.stages = stages;
+  uint32_t off = (uint32_t)stages * p.stage_bytes;
+  p.bres_off = off; off += p.resident ? bres : 0u;
+  p.stg_off = off; off += (uint32_t)p.nbuf * stg_bytes;
+  p.stg_stride = stg_stride;
+  p.stg_bytes = stg_bytes;
+  p.coef_off = off; off += coef_bytes;
+  p.misc_off = off; off += kMisc2;
+  const uint32_t smem_bytes = off + 1024;
+  if (smem_bytes > kSmemLimit2) return -1;
+  const long long tiles = p.m_tiles * p.n_tiles;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  typedef void (*KernelFn)(const Tc2Params);
+  KernelFn fn;
+  if (p.debug) fn = p.conv_mode >= 0 ? (p.fast ? gemm_tc2_kernel<true, true, true> : gemm_tc2_kernel<true, false, true>)
+                                     : (p.fast ? gemm_tc2_kernel<false, true, true> : gemm_tc2_kernel<false, false, true>);
+  else fn = p.conv_mode >= 0 ? (p.fast ? gemm_tc2_kernel<true, true, false> : gemm_tc2_kernel<true, false, false>)
+                             : (p.fast ? gemm_tc2_kernel<false, true, false> : gemm_tc2_kernel<false, false, false>);
+  static std::unordered_map<void*, bool> attr_done;
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (!attr_done[(void*)fn]) {
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit2) != cudaSuccess) return -2;
+      attr_done[(void*)fn] = true;
+    }
+  }
+  fn<<<grid, kThreads2, smem_bytes, st>>>(p);
+  return 0;
+}
+
+}  // namespace lcm

@@ -120,5 +120,6 @@ struct ConvGeom {   // conv3x3 producer geometry (mode < 0: plain 1x1 GEMM)
 };
 int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_sms, cudaStream_t st);
 int gemm_tc_pick_block_n(int Nc);
+int gemm_tc_read_timeline(long long* host, int n);   // debug: per-tile clock stamps of block 0 (LCM_TC_DEBUG & 64)
 
 }  // namespace lcm

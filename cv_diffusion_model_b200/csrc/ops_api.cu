@@ -32,6 +32,8 @@ int finish(cudaStream_t st) {
 
 extern "C" {
 
+int lcm_debug_timeline(long long* host, int n) { return gemm_tc_read_timeline(host, n); }
+
 int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
                 int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream) {
   if (!segs || nseg < 1 || nseg > LCM_MAX_SEGS || !w_dev || !out_dev || repeat < 1) return LCM_ERR_INVALID;

@@ -65,6 +65,7 @@ SIGNATURES = {
     "lcm_plan_profile_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OpProfileC),
                                            C.c_int]),
+    "lcm_debug_timeline": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "lcm_op_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "lcm_op_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

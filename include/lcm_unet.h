@@ -157,6 +157,8 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
 int lcm_op_conv3x3(const void* in_dev, const float* w_dev, const float* bias_dev, void* out_dev, double* stats_dev,
                    int N, int Hin, int Win, int Ci, int Co, int mode, int precision, int impl, int repeat,
                    float* ms_out, void* stream);
+/* debug aid: clock64 stamps of the tcgen05 GEMM pipeline roles (block 0, first 64 tiles; LCM_TC_DEBUG=64) */
+int lcm_debug_timeline(long long* host, int n);
 /* depthwise 3x3 with relu6(a*x+b) prologue and pooled-sum epilogue (efficient_unet.py:212-223); w_dev [C][1][3][3] */
 int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, double* pool_dev, int N,
                   int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream);

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""GPU diagnostic: per-tile timeline of the tcgen05 GEMM pipeline roles (LCM_TC_DEBUG must include 64)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cv_diffusion_model_b200 import native, ops  # noqa: E402
+
+images, P, Ks, Nc, modes = 64, 65536, [32], 128, [2]
+if len(sys.argv) > 1 and sys.argv[1] == "project":
+    Ks, Nc, modes = [128, 32], 32, [1, 0]
+g = torch.Generator(device="cuda").manual_seed(7)
+M = images * P
+segs = []
+for K, mode in zip(Ks, modes):
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
+                        torch.randn(images, K, device="cuda", generator=g) * 0.3], -1) if mode else None
+    segs.append((a, coef, mode))
+w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / sum(Ks) ** 0.5
+ops.gemm(segs, w, P, impl=1)
+out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True)
+buf = (C.c_longlong * 1024)()
+native.lib().lcm_debug_timeline(buf, 1024)
+t0 = min(buf[i] for i in range(16) if buf[i] > 0)
+names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done"]
+print(f"{ms*1e3:.1f} us;  cycles relative to first stamp")
+print("tile " + " ".join(f"{n:>10s}" for n in names))
+for it in range(0, 40):
+    print(f"{it:4d} " + " ".join(f"{(buf[it*16+s]-t0) if buf[it*16+s] else -1:10d}" for s in range(len(names))))
