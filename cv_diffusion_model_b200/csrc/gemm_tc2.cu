@@ -62,6 +62,7 @@ struct alignas(64) Tc2Params {
   int P, Nc, block_n, n_tiles, nchunks;
   int resident, stages, fast, nbuf;
   int conv_mode, Hin, Win, Hout, Wout, Ci;
+  int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
   uint32_t chunk[kMaxChunks2];  // seg/tap | kvalid << 8 | c0 << 16
@@ -81,6 +82,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // (P % 128 == 0); kDebug: bottleneck-experiment switches and the timeline (never instantiated on the product path
 // unless LCM_TC_DEBUG is set).  Specialising keeps each instantiation's code small: the five roles run different
 // code concurrently and the instruction cache is a real constraint.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
 template <bool kConv, bool kFast, bool kDebug>
 __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (!conv)
-      for (int s = 0; s < p.nseg; ++s)
+      for (int s = 0; s < (p.conv_tma ? 1 : p.nseg); ++s)
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap[s])) : "memory");
   }
   if (warp == 4) {
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         const int stage = ring.stage;
         const uint32_t a_smem = sbase + stage * p.stage_bytes;
         if constexpr (!conv) {
-          const int mode = p.seg[sidx].mode;
+          const int mode = p.conv_tma ? (int)XF_NONE : p.seg[sidx].mode;
           par ^= 1;
           if (par != (group ^ 1)) continue;       // chunks alternate between the two groups
           // Every chunk passes through this stage so that xf_bar completes exactly one phase per use of the
@@ -296,6 +304,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
         }
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
+        int ty0 = 0, tx0 = 0;               // conv_tma: first pixel of this tile inside its image
+        if (p.conv_tma) { ty0 = ti.rem / p.Win; tx0 = ti.rem - ty0 * p.Win; }
         for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
@@ -305,7 +315,14 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const bool load_a = !conv && !(dbg & 1);
           if (elect_one()) {
             mbar_expect_tx(raw_bar(stage), (load_a ? kStageA2 : 0u) + (p.resident ? 0u : b_chunk_bytes));
-            if (load_a) tma_load_2d(a_smem, &p.tmap[cd & 0xff], (int)(cd >> 16), ti.m0, raw_bar(stage));
+            if (load_a) {
+              if (p.conv_tma) {
+                const int tap = cd & 0xff, ky = tap / 3, kx = tap - ky * 3;
+                tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), tx0 + kx - 1, ty0 + ky - 1, ti.img, raw_bar(stage));
+              } else {
+                tma_load_2d(a_smem, &p.tmap[cd & 0xff], (int)(cd >> 16), ti.m0, raw_bar(stage));
+              }
+            }
             if (!p.resident)
               bulk_g2s(a_smem + kStageA2, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, raw_bar(stage));
           }
@@ -545,6 +562,19 @@ bool activation_map(const void* ptr, long long M, int K, int ld, CUtensorMap* ou
   return true;
 }
 
+// NHWC image tensor [N][H][W][C] bf16: box = 64 channels x box_w pixels x box_h rows (box_w * box_h = 128), zero fill
+bool image_map(const void* ptr, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 int gemm_tc_read_timeline(long long* host, int n) {
@@ -588,6 +618,22 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
     p.seg[0] = g.seg[0];
     p.Hin = cg.Hin; p.Win = cg.Win; p.Hout = cg.Hout; p.Wout = cg.Wout; p.Ci = cg.Ci;
     if (cg.Ci % 16) return -1;
+    // stride-1 convs whose 128-pixel tiles are boxes of the image go through TMA (the zero fill of out-of-bounds
+    // coordinates is the conv's zero padding): W >= 128 with 128 | W (tile = part of a row) or W | 128 (whole rows)
+    {
+      static int no_tma = -1;
+      if (no_tma < 0) { const char* e = getenv("LCM_CONV_GATHER"); no_tma = (e && atoi(e)) ? 1 : 0; }
+      const int W = cg.Win, H = cg.Hin;
+      const bool boxable = (W >= 128 ? W % 128 == 0 : 128 % W == 0) && ((long long)H * W) % 128 == 0;
+      if (cg.mode == CONV_S1 && boxable && !no_tma) {
+        const int bw = W >= 128 ? 128 : W, bh = 128 / bw;
+        const long long imgs = g.M / ((long long)H * W);
+        if (!image_map(g.seg[0].A, (int)imgs, H, W, cg.Ci, bw, bh, &p.tmap[0])) return -3;
+        p.conv_tma = 1;
+        p.box_w = bw;
+        p.conv_mode = -1;   // runs the TMA-fed (non-gather) kernel variant
+      }
+    }
     for (int tap = 0; tap < 9; ++tap)
       for (int c0 = 0; c0 < cg.Ci; c0 += 64) {
         if (nch >= kMaxChunks2) return -1;

@@ -42,6 +42,8 @@ enum Conv3Mode : int { CONV_S1 = 0, CONV_S2 = 1, CONV_UP2 = 2 };
 // Hin,Win are the stored input size; output is Hin x Win (S1), Hin/2 (S2, pad 1) or 2*Hin (UP2: bilinear x2 first).
 void launch_conv3x3_simt(const void* in, const void* Wt, const float* bias, void* out, double* stats, int N,
                          int Hin, int Win, int Ci, int Co, int mode, int bf16act, cudaStream_t st);
+// bf16 NHWC bilinear x2 (align_corners=False) materialisation for the tensor-core up-convolution
+void launch_upsample2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t st);
 // init_conv: x = cat([xa, xb]) fp32 NCHW -> NHWC; w fp32 [9*Cin][Co] (k = tap*Cin + ci), bias.
 void launch_init_conv(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const float* w,
                       const float* bias, void* out, double* stats, int N, int H, int W, int Co, int bf16act,

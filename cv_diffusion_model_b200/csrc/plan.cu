@@ -410,7 +410,22 @@ struct Builder {
   }
 
   // ---- Downsample / Upsample (efficient_unet.py:360-384) -------------------------------------
-  TensorP conv3(const std::string& name, const std::string& wname, const TensorP& x, int mode) {
+  TensorP conv3(const std::string& name, const std::string& wname, const TensorP& x_in, int mode_in) {
+    TensorP x = x_in;
+    int mode = mode_in;
+    if (p->tc && mode == CONV_UP2) {
+      // tensor-core path: materialise the bilinear x2 once (memory-bound), then a stride-1 conv whose operand
+      // tiles are TMA boxes; the algorithmic accounting stays with the conv op below.
+      TensorP up = p->new_tensor(x_in->C, x_in->H * 2, x_in->W * 2, false, "");
+      lcm_plan* pl = p; const int n = N;
+      TensorP src = x_in;
+      push(name + ".bilinear", "upsample2x", 0, 0, [=](const RunCtx& c, cudaStream_t st) {
+        launch_upsample2x(c.a + src->off, c.a + up->off, n, src->H, src->W, src->C, st);
+      });
+      p->release(x_in);
+      x = up;
+      mode = CONV_S1;
+    }
     const int C = x->C;
     const int Ho = mode == CONV_S2 ? x->H / 2 : (mode == CONV_UP2 ? x->H * 2 : x->H);
     const int Wo = mode == CONV_S2 ? x->W / 2 : (mode == CONV_UP2 ? x->W * 2 : x->W);
@@ -435,7 +450,8 @@ struct Builder {
     const int Hin = x->H, Win = x->W;
     const double es = (double)p->esz;
     push(name, pl->tc ? "conv3x3_tc" : "conv3x3_simt",
-         ((double)C * Hin * Win + (double)C * Ho * Wo) * N * es + 9.0 * C * C * es, 18.0 * N * Ho * Wo * C * C,
+         ((double)C * (mode_in == CONV_UP2 ? Hin * Win / 4.0 : (double)Hin * Win) + (double)C * Ho * Wo) * N * es + 9.0 * C * C * es,
+         18.0 * N * Ho * Wo * C * C,
          [=](const RunCtx& c, cudaStream_t st) {
            if (pl->tc) {
              GemmParams gp{};
