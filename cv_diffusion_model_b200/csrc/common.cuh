@@ -13,11 +13,14 @@ enum XformMode : int {
   XF_NONE = 0,         // y = x
   XF_AFFINE = 1,       // y = a*x + b                      (GroupNorm, or SE gate with b = 0)
   XF_AFFINE_RELU6 = 2, // y = min(max(a*x + b, 0), 6)      (GroupNorm [+FiLM] then ReLU6)
-  XF_AFFINE_SILU = 3   // y = silu(a*x + b)                (final_norm + SiLU)
+  XF_AFFINE_SILU = 3,  // y = silu(a*x + b)                (final_norm + SiLU)
+  XF_SCALE = 4         // y = a*x                          (SE gate; linear, so the tensor-core GEMM may fold it
+                       //                                   into the weights per image instead of touching A)
 };
 
 __device__ __forceinline__ float xform(float x, float2 ab, int mode) {
   if (mode == XF_NONE) return x;
+  if (mode == XF_SCALE) return ab.x * x;
   float y = fmaf(ab.x, x, ab.y);
   if (mode == XF_AFFINE_RELU6) y = fminf(fmaxf(y, 0.f), 6.f);
   else if (mode == XF_AFFINE_SILU) y = y / (1.f + __expf(-y));

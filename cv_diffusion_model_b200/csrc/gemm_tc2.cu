@@ -62,10 +62,13 @@ struct alignas(64) Tc2Params {
   int P, Nc, block_n, n_tiles, nchunks;
   int resident, stages, fast, nbuf;
   int conv_mode, Hin, Win, Hout, Wout, Ci;
+  int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
+  int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
   uint32_t chunk[kMaxChunks2];  // seg/tap | kvalid << 8 | c0 << 16
+  uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
 };
 
 __device__ long long g_timeline[64 * 16];   // LCM_TC_DEBUG & 64: per-tile clock64 stamps of block 0
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   auto sfull_bar = [&](int b) { return bar0 + 8u * (28 + b); };
   auto sempty_bar = [&](int b) { return bar0 + 8u * (30 + b); };
   const uint32_t bres_bar = bar0 + 8u * 32;
+  const uint32_t bsc_bar = bar0 + 8u * 33;    // weights rescaled by the SE gate of the current image
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 320);
   float* s_sum = reinterpret_cast<float*>(misc + 512);
   float* s_sq = s_sum + 256;
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       mbar_init(sempty_bar(a), kE2Threads);
     }
     mbar_init(bres_bar, 1);
+    mbar_init(bsc_bar, kXfThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (!conv)
       for (int s = 0; s < (p.conv_tma ? 1 : p.nseg); ++s)
@@ -158,7 +163,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     // ================================ XF: prologue transform / conv gather ==========================
     const int ptid = tid - kXfBase;
     const int group = ptid >> 7, gt = ptid & 127;
-    int cur_img = -1;
+    int cur_img = -1, gate_img = -1, gate_nt = -1;
+    uint32_t gate_phase = 0;
     TileIter ti; ti.init(t_begin, m_tiles, p.P);
     Ring ring{0, 0u, p.stages};
     int par = 0;
@@ -174,6 +180,40 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         bar_sync(1, kXfThreads);
         cur_img = ti.img;
       }
+      if (p.wgate && (ti.img != gate_img || ti.n_tile != gate_nt)) {
+        // fold gate[img][k] into the freshly (re)loaded weight tile: W'[co][k] = W[co][k] * gate[k]
+        mbar_wait(bres_bar, gate_phase);
+        gate_phase ^= 1u;
+        for (int ci = 0; ci < p.nchunks; ++ci) {
+          const uint32_t cd = p.chunk[ci];
+          const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
+          if (p.seg[sidx].mode != XF_SCALE) continue;
+          const uint32_t b_smem = sbase + p.bres_off + ci * b_chunk_bytes;
+          for (int u = ptid; u < p.block_n * 8; u += kXfThreads) {
+            const int co = u >> 3, cu = (u & 7) ^ (co & 7);
+            if (cu * 8 < kvalid) {
+              // W' = W * gate is kept to ~16 bits as a bf16 pair (hi, lo): both images are multiplied by the
+              // same A tile, so folding the gate into the weights costs no accuracy (it removes the rounding
+              // of gate * h2 that the A-side prologue would add).
+              float f[8], l[8];
+              unpack8(ld_s(b_smem + (uint32_t)u * 16u), f);
+              const float2* gk = s_coef + p.coef_base[sidx] + c0 + cu * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] *= gk[j].x;
+                l[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+              }
+              st_s(b_smem + (uint32_t)u * 16u, pack8(f));
+              st_s(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes + (uint32_t)u * 16u, pack8(l));
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bsc_bar);
+        gate_img = ti.img;
+        gate_nt = ti.n_tile;
+      }
+      if (p.all_raw) continue;   // nothing per chunk: the MMA warp reads the TMA tiles directly
       int cy = 0, cx = 0, cn = 0;
       const int cm = m0 + gt;
       if constexpr (conv) {
@@ -189,7 +229,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         const int stage = ring.stage;
         const uint32_t a_smem = sbase + stage * p.stage_bytes;
         if constexpr (!conv) {
-          const int mode = p.conv_tma ? (int)XF_NONE : p.seg[sidx].mode;
+          int mode = p.conv_tma ? (int)XF_NONE : p.seg[sidx].mode;
+          if (p.wgate && mode == XF_SCALE) mode = XF_NONE;
           par ^= 1;
           if (par != (group ^ 1)) continue;       // chunks alternate between the two groups
           // Every chunk passes through this stage so that xf_bar completes exactly one phase per use of the
@@ -284,14 +325,14 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     // The whole warp runs the (uniform) control flow so that addresses and barriers live in uniform
     // registers; one elected lane issues the copies.
     {
-      int cur_nt = -1;
+      int cur_nt = -1, cur_img = -1;
       TileIter ti; ti.init(t_begin, m_tiles, p.P);
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
         if (p.resident) {
-          if (ti.n_tile != cur_nt) {
+          if (ti.n_tile != cur_nt || (p.wgate && ti.img != cur_img)) {
             if (it > 0) mbar_wait(tfull_bar(acc), aphase);   // MMAs of the previous tile done: old weights dead
             if (elect_one()) {
               mbar_expect_tx(bres_bar, (uint32_t)p.nchunks * b_chunk_bytes);
@@ -300,6 +341,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             }
             __syncwarp();
             cur_nt = ti.n_tile;
+            cur_img = ti.img;
           }
           if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
         }
@@ -334,17 +376,18 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     // ================================ MMA issuer (warp-uniform control, one elected lane issues) =====
     {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
-      int cur_nt = -1;
+      int cur_nt = -1, cur_img = -1;
       uint32_t bres_phase = 0;
       TileIter ti; ti.init(t_begin, m_tiles, p.P);
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
-        if (p.resident && ti.n_tile != cur_nt) {
-          mbar_wait(bres_bar, bres_phase);
+        if (p.resident && (ti.n_tile != cur_nt || (p.wgate && ti.img != cur_img))) {
+          mbar_wait(p.wgate ? bsc_bar : bres_bar, bres_phase);
           bres_phase ^= 1u;
           cur_nt = ti.n_tile;
+          cur_img = ti.img;
         }
         mbar_wait(tempty_bar(acc), aphase ^ 1u);
         TSTAMP(3);
@@ -353,7 +396,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
-          mbar_wait(xf_bar(stage), ring.phase);
+          mbar_wait(p.all_raw ? raw_bar(stage) : xf_bar(stage), ring.phase);
           if (ci == 0) TSTAMP(4);
           if (conv && !p.resident) mbar_wait(raw_bar(stage), ring.phase);   // streamed weights of a 3x3 conv
           tc_fence_after();
@@ -361,9 +404,13 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const uint32_t a_addr = sbase + stage * p.stage_bytes;
           const uint32_t b_addr = p.resident ? sbase + p.bres_off + ci * b_chunk_bytes : a_addr + kStageA2;
           const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+          const bool gated = p.wgate && p.lo_slot[ci] != 0xff;
+          const uint64_t bl = umma_desc(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes);
           if (elect_one()) {
             for (int k = 0; k < ksteps; ++k)
               umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
+            if (gated)
+              for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
             umma_commit(empty_bar(stage));
             if (ci == p.nchunks - 1) umma_commit(tfull_bar(acc));
           }
@@ -643,6 +690,9 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   }
   p.nchunks = nch;
   p.ncoef = ncoef;
+  bool has_gate = false;
+  if (p.conv_mode < 0 && !p.conv_tma)
+    for (int s2 = 0; s2 < g.nseg; ++s2) has_gate |= g.seg[s2].mode == XF_SCALE;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
@@ -650,8 +700,26 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   const uint32_t stg_bytes = (128u * stg_stride + 1023u) & ~1023u;
   const uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
   const uint32_t base_fixed = coef_bytes + kMisc2 + 1024;
-  const uint32_t bres = (uint32_t)nch * b_chunk;
+  int ngate = 0;
+  for (int ci = 0; ci < nch; ++ci) {
+    p.lo_slot[ci] = 0xff;
+    if (has_gate && g.seg[p.chunk[ci] & 0xff].mode == XF_SCALE) p.lo_slot[ci] = (uint8_t)ngate++;
+  }
+  static int no_wgate = -1;
+  if (no_wgate < 0) { const char* e = getenv("LCM_NO_WGATE"); no_wgate = (e && atoi(e)) ? 1 : 0; }
+  uint32_t bres = (uint32_t)nch * b_chunk;
   p.resident = (bres <= 98304 && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
+  if (has_gate && p.resident && p.fast && !no_wgate) {
+    const uint32_t bres2 = (uint32_t)(nch + ngate) * b_chunk;   // + low-order images of the gated chunks
+    if (bres2 <= 131072 && base_fixed + stg_bytes + bres2 + 3 * kStageA2 <= kSmemLimit2) { p.wgate = 1; bres = bres2; }
+  }
+  p.all_raw = p.conv_tma ? 1 : 0;
+  if (p.conv_mode < 0 && !p.conv_tma) {
+    bool raw = true;
+    for (int s2 = 0; s2 < g.nseg; ++s2)
+      raw &= g.seg[s2].mode == XF_NONE || (p.wgate && g.seg[s2].mode == XF_SCALE);
+    p.all_raw = raw ? 1 : 0;
+  }
   p.stage_bytes = kStageA2 + (p.resident ? 0u : b_chunk);
   const uint32_t used1 = base_fixed + stg_bytes + (p.resident ? bres : 0u);
   p.nbuf = (used1 + stg_bytes + 4 * p.stage_bytes <= kSmemLimit2) ? 2 : 1;

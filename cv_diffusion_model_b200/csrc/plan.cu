@@ -348,7 +348,7 @@ struct Builder {
       GemmW wp = make_w(Co, pk);
       p->add_weight(name + ".project.weight", (int64_t)Co * Ch, mat_job(wp, 0, PACK_MAT, Co, Ch, Ch, 0));
       std::vector<SegSpec> segs;
-      segs.push_back({h2, gate, Ch, 0, XF_AFFINE});
+      segs.push_back({h2, gate, Ch, 0, XF_SCALE});
       int col = 0;
       for (int i = 0; i < x.n; ++i) {
         segs.push_back({x.part[i], 0, 0, 0, XF_NONE});

@@ -147,7 +147,7 @@ typedef struct {
   const void* A;      /* [M][K] activation slice source, channel stride == K                      */
   const void* coef;   /* float2 [images][K] prologue coefficients for this segment, or NULL        */
   int32_t K;
-  int32_t mode;       /* 0 none, 1 a*x+b, 2 relu6(a*x+b), 3 silu(a*x+b)                           */
+  int32_t mode;       /* 0 none, 1 a*x+b, 2 relu6(a*x+b), 3 silu(a*x+b), 4 a*x (SE gate; b must be 0) */
 } lcm_gemm_seg;
 /* out[m][n] = sum_s sum_k xform_s(A_s[m][k]) * W[n][koff_s + k]   (1x1 convs, efficient_unet.py:174,186,199,265,267) */
 int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,

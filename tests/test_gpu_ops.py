@@ -11,6 +11,8 @@ pytestmark = pytest.mark.gpu
 def _xform(x, coef, mode):
     if coef is None or mode == 0:
         return x
+    if mode == 4:          # SE gate: pure scale (the b slot is defined to be 0)
+        return x * coef[..., 0]
     y = x * coef[..., 0] + coef[..., 1]
     if mode == 2:
         y = y.clamp(0, 6)
@@ -47,6 +49,10 @@ GEMM_CASES = [  # (images, P, [K...], Nc, modes)
     (2, 1024, [64], 256, [2]),           # block_n 256 with per-image statistics kept in smem
     (3, 256, [256, 64], 64, [1, 0]),
     (2, 384, [96], 384, [2]),            # block_n 192, P multiple of 128
+    (3, 256, [128, 32], 32, [4, 0]),     # SE-gated project: gate folded into the resident weights per image
+    (2, 384, [384, 64, 32], 32, [4, 0, 0]),
+    (2, 64, [128, 32], 64, [4, 0]),      # same, tile spans images -> A-side gating
+    (2, 128, [1024, 256], 256, [4, 0]),  # weights too large to stay resident -> A-side gating
 ]
 
 
@@ -67,7 +73,7 @@ def test_gemm(images, P, Ks, Nc, modes, dtype, impl):
         coef = None
         if mode != 0:
             coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
-                                torch.randn(images, K, device="cuda", generator=g) * 0.3], dim=-1)
+                                torch.randn(images, K, device="cuda", generator=g) * (0.0 if mode == 4 else 0.3)], dim=-1)
         segs.append((a, coef, mode))
     w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / (sum(Ks) ** 0.5)
     if dtype == torch.bfloat16:
