@@ -82,7 +82,7 @@ struct GemmSeg {
   int coef_ld;
   int coef_off;
   int mode;            // XformMode
-  int pad_;
+  int f16;             // tcgen05 path only: this segment is stored as fp16 (hidden tensors of a block), not bf16
 };
 
 struct GemmParams {
@@ -95,6 +95,7 @@ struct GemmParams {
   long long M;     // rows = images * P
   int P;           // pixels per image
   int Nc;          // output channels
+  int out_f16;     // tcgen05 path only: store the output as fp16 (the expand GEMM's hidden tensor)
 };
 
 }  // namespace lcm

@@ -33,6 +33,7 @@
 
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "tmap.h"
 
 namespace lcm {
 
@@ -575,7 +576,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; long long M; int K, ld;
+  const void* ptr; long long M; int K, ld;   // ld carries the element type in bit 30
   bool operator==(const MapKey& o) const { return ptr == o.ptr && M == o.M && K == o.K && ld == o.ld; }
 };
 struct MapKeyHash {
@@ -587,22 +588,16 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // [M][K] bf16 activation slice with row stride ld: box = 64 channels x 128 rows, 128-byte swizzle, zero fill
-bool activation_map(const void* ptr, long long M, int K, int ld, CUtensorMap* out) {
-  MapKey key{ptr, M, K, ld};
+bool activation_map(const void* ptr, long long M, int K, int ld, bool f16, CUtensorMap* out) {
+  MapKey key{ptr, M, K, ld | (f16 ? (1 << 30) : 0)};
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return true; }
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, 128};
-  cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return false;
+  if (!encode_tmap(&m, f16 ? TMAP_F16 : TMAP_BF16, 2, ptr, gdim, gstride, box, true)) return false;
   if (g_maps.size() > 4096) g_maps.clear();
   g_maps[key] = m;
   *out = m;
@@ -611,18 +606,24 @@ bool activation_map(const void* ptr, long long M, int K, int ld, CUtensorMap* ou
 
 // NHWC image tensor [N][H][W][C] bf16: box = 64 channels x box_w pixels x box_h rows (box_w * box_h = 128), zero fill
 bool image_map(const void* ptr, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  return enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return encode_tmap(out, TMAP_BF16, 4, ptr, gdim, gstride, box, true);
 }
 
 }  // namespace
+
+bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const cuuint64_t* gdim,
+                 const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(out, dtype == TMAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+             const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int gemm_tc_read_timeline(long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_timeline, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : -1;
@@ -653,7 +654,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
       if (g.seg[s].K % 16 || g.seg[s].ld % 8) return -1;
       p.coef_base[s] = -1;
       if (g.seg[s].mode != XF_NONE) { p.coef_base[s] = ncoef; ncoef += g.seg[s].K; }
-      if (!activation_map(g.seg[s].A, g.M, g.seg[s].K, g.seg[s].ld, &p.tmap[s])) return -3;
+      if (!activation_map(g.seg[s].A, g.M, g.seg[s].K, g.seg[s].ld, g.seg[s].f16 != 0, &p.tmap[s])) return -3;
       for (int c0 = 0; c0 < g.seg[s].K; c0 += 64) {
         if (nch >= kMaxChunks2) return -1;
         const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;

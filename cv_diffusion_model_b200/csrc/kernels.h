@@ -32,6 +32,11 @@ void launch_gemm_simt(const GemmParams& p, int bf16act, cudaStream_t st);
 void launch_dwconv(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                    int C, int bf16act, int fast, cudaStream_t st);
 
+// tcgen05 product path: fp16 NHWC in and out (the block's hidden tensors), TMA-streamed rows (dwconv_stream.cu).
+// Returns non-zero when the shape is not supported.
+int launch_dwconv_f16(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
+                      int C, int num_sms, cudaStream_t st);
+
 // ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0) -------------------------------
 void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                     const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st);

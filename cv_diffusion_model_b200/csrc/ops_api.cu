@@ -121,13 +121,18 @@ int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, 
   if (cudaMalloc((void**)&wbuf, (size_t)9 * C * 4) != cudaSuccess) return LCM_ERR_CUDA;
   PackJob j{}; j.kind = PACK_DW; j.dst = wbuf; j.R = C;
   launch_pack(j, w_dev, st);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int bad = 0;
   Timer t(st, ms_out, repeat);
-  for (int r = 0; r < repeat; ++r)
-    launch_dwconv(in_dev, (const float2*)coef_dev, wbuf, out_dev, pool_dev, N, H, W, C, bf, impl, st);
+  for (int r = 0; r < repeat && !bad; ++r) {
+    if (precision == LCM_ACT_F16) bad = launch_dwconv_f16(in_dev, (const float2*)coef_dev, wbuf, out_dev, pool_dev, N, H, W, C, sms, st);
+    else launch_dwconv(in_dev, (const float2*)coef_dev, wbuf, out_dev, pool_dev, N, H, W, C, bf, impl, st);
+  }
   t.stop();
   int rc = finish(st);
   cudaFree(wbuf);
-  return rc;
+  return bad ? LCM_ERR_INVALID : rc;
 }
 
 }  // extern "C"

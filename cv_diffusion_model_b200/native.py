@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "liblcmunet.so")
 
 LCM_MAX_LEVELS = 8
 PREC_FP32, PREC_BF16 = 0, 1
+ACT_F16 = 2   # single-kernel entry points: fp16 hidden tensors of the tensor-core plan
 FLAG_SIMT_GEMM, FLAG_TAPS = 1, 2
 ERR_INVALID, ERR_CUDA, ERR_UNKNOWN_WEIGHT, ERR_MISSING_WEIGHT, ERR_WORKSPACE = -1, -2, -3, -4, -5
 

@@ -21,6 +21,8 @@ def _prec(t: torch.Tensor) -> int:
         return native.PREC_FP32
     if t.dtype == torch.bfloat16:
         return native.PREC_BF16
+    if t.dtype == torch.float16:
+        return native.ACT_F16
     raise ValueError(f"unsupported activation dtype {t.dtype}")
 
 

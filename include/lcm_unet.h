@@ -39,6 +39,9 @@ typedef enum {
 } lcm_status;
 
 typedef enum { LCM_PREC_FP32 = 0, LCM_PREC_BF16 = 1 } lcm_precision;
+/* Activation element type accepted by the single-kernel entry points only: the bf16 tensor-core plan stores the
+ * two hidden tensors of every inverted-residual block (expand output, depthwise output) as fp16. */
+#define LCM_ACT_F16 2
 
 /* plan flags */
 #define LCM_FLAG_SIMT_GEMM 1u     /* bf16 plans: use the CUDA-core GEMM/conv kernels instead of tcgen05 (cross-check) */
@@ -159,7 +162,8 @@ int lcm_op_conv3x3(const void* in_dev, const float* w_dev, const float* bias_dev
                    float* ms_out, void* stream);
 /* debug aid: clock64 stamps of the tcgen05 GEMM pipeline roles (block 0, first 64 tiles; LCM_TC_DEBUG=64) */
 int lcm_debug_timeline(long long* host, int n);
-/* depthwise 3x3 with relu6(a*x+b) prologue and pooled-sum epilogue (efficient_unet.py:212-223); w_dev [C][1][3][3] */
+/* depthwise 3x3 with relu6(a*x+b) prologue and pooled-sum epilogue (efficient_unet.py:212-223); w_dev [C][1][3][3];
+ * precision LCM_ACT_F16 selects the TMA-streamed fp16 kernel of the tensor-core plan (impl ignored) */
 int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, double* pool_dev, int N,
                   int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream);
 

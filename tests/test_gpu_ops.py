@@ -142,3 +142,27 @@ def test_dwconv(N, H, W, C, dtype, impl):
     assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
     pref = ref.sum(dim=(1, 2))
     assert torch.allclose(pool.float(), pref, rtol=2e-3 if dtype == torch.float32 else 2e-2, atol=0.05 * H * W ** 0.5)
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 128), (1, 32, 32, 64), (2, 8, 8, 512), (1, 20, 12, 96), (3, 4, 4, 2048),
+                                     (2, 64, 64, 128), (1, 40, 72, 256), (1, 9, 200, 128), (2, 128, 128, 384), (1, 3, 5, 32)])
+def test_dwconv_f16_stream(N, H, W, C):
+    """TMA-streamed fp16 depthwise kernel of the tensor-core plan (dwconv_stream.cu) vs torch fp32 conv2d."""
+    from cv_diffusion_model_b200 import ops
+    if os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).half()
+    coef = torch.stack([torch.rand(N, C, device="cuda", generator=g) + 0.5, torch.randn(N, C, device="cuda", generator=g)], dim=-1)
+    w = torch.randn(C, 1, 3, 3, device="cuda", generator=g) / 3
+    out, pool = ops.dwconv(x, coef, w)
+    assert out.dtype == torch.float16
+    a = (x.float() * coef[:, None, None, :, 0] + coef[:, None, None, :, 1]).clamp(0, 6).permute(0, 3, 1, 2)
+    ref = F.conv2d(a, w, padding=1, groups=C).permute(0, 2, 3, 1)
+    # fp16 prologue (coefficients and result rounded to 11 bits), fp16 taps and accumulation, fp16 store
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.012 * max(1.0, ref.abs().max().item()), err
+    rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel < 2e-3, rel
+    pref = ref.sum(dim=(1, 2))
+    assert torch.allclose(pool.float(), pref, rtol=5e-3, atol=0.01 * H * W ** 0.5), (pool.float() - pref).abs().max()
