@@ -63,12 +63,13 @@ struct alignas(64) Tc2Params {
   int P, Nc, block_n, n_tiles, nchunks;
   int resident, stages, fast, nbuf;
   int conv_mode, Hin, Win, Hout, Wout, Ci;
+  int out_f16;           // store the output (and take its statistics) as fp16
   int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
   int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
-  uint32_t chunk[kMaxChunks2];  // seg/tap | kvalid << 8 | c0 << 16
+  uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
   uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
 };
 
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         gate_phase ^= 1u;
         for (int ci = 0; ci < p.nchunks; ++ci) {
           const uint32_t cd = p.chunk[ci];
-          const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
+          const int sidx = cd & 0x7f, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
           if (p.seg[sidx].mode != XF_SCALE) continue;
           const uint32_t b_smem = sbase + p.bres_off + ci * b_chunk_bytes;
           for (int u = ptid; u < p.block_n * 8; u += kXfThreads) {
@@ -197,15 +198,17 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               // same A tile, so folding the gate into the weights costs no accuracy (it removes the rounding
               // of gate * h2 that the A-side prologue would add).
               float f[8], l[8];
-              unpack8(ld_s(b_smem + (uint32_t)u * 16u), f);
+              const bool h16 = p.seg[sidx].f16 != 0;   // weights of an fp16 segment are packed as fp16
+              const uint4 wraw = ld_s(b_smem + (uint32_t)u * 16u);
+              if (h16) unpack8h(wraw, f); else unpack8(wraw, f);
               const float2* gk = s_coef + p.coef_base[sidx] + c0 + cu * 8;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 f[j] *= gk[j].x;
-                l[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+                l[j] = f[j] - (h16 ? __half2float(__float2half_rn(f[j])) : __bfloat162float(__float2bfloat16_rn(f[j])));
               }
-              st_s(b_smem + (uint32_t)u * 16u, pack8(f));
-              st_s(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes + (uint32_t)u * 16u, pack8(l));
+              st_s(b_smem + (uint32_t)u * 16u, h16 ? pack8h(f) : pack8(f));
+              st_s(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes + (uint32_t)u * 16u, h16 ? pack8h(l) : pack8(l));
             }
           }
         }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       }
       for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
         const uint32_t cd = p.chunk[ci];
-        const int sidx = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
+        const int sidx = cd & 0x7f, kvalid = (cd >> 8) & 0xff, c0 = cd >> 16;
         const int upr = kvalid >> 3;
         const int stage = ring.stage;
         const uint32_t a_smem = sbase + stage * p.stage_bytes;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 if (dbg & 256) {
                   o = v[i];
                 } else if (kFast) {
-                  o = apply_xform(v[i], s_coef + p.coef_base[sidx] + c0 + cu * 8, mode);
+                  o = apply_xform(v[i], s_coef + p.coef_base[sidx] + c0 + cu * 8, mode, sg.f16 != 0);
                 } else {
                   const int mrow = min(m0 + row, M - 1);
                   const int img = mrow / p.P;
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                   const float2* src = sg.coef + (size_t)img * sg.coef_ld + sg.coef_off + c0 + cu * 8;
 #pragma unroll
                   for (int j = 0; j < 8; ++j) ab[j] = src[j];
-                  o = apply_xform(v[i], ab, mode);
+                  o = apply_xform(v[i], ab, mode, sg.f16 != 0);
                 }
                 st_s(a_smem + (uint32_t)u * 16u, o);
               }
@@ -360,10 +363,10 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             mbar_expect_tx(raw_bar(stage), (load_a ? kStageA2 : 0u) + (p.resident ? 0u : b_chunk_bytes));
             if (load_a) {
               if (p.conv_tma) {
-                const int tap = cd & 0xff, ky = tap / 3, kx = tap - ky * 3;
+                const int tap = cd & 0x7f, ky = tap / 3, kx = tap - ky * 3;
                 tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), tx0 + kx - 1, ty0 + ky - 1, ti.img, raw_bar(stage));
               } else {
-                tma_load_2d(a_smem, &p.tmap[cd & 0xff], (int)(cd >> 16), ti.m0, raw_bar(stage));
+                tma_load_2d(a_smem, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
               }
             }
             if (!p.resident)
@@ -376,7 +379,9 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   } else if (warp == 4) {
     // ================================ MMA issuer (warp-uniform control, one elected lane issues) =====
     {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
+      // D = f32; A/B element format (bits 7-9 / 10-12): 1 = bf16, 0 = f16 (chunks of an fp16 segment)
+      const uint32_t idesc_h = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | (8u << 24);
+      const uint32_t idesc_b = idesc_h | (1u << 7) | (1u << 10);
       int cur_nt = -1, cur_img = -1;
       uint32_t bres_phase = 0;
       TileIter ti; ti.init(t_begin, m_tiles, p.P);
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const uint32_t b_addr = p.resident ? sbase + p.bres_off + ci * b_chunk_bytes : a_addr + kStageA2;
           const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
           const bool gated = p.wgate && p.lo_slot[ci] != 0xff;
+          const uint32_t idesc = (cd & 0x80u) ? idesc_h : idesc_b;
           const uint64_t bl = umma_desc(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes);
           if (elect_one()) {
             for (int k = 0; k < ksteps; ++k)
@@ -459,8 +465,13 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             for (int j = 0; j < 16; ++j) f[j] += s_bias[cb + h * 16 + j];
           }
           const uint32_t dst = my_row + (cb + h * 16) * 2;
-          st_s(dst, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
-          st_s(dst + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
+          if (p.out_f16) {
+            st_s(dst, make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7])));
+            st_s(dst + 16, make_uint4(pack_f16(f[8], f[9]), pack_f16(f[10], f[11]), pack_f16(f[12], f[13]), pack_f16(f[14], f[15])));
+          } else {
+            st_s(dst, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+            st_s(dst + 16, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
+          }
         }
       }
       tc_fence_before();
@@ -530,7 +541,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (!(dbg & 2)) *reinterpret_cast<uint4*>(dst) = v;
           if (do_stats) {
             float f[8];
-            unpack8(v, f);
+            if (p.out_f16) unpack8h(v, f); else unpack8(v, f);
             if (kFast) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { cs[j] += f[j]; cq[j] = fmaf(f[j], f[j], cq[j]); }
@@ -643,6 +654,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   p.out = reinterpret_cast<bf16*>(g.out);
   p.stats = g.stats;
   p.M = g.M; p.P = g.P; p.Nc = g.Nc; p.block_n = block_n;
+  p.out_f16 = g.out_f16;
   p.n_tiles = g.Nc / block_n;
   p.m_tiles = (g.M + 127) / 128;
   p.fast = (g.P % 128 == 0) ? 1 : 0;
@@ -658,7 +670,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
       for (int c0 = 0; c0 < g.seg[s].K; c0 += 64) {
         if (nch >= kMaxChunks2) return -1;
         const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;
-        p.chunk[nch++] = (uint32_t)s | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
+        p.chunk[nch++] = (uint32_t)s | (g.seg[s].f16 ? 0x80u : 0u) | ((uint32_t)kv << 8) | ((uint32_t)c0 << 16);
       }
     }
   } else {
@@ -704,7 +716,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   int ngate = 0;
   for (int ci = 0; ci < nch; ++ci) {
     p.lo_slot[ci] = 0xff;
-    if (has_gate && g.seg[p.chunk[ci] & 0xff].mode == XF_SCALE) p.lo_slot[ci] = (uint8_t)ngate++;
+    if (has_gate && g.seg[p.chunk[ci] & 0x7f].mode == XF_SCALE) p.lo_slot[ci] = (uint8_t)ngate++;
   }
   static int no_wgate = -1;
   if (no_wgate < 0) { const char* e = getenv("LCM_NO_WGATE"); no_wgate = (e && atoi(e)) ? 1 : 0; }

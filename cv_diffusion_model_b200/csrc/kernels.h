@@ -37,9 +37,9 @@ void launch_dwconv(const void* in, const float2* coef, const float* w, void* out
 int launch_dwconv_f16(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                       int C, int num_sms, cudaStream_t st);
 
-// ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0) -------------------------------
+// ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0); hid = scratch [N][SQ] (2 launches) -----
 void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
-                    const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st);
+                    const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st);
 
 // ---- a3/a6/a7: dense 3x3 convs ------------------------------------------------------------------
 enum Conv3Mode : int { CONV_S1 = 0, CONV_S2 = 1, CONV_UP2 = 2 };
@@ -94,7 +94,7 @@ enum WLayout : int { WL_ROWMAJOR = 0, WL_UMMA = 1 };
 struct PackJob {
   int kind;
   int layout;      // WLayout (for logical-matrix kinds)
-  int bf16;        // destination element type for logical-matrix kinds
+  int bf16;        // destination element type for logical-matrix kinds: 0 fp32, 1 bf16, 2 fp16 (fp16 segments of a tcgen05 GEMM)
   void* dst;       // plan-time: byte offset in the weight arena; resolved to a pointer before launch
   int R, Cc, Ci;   // rows (out channels), columns taken from this source, conv input channels
   int src_ld;      // PACK_MAT: source row stride (elements)
@@ -115,7 +115,7 @@ __host__ __device__ inline long long umma_weight_offset(int n, int k, int Ktot, 
   return base + (long long)r * 64 + unit * 8 + (kk % 8);
 }
 
-// NHWC (storage type) -> fp32 NCHW, for taps
+// NHWC (storage type: bf16act 0 fp32, 1 bf16, 2 fp16) -> fp32 NCHW, for taps
 void launch_nhwc_to_nchw(const void* in, float* out, int N, int H, int W, int C, int bf16act, cudaStream_t st);
 
 // ---- tcgen05 kernels (gemm_tcgen05.cu) ------------------------------------------------------------------

@@ -1,6 +1,8 @@
 // Small kernels of the hot path: time embedding, FiLM, GroupNorm finalise, SE gate, scheduler step,
 // weight packing, layout conversion.  None of these moves a full activation tensor; they exist so
 // that the heavy kernels' prologues are a single per-(image, channel) affine.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace lcm {
@@ -123,38 +125,58 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Squeeze-and-Excitation gate (efficient_unet.py:96-100).  One block per image; fc weights fp32
-// [SQ][C] and [C][SQ].  Output is a prologue coefficient (gate, 0) for the project GEMM.
-__global__ void se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __restrict__ w1,
-                               const float* __restrict__ b1, const float* __restrict__ w2,
-                               const float* __restrict__ b2, float2* __restrict__ coef, int C, int SQ) {
-  extern __shared__ float sm[];
-  float* mean = sm;       // [C]
-  float* hid = sm + C;    // [SQ]
-  const int n = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = (float)pool[(size_t)n * C + c] * inv_count;
-  __syncthreads();
-  for (int j = warp; j < SQ; j += nw) {
+// Squeeze-and-Excitation gate (efficient_unet.py:96-100) as two batched row-GEMVs:
+//   hid[n][j]  = relu6(b1[j] + sum_c w1[j][c] * mean[n][c])          (mean = pooled sum * inv_count)
+//   gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * hid[n][j])         -> prologue coefficient (gate, 0)
+// One warp owns one weight row for a chunk of 16 images (the row stays in L1 while the images stream through), so
+// the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per 16 images instead of once per image.
+template <bool kFirst>
+__global__ void __launch_bounds__(256) se_fc_kernel(const void* __restrict__ in_, float scale, const float* __restrict__ W,
+                                                    const float* __restrict__ bias, void* __restrict__ out_, int N, int R,
+                                                    int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  const int n0 = blockIdx.y * 16, n1 = min(N, n0 + 16);
+  if (r >= R) return;
+  const float* wr = W + (size_t)r * K;
+  const float b = bias[r];
+  for (int n = n0; n < n1; ++n) {
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], mean[c], acc);
+    if ((K & 3) == 0) {
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+        float x0, x1, x2, x3;
+        if (kFirst) {
+          const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(in_) + (size_t)n * K + k);
+          const double2 a = p[0], c = p[1];
+          x0 = (float)a.x * scale; x1 = (float)a.y * scale; x2 = (float)c.x * scale; x3 = (float)c.y * scale;
+        } else {
+          const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in_) + (size_t)n * K + k);
+          x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w;
+        }
+        acc = fmaf(w4.x, x0, acc); acc = fmaf(w4.y, x1, acc); acc = fmaf(w4.z, x2, acc); acc = fmaf(w4.w, x3, acc);
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float x = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)n * K + k] * scale
+                               : reinterpret_cast<const float*>(in_)[(size_t)n * K + k];
+        acc = fmaf(wr[k], x, acc);
+      }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) hid[j] = fminf(fmaxf(acc + b1[j], 0.f), 6.f);
-  }
-  __syncthreads();
-  for (int c = warp; c < C; c += nw) {
-    float acc = 0.f;
-    for (int j = lane; j < SQ; j += 32) acc = fmaf(w2[(size_t)c * SQ + j], hid[j], acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) coef[(size_t)n * C + c] = make_float2(1.f / (1.f + expf(-(acc + b2[c]))), 0.f);
+    if (lane == 0) {
+      if (kFirst) reinterpret_cast<float*>(out_)[(size_t)n * R + r] = fminf(fmaxf(acc + b, 0.f), 6.f);
+      else reinterpret_cast<float2*>(out_)[(size_t)n * R + r] = make_float2(1.f / (1.f + expf(-(acc + b))), 0.f);
+    }
   }
 }
 
 void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
-                    const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st) {
-  se_gate_kernel<<<N, 512, (C + SQ) * sizeof(float), st>>>(pool, inv_count, w1, b1, w2, b2, coef, C, SQ);
+                    const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st) {
+  const int chunks = (N + 15) / 16;
+  se_fc_kernel<true><<<dim3((SQ + 7) / 8, chunks), 256, 0, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
+  se_fc_kernel<false><<<dim3((C + 7) / 8, chunks), 256, 0, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -203,10 +225,12 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 
 // ------------------------------------------------------------------------------------------------
 // Weight packing: fp32 state_dict tensors -> the layouts the kernels read.
-template <typename T>
-__device__ __forceinline__ void put_logical(const PackJob& j, int n, int k, float v) {
+// destination element type of a logical-matrix job: PackJob::bf16 = 0 fp32, 1 bf16, 2 fp16
+__device__ __forceinline__ void put_any(const PackJob& j, int n, int k, float v) {
   long long o = (j.layout == WL_UMMA) ? umma_weight_offset(n, k, j.ld, j.block_n) : (long long)n * j.ld + k;
-  reinterpret_cast<T*>(j.dst)[o] = from_f<T>(v);
+  if (j.bf16 == 1) reinterpret_cast<bf16*>(j.dst)[o] = __float2bfloat16_rn(v);
+  else if (j.bf16 == 2) reinterpret_cast<__half*>(j.dst)[o] = __float2half_rn(v);
+  else reinterpret_cast<float*>(j.dst)[o] = v;
 }
 
 __global__ void pack_kernel(PackJob j, const float* __restrict__ src, long long total) {
@@ -219,13 +243,13 @@ __global__ void pack_kernel(PackJob j, const float* __restrict__ src, long long 
       case PACK_MAT: {
         int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
         const float v = src[(size_t)r * j.src_ld + j.src_col0 + c];
-        if (j.bf16) put_logical<bf16>(j, r, j.off + c, v); else put_logical<float>(j, r, j.off + c, v);
+        put_any(j, r, j.off + c, v);
         break;
       }
       case PACK_IDENTITY: {
         int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
         float v = (r == c) ? 1.f : 0.f;
-        if (j.bf16) put_logical<bf16>(j, r, j.off + c, v); else put_logical<float>(j, r, j.off + c, v);
+        put_any(j, r, j.off + c, v);
         break;
       }
       case PACK_CONV3: {  // src [Co][Ci][3][3]
@@ -233,7 +257,7 @@ __global__ void pack_kernel(PackJob j, const float* __restrict__ src, long long 
         long long q = i / 9;
         int ci = (int)(q % j.Ci), co = (int)(q / j.Ci);
         int k = j.off + tap * j.tap_stride + ci;
-        if (j.bf16) put_logical<bf16>(j, co, k, src[i]); else put_logical<float>(j, co, k, src[i]);
+        put_any(j, co, k, src[i]);
         break;
       }
       case PACK_CONV3_KN: {
@@ -267,6 +291,7 @@ void launch_pack(const PackJob& job, const float* src, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int HW, int C, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -282,7 +307,8 @@ void launch_nhwc_to_nchw(const void* in, float* out, int N, int H, int W, int C,
   long long total = (long long)N * H * W * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  if (bf16act) nhwc_to_nchw_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)in, out, H * W, C, total);
+  if (bf16act == 2) nhwc_to_nchw_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)in, out, H * W, C, total);
+  else if (bf16act) nhwc_to_nchw_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)in, out, H * W, C, total);
   else nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, out, H * W, C, total);
 }
 

@@ -38,8 +38,12 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
                 int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream) {
   if (!segs || nseg < 1 || nseg > LCM_MAX_SEGS || !w_dev || !out_dev || repeat < 1) return LCM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool out16 = (impl & 0x100) != 0;
+  impl &= 0xff;
   const bool bf = precision == LCM_PREC_BF16, tc = bf && impl == 1;
+  if (!tc && out16) return LCM_ERR_INVALID;
   GemmParams gp{};
+  gp.out_f16 = out16 ? 1 : 0;
   int Ktot = 0, Kpad = 0;
   std::vector<int> off, poff;
   for (int i = 0; i < nseg; ++i) { off.push_back(Ktot); poff.push_back(Kpad); Ktot += segs[i].K; Kpad += (segs[i].K + 63) / 64 * 64; }
@@ -50,12 +54,14 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   cudaMemsetAsync(wbuf, 0, wbytes, st);
   for (int i = 0; i < nseg; ++i) {
     PackJob j{};
-    j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = bf; j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
+    if (segs[i].f16 && !tc) { cudaFree(wbuf); return LCM_ERR_INVALID; }
+    j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = segs[i].f16 ? 2 : (bf ? 1 : 0); j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
     j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = tc ? Kpad : Ktot; j.off = tc ? poff[i] : off[i]; j.block_n = block_n;
     launch_pack(j, w_dev, st);
     gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
     gp.seg[i].coef = (const float2*)segs[i].coef; gp.seg[i].coef_ld = segs[i].K; gp.seg[i].coef_off = 0;
     gp.seg[i].mode = segs[i].coef ? segs[i].mode : XF_NONE;
+    gp.seg[i].f16 = segs[i].f16 ? 1 : 0;
   }
   gp.nseg = nseg; gp.Ktot = Ktot; gp.W = wbuf; gp.out = out_dev; gp.stats = stats_dev; gp.M = M; gp.P = P; gp.Nc = Nc;
   int dev = 0, sms = 148;

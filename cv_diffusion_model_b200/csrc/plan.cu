@@ -49,6 +49,7 @@ struct Tensor {
   size_t off = 0;        // byte offset in region A
   size_t bytes = 0;
   int C = 0, H = 0, W = 0;
+  bool f16 = false;      // stored as fp16 (hidden tensors of a block on the tcgen05 path), else the plan's type
   size_t stats_off = 0;  // byte offset of double[N][C][2] in region Z
   int refs = 0;
 };
@@ -68,6 +69,7 @@ typedef std::function<void(const RunCtx&, cudaStream_t)> RunFn;
 struct Op {
   std::string name, kernel;
   double bytes = 0, flops = 0;
+  int launches = 1;   // kernels this op enqueues
   RunFn run;
 };
 
@@ -157,9 +159,9 @@ struct lcm_plan {
     if (C % g == 0) return g;
     return cfg.groupnorm_gcd ? gcd_i(32, C) : -1;
   }
-  TensorP new_tensor(int C, int h, int w, bool stats, const std::string& tap) {
+  TensorP new_tensor(int C, int h, int w, bool stats, const std::string& tap, bool f16 = false) {
     TensorP t = std::make_shared<Tensor>();
-    t->C = C; t->H = h; t->W = w;
+    t->C = C; t->H = h; t->W = w; t->f16 = f16;
     t->bytes = (size_t)N * h * w * C * esz;
     t->off = pool.alloc(t->bytes);
     t->refs = 1;
@@ -225,11 +227,11 @@ struct Builder {
     return g;
   }
   // job that writes columns [src_col0, src_col0+Cc) of a [R][src_ld] source into segment `seg`
-  PackJob mat_job(const GemmW& g, int seg, int kind, int R, int Cc, int src_ld, int src_col0) {
+  PackJob mat_job(const GemmW& g, int seg, int kind, int R, int Cc, int src_ld, int src_col0, bool f16 = false) {
     PackJob j{};
     j.kind = kind;
     j.layout = p->tc ? WL_UMMA : WL_ROWMAJOR;
-    j.bf16 = p->bf16 ? 1 : 0;
+    j.bf16 = f16 ? 2 : (p->bf16 ? 1 : 0);   // weights of an fp16 activation segment are fp16 too
     j.dst = (void*)g.off;
     j.R = R; j.Cc = Cc; j.src_ld = src_ld; j.src_col0 = src_col0;
     j.ld = p->tc ? g.Kpad : g.Ktot;
@@ -272,6 +274,7 @@ struct Builder {
         gp.seg[i].coef_ld = sg[i].coef_ld;
         gp.seg[i].coef_off = sg[i].coef_off;
         gp.seg[i].mode = sg[i].mode;
+        gp.seg[i].f16 = sg[i].t->f16 ? 1 : 0;
       }
       gp.Ktot = w.Ktot;
       gp.W = pl->wbase + w.off;
@@ -280,6 +283,7 @@ struct Builder {
       gp.P = out->H * out->W;
       gp.M = (long long)n * gp.P;
       gp.Nc = w.Nc;
+      gp.out_f16 = out->f16 ? 1 : 0;
       if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });
@@ -298,7 +302,9 @@ struct Builder {
 
     // norm1 -> ReLU6 -> expand (:207-209)
     const size_t coef1 = gn_coef(name + ".norm1", x, name + ".norm1", -1);
-    TensorP h1 = p->new_tensor(Ch, h, w, true, name + ".expand");
+    // tcgen05 path: both hidden tensors are fp16 (dwconv_stream.cu explains why)
+    const bool hid16 = p->tc;
+    TensorP h1 = p->new_tensor(Ch, h, w, true, name + ".expand", hid16);
     {
       std::vector<int> segK;
       for (int i = 0; i < x.n; ++i) segK.push_back(x.part[i]->C);
@@ -314,7 +320,7 @@ struct Builder {
     }
     // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
     const size_t coef2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
-    TensorP h2 = p->new_tensor(Ch, h, w, false, name + ".depthwise");
+    TensorP h2 = p->new_tensor(Ch, h, w, false, name + ".depthwise", hid16);
     const size_t pool = p->zalloc((size_t)N * Ch * sizeof(double));
     const size_t dw_off = p->walloc((size_t)9 * Ch * sizeof(float));
     { PackJob j{}; j.kind = PACK_DW; j.dst = (void*)dw_off; j.R = Ch; p->add_weight(name + ".depthwise.weight", (int64_t)Ch * 9, j); }
@@ -322,13 +328,19 @@ struct Builder {
       lcm_plan* pl = p; const int n = N;
       push(name + ".depthwise", "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
            [=](const RunCtx& c, cudaStream_t st) {
-             launch_dwconv(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
-                           (double*)(c.z + pool), n, h, w, Ch, pl->bf16, pl->bf16 && pl->tc, st);
+             if (hid16) {
+               if (launch_dwconv_f16(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
+                                     (double*)(c.z + pool), n, h, w, Ch, pl->num_sms, st)) *c.launch_err = 1;
+             } else {
+               launch_dwconv(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
+                             (double*)(c.z + pool), n, h, w, Ch, pl->bf16, 0, st);
+             }
            });
     }
     p->release(h1);
     // SE gate (:98-99)
     const size_t gate = p->falloc((size_t)N * Ch * sizeof(float2));
+    const size_t se_hid = p->falloc((size_t)N * SQ * sizeof(float));
     const size_t w1 = p->add_copy(name + ".se.fc1.weight", (int64_t)SQ * Ch), b1 = p->add_copy(name + ".se.fc1.bias", SQ);
     const size_t w2 = p->add_copy(name + ".se.fc2.weight", (int64_t)Ch * SQ), b2 = p->add_copy(name + ".se.fc2.bias", Ch);
     {
@@ -336,8 +348,9 @@ struct Builder {
       push(name + ".se", "se_gate", 2.0 * Ch * SQ * 4 + 8.0 * N * Ch, 4.0 * N * Ch * SQ,
            [=](const RunCtx& c, cudaStream_t st) {
              launch_se_gate((const double*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2), pl->wf(b2),
-                            (float2*)(c.f + gate), n, Ch, SQ, st);
+                            (float*)(c.f + se_hid), (float2*)(c.f + gate), n, Ch, SQ, st);
            });
+      p->ops.back().launches = 2;
     }
     // SE scale -> project -> + (skip conv | identity)(x)  (:100,226,230-234) as ONE GEMM over [h2 | x]
     TensorP out = p->new_tensor(Co, h, w, true, name + ".out");
@@ -346,7 +359,7 @@ struct Builder {
       pk.push_back(Ch);
       for (int i = 0; i < x.n; ++i) pk.push_back(x.part[i]->C);
       GemmW wp = make_w(Co, pk);
-      p->add_weight(name + ".project.weight", (int64_t)Co * Ch, mat_job(wp, 0, PACK_MAT, Co, Ch, Ch, 0));
+      p->add_weight(name + ".project.weight", (int64_t)Co * Ch, mat_job(wp, 0, PACK_MAT, Co, Ch, Ch, 0, hid16));
       std::vector<SegSpec> segs;
       segs.push_back({h2, gate, Ch, 0, XF_SCALE});
       int col = 0;
@@ -840,12 +853,16 @@ int lcm_plan_read_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, voi
   if (it == plan->tap_map.end()) return fail(LCM_ERR_INVALID, "unknown tap '%s' (plan created without LCM_FLAG_TAPS?)", name);
   RunCtx c = make_ctx(plan, workspace);
   const TensorP& t = it->second;
-  launch_nhwc_to_nchw(c.a + t->off, out_nchw_dev, plan->N, t->H, t->W, t->C, plan->bf16, (cudaStream_t)stream);
+  launch_nhwc_to_nchw(c.a + t->off, out_nchw_dev, plan->N, t->H, t->W, t->C, t->f16 ? 2 : (plan->bf16 ? 1 : 0), (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int lcm_plan_launches_per_forward(const lcm_plan* plan) { return plan ? (int)plan->ops.size() + 1 : 0; }
+int lcm_plan_launches_per_forward(const lcm_plan* plan) {   // kernels of this library (the workspace memset is not counted)
+  int n = 0;
+  if (plan) for (const Op& o : plan->ops) n += o.launches;
+  return n;
+}
 double lcm_plan_algorithmic_bytes(const lcm_plan* plan) { return plan ? plan->total_bytes : 0; }
 double lcm_plan_algorithmic_flops(const lcm_plan* plan) { return plan ? plan->total_flops : 0; }
 

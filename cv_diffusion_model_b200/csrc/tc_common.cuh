@@ -1,5 +1,7 @@
 // PTX wrappers and small device helpers shared by the tcgen05 kernels.
 #pragma once
+#include <cuda_fp16.h>
+
 #include <cstdio>
 
 #include "common.cuh"
@@ -18,14 +20,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit expires; the hint raises that limit so
+// that a waiting role costs (almost) no issue slots — with the default limit, spinning waiters executed a
+// quarter of all instructions of the GEMM kernel (ncu, round 1).
+constexpr uint32_t kSuspendHintNs = 200000;
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -48,9 +54,9 @@ static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) 
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  uint32_t spins = 0;
+  const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 26)) mbar_timeout(bar, parity);   // try_wait itself sleeps in hardware between probes
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);   // ~2 s: a protocol bug, not a slow producer
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -116,12 +122,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+// fp16 flavours (hidden tensors of the inverted-residual block)
+__device__ __forceinline__ void unpack8h(uint4 u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 v = __half22float2(h[j]); f[2 * j] = v.x; f[2 * j + 1] = v.y; }
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  // satfinite: an out-of-range value becomes +-65504 instead of inf (GroupNorm statistics stay finite)
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
+  return make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
+}
+
 // 16 bytes of activations through the prologue: coef = 8 x (a, b).  XF_AFFINE and XF_AFFINE_RELU6 share one
 // instruction stream (clamp bounds are +-inf for the plain affine) to keep the code small; SiLU is only
 // used by the final conv, which has its own kernel.
-__device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mode) {
+__device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mode, bool f16 = false) {
   float f[8];
-  unpack8(raw, f);
+  if (f16) unpack8h(raw, f); else unpack8(raw, f);
   const float4* c4 = reinterpret_cast<const float4*>(ab);
   const float lo = mode == XF_AFFINE_RELU6 ? 0.f : -3.0e38f, hi = mode == XF_AFFINE_RELU6 ? 6.f : 3.0e38f;
 #pragma unroll
@@ -130,7 +152,7 @@ __device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mo
     f[2 * j] = fminf(fmaxf(fmaf(c.x, f[2 * j], c.y), lo), hi);
     f[2 * j + 1] = fminf(fmaxf(fmaf(c.z, f[2 * j + 1], c.w), lo), hi);
   }
-  return pack8(f);
+  return f16 ? pack8h(f) : pack8(f);
 }
 
 __device__ __forceinline__ int div_upr(int u, int upr) {

@@ -29,7 +29,8 @@ class UNetConfigC(C.Structure):
 
 
 class GemmSegC(C.Structure):
-    _fields_ = [("A", C.c_void_p), ("coef", C.c_void_p), ("K", C.c_int32), ("mode", C.c_int32)]
+    _fields_ = [("A", C.c_void_p), ("coef", C.c_void_p), ("K", C.c_int32), ("mode", C.c_int32), ("f16", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class OpProfileC(C.Structure):

@@ -31,10 +31,12 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def gemm(segs: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], int]], weight: torch.Tensor, pixels_per_image: int,
-         impl: int = 0, want_stats: bool = True, repeat: int = 1, timing: bool = False):
+         impl: int = 0, want_stats: bool = True, repeat: int = 1, timing: bool = False, out_f16: bool = False):
     """segs: [(A [M,K] activations, coef [images,K,2] fp32 or None, mode)], weight fp32 [Nc, sum K].
-    Returns (out [M,Nc], stats [images,Nc,2] float64 or None[, ms])."""
-    a0 = segs[0][0]
+    With impl=1 a segment may be torch.float16 (a block's hidden tensor) among bfloat16 ones, and out_f16 stores
+    the result as fp16.  Returns (out [M,Nc], stats [images,Nc,2] float64 or None[, ms])."""
+    a0 = next((a for a, _, _ in segs if a.dtype != torch.float16), segs[0][0])
+    plan_dtype = torch.bfloat16 if a0.dtype == torch.float16 else a0.dtype
     M, Nc = a0.shape[0], weight.shape[0]
     images = M // pixels_per_image
     arr = (native.GemmSegC * len(segs))()
@@ -51,13 +53,16 @@ def gemm(segs: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], int]], weigh
             arr[i].coef = None
         arr[i].K = a.shape[1]
         arr[i].mode = mode
+        arr[i].f16 = 1 if a.dtype == torch.float16 else 0
     w = weight.to(torch.float32).contiguous()
-    out = torch.empty(M, Nc, dtype=a0.dtype, device=a0.device)
+    out = torch.empty(M, Nc, dtype=torch.float16 if out_f16 else plan_dtype, device=a0.device)
     stats = torch.zeros(images, Nc, 2, dtype=torch.float64, device=a0.device) if want_stats else None
     ms = C.c_float(0)
     with torch.cuda.device(a0.device):
+        prec = native.PREC_BF16 if plan_dtype == torch.bfloat16 else native.PREC_FP32
         native.check(native.lib().lcm_op_gemm(arr, len(segs), _p(w), _p(out), _p(stats), M, pixels_per_image, Nc,
-                                              _prec(a0), impl, repeat, C.byref(ms) if timing else None, _stream_ptr()))
+                                              prec, impl | (0x100 if out_f16 else 0), repeat,
+                                              C.byref(ms) if timing else None, _stream_ptr()))
     return (out, stats, ms.value) if timing else (out, stats)
 
 

@@ -151,8 +151,11 @@ typedef struct {
   const void* coef;   /* float2 [images][K] prologue coefficients for this segment, or NULL        */
   int32_t K;
   int32_t mode;       /* 0 none, 1 a*x+b, 2 relu6(a*x+b), 3 silu(a*x+b), 4 a*x (SE gate; b must be 0) */
+  int32_t f16;        /* tcgen05 kernel only: this segment is fp16 (a block's hidden tensor), not bf16        */
+  int32_t reserved;
 } lcm_gemm_seg;
-/* out[m][n] = sum_s sum_k xform_s(A_s[m][k]) * W[n][koff_s + k]   (1x1 convs, efficient_unet.py:174,186,199,265,267) */
+/* out[m][n] = sum_s sum_k xform_s(A_s[m][k]) * W[n][koff_s + k]   (1x1 convs, efficient_unet.py:174,186,199,265,267)
+ * impl bit 8 (0x100, tcgen05 kernel only): store the output as fp16 (the expand GEMM's hidden tensor) */
 int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
                 int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream);
 /* dense 3x3 conv, mode 0: stride 1, 1: stride 2, 2: bilinear x2 then stride 1 (efficient_unet.py:367,380-384);

@@ -166,3 +166,43 @@ def test_dwconv_f16_stream(N, H, W, C):
     assert rel < 2e-3, rel
     pref = ref.sum(dim=(1, 2))
     assert torch.allclose(pool.float(), pref, rtol=5e-3, atol=0.01 * H * W ** 0.5), (pool.float() - pref).abs().max()
+
+
+GEMM_F16_CASES = [  # (images, P, [K...], [segment is fp16], Nc, modes, out_f16)
+    (2, 256, [32], [False], 128, [2], True),                 # expand: bf16 in, fp16 hidden out
+    (3, 64, [64, 32], [False, False], 384, [2, 2], True),
+    (3, 256, [128, 32], [True, False], 32, [4, 0], False),   # project: fp16 hidden (SE-gated, folded into weights) + bf16 residual
+    (2, 384, [384, 64, 32], [True, False, False], 32, [4, 0, 0], False),
+    (2, 64, [128, 32], [True, False], 64, [4, 0], False),    # tile spans images -> A-side gating of the fp16 operand
+    (2, 128, [1024, 256], [True, False], 256, [4, 0], False),
+    (2, 100, [192, 48], [True, False], 48, [4, 0], False),   # ragged M
+]
+
+
+@pytest.mark.parametrize("images,P,Ks,h16,Nc,modes,out_f16", GEMM_F16_CASES)
+def test_gemm_f16_segments(images, P, Ks, h16, Nc, modes, out_f16):
+    """tcgen05 GEMM with fp16 hidden-tensor operands / outputs mixed with bf16 residual-stream operands."""
+    from cv_diffusion_model_b200 import ops
+    if os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    g = torch.Generator(device="cuda").manual_seed(23)
+    M = images * P
+    segs, wcols = [], []
+    for K, mode, is16 in zip(Ks, modes, h16):
+        a = torch.randn(M, K, device="cuda", generator=g).to(torch.float16 if is16 else torch.bfloat16)
+        coef = None
+        if mode != 0:
+            coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
+                                torch.randn(images, K, device="cuda", generator=g) * (0.0 if mode == 4 else 0.3)], dim=-1)
+        segs.append((a, coef, mode))
+        wk = torch.randn(Nc, K, device="cuda", generator=g) / (sum(Ks) ** 0.5)
+        wcols.append(wk.half().float() if is16 else wk.bfloat16().float())   # weights follow the segment's type
+    w = torch.cat(wcols, dim=1)
+    out, stats = ops.gemm(segs, w, P, impl=1, out_f16=out_f16)
+    assert out.dtype == (torch.float16 if out_f16 else torch.bfloat16)
+    ref = _gemm_ref(segs, w, P)
+    assert (out.float() - ref).abs().max().item() < 0.06 * ref.abs().max().item() + 0.02
+    rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel < (8e-3 if not out_f16 else 6e-3), rel
+    sref = _stats_ref(out.float(), P)
+    assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3), (stats - sref).abs().max()
