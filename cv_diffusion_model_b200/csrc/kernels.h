@@ -103,6 +103,7 @@ struct PackJob {
   int ld;          // K extent of the logical matrix (padded for WL_UMMA)
   int off;         // column offset of this source in the logical matrix
   int block_n;     // WL_UMMA: rows per N tile
+  float scale;     // logical-matrix kinds: values are multiplied by this (0 = 1; the expand kernel folds relu6's 6 here)
 };
 void launch_pack(const PackJob& job, const float* src, cudaStream_t st);
 // element offset of logical (n, k) in the tcgen05 weight image (shared with the kernel's consumer side)
@@ -126,6 +127,11 @@ struct ConvGeom {   // conv3x3 producer geometry (mode < 0: plain 1x1 GEMM)
   const float* bias;
 };
 int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_sms, cudaStream_t st);
+// Expand GEMM specialisation (gemm_expand.cu): bf16 segments with relu6(a x + b) prologue, fp16 output + statistics,
+// weights packed with block_n = 64 and scale = 6.  `supported` is a pure shape test (plan time).
+bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P);
+int launch_gemm_expand(const GemmParams& p, int num_sms, cudaStream_t st);
+int gemm_expand_read_timeline(long long* host, int n);   // debug: LCM_X_TIMELINE=1
 int gemm_tc_pick_block_n(int Nc);
 int gemm_tc_read_timeline(long long* host, int n);   // debug: per-tile clock stamps of block 0 (LCM_TC_DEBUG & 64)
 

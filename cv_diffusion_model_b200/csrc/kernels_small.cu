@@ -227,6 +227,7 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 // Weight packing: fp32 state_dict tensors -> the layouts the kernels read.
 // destination element type of a logical-matrix job: PackJob::bf16 = 0 fp32, 1 bf16, 2 fp16
 __device__ __forceinline__ void put_any(const PackJob& j, int n, int k, float v) {
+  if (j.scale != 0.f) v *= j.scale;
   long long o = (j.layout == WL_UMMA) ? umma_weight_offset(n, k, j.ld, j.block_n) : (long long)n * j.ld + k;
   if (j.bf16 == 1) reinterpret_cast<bf16*>(j.dst)[o] = __float2bfloat16_rn(v);
   else if (j.bf16 == 2) reinterpret_cast<__half*>(j.dst)[o] = __float2half_rn(v);

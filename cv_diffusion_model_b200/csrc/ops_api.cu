@@ -32,7 +32,7 @@ int finish(cudaStream_t st) {
 
 extern "C" {
 
-int lcm_debug_timeline(long long* host, int n) { return gemm_tc_read_timeline(host, n); }
+int lcm_debug_timeline(long long* host, int n) { return n < 0 ? gemm_expand_read_timeline(host, -n) : gemm_tc_read_timeline(host, n); }
 
 int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
                 int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream) {
@@ -47,7 +47,13 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   int Ktot = 0, Kpad = 0;
   std::vector<int> off, poff;
   for (int i = 0; i < nseg; ++i) { off.push_back(Ktot); poff.push_back(Kpad); Ktot += segs[i].K; Kpad += (segs[i].K + 63) / 64 * 64; }
-  const int block_n = tc ? gemm_tc_pick_block_n(Nc) : 0;
+  bool expand = tc && out16 && stats_dev && nseg <= 2;
+  if (expand) {
+    int segK[2] = {0, 0};
+    for (int i = 0; i < nseg; ++i) { segK[i] = segs[i].K; expand = expand && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6 && !segs[i].f16; }
+    expand = expand && gemm_expand_supported(nseg, segK, Nc, P) && M % 128 == 0;
+  }
+  const int block_n = tc ? (expand ? 64 : gemm_tc_pick_block_n(Nc)) : 0;
   const size_t wbytes = tc ? (size_t)Nc * Kpad * 2 : (size_t)Nc * Ktot * (bf ? 2 : 4);
   void* wbuf = nullptr;
   if (cudaMalloc(&wbuf, wbytes) != cudaSuccess) return LCM_ERR_CUDA;
@@ -57,6 +63,7 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
     if (segs[i].f16 && !tc) { cudaFree(wbuf); return LCM_ERR_INVALID; }
     j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = segs[i].f16 ? 2 : (bf ? 1 : 0); j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
     j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = tc ? Kpad : Ktot; j.off = tc ? poff[i] : off[i]; j.block_n = block_n;
+    j.scale = expand ? 6.f : 0.f;
     launch_pack(j, w_dev, st);
     gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
     gp.seg[i].coef = (const float2*)segs[i].coef; gp.seg[i].coef_ld = segs[i].K; gp.seg[i].coef_off = 0;
@@ -69,7 +76,8 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   int rc = 0;
   Timer t(st, ms_out, repeat);
   for (int r = 0; r < repeat && rc == 0; ++r) {
-    if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
+    if (expand) rc = launch_gemm_expand(gp, sms, st);
+    else if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
     else launch_gemm_simt(gp, bf, st);
   }
   t.stop();

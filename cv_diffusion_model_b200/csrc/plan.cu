@@ -190,6 +190,7 @@ namespace {
 struct GemmW {
   size_t off = 0;
   int Nc = 0, Ktot = 0, Kpad = 0, block_n = 0;
+  bool expand = false;   // served by gemm_expand.cu: block_n = 64, weights scaled by 6
   std::vector<int> seg_off, seg_pad_off;
 };
 
@@ -213,16 +214,17 @@ struct Builder {
     p->ops.push_back(std::move(o));
   }
 
-  GemmW make_w(int Nc, const std::vector<int>& segK) {
+  GemmW make_w(int Nc, const std::vector<int>& segK, int expand_P = 0) {
     GemmW g;
     g.Nc = Nc;
+    g.expand = p->tc && expand_P > 0 && gemm_expand_supported((int)segK.size(), segK.data(), Nc, expand_P);
     for (int k : segK) {
       g.seg_off.push_back(g.Ktot);
       g.seg_pad_off.push_back(g.Kpad);
       g.Ktot += k;
       g.Kpad += (k + 63) / 64 * 64;
     }
-    if (p->tc) { g.block_n = gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
+    if (p->tc) { g.block_n = g.expand ? 64 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
     else g.off = p->walloc((size_t)Nc * g.Ktot * p->esz);
     return g;
   }
@@ -237,6 +239,7 @@ struct Builder {
     j.ld = p->tc ? g.Kpad : g.Ktot;
     j.off = p->tc ? g.seg_pad_off[seg] : g.seg_off[seg];
     j.block_n = g.block_n;
+    j.scale = g.expand ? 6.f : 0.f;
     return j;
   }
 
@@ -284,7 +287,8 @@ struct Builder {
       gp.M = (long long)n * gp.P;
       gp.Nc = w.Nc;
       gp.out_f16 = out->f16 ? 1 : 0;
-      if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
+      if (pl->tc && w.expand) { if (launch_gemm_expand(gp, pl->num_sms, st)) *c.launch_err = 1; }
+      else if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });
   }
@@ -308,7 +312,7 @@ struct Builder {
     {
       std::vector<int> segK;
       for (int i = 0; i < x.n; ++i) segK.push_back(x.part[i]->C);
-      GemmW we = make_w(Ch, segK);
+      GemmW we = make_w(Ch, segK, h * w);
       std::vector<SegSpec> segs;
       int col = 0;
       for (int i = 0; i < x.n; ++i) {

@@ -206,3 +206,41 @@ def test_gemm_f16_segments(images, P, Ks, h16, Nc, modes, out_f16):
     assert rel < (8e-3 if not out_f16 else 6e-3), rel
     sref = _stats_ref(out.float(), P)
     assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3), (stats - sref).abs().max()
+
+
+EXPAND_CASES = [  # (images, P, [K...], Nc): bf16 segments, relu6 prologue, fp16 output -> gemm_expand.cu (P % 128 == 0)
+    (2, 256, [32], 128),
+    (3, 128, [64], 256),
+    (5, 128 * 37, [32], 128),        # many tiles per CTA, image boundaries inside a CTA's range
+    (2, 1024, [64, 32], 384),        # concat expand of decoder level 3 (K = 96, six n-blocks)
+    (3, 640, [96], 384),
+    (2, 512, [128], 512),            # weights too large to stay resident -> general kernel
+    (2, 384, [16], 64),
+    (200, 128, [32], 128),           # more images than a CTA has tiles
+]
+
+
+@pytest.mark.parametrize("images,P,Ks,Nc", EXPAND_CASES)
+def test_gemm_expand_kernel(images, P, Ks, Nc):
+    """Expand GEMM specialisation: TMA store + tensor-core column statistics, x read once for all n-blocks."""
+    from cv_diffusion_model_b200 import ops
+    if os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    g = torch.Generator(device="cuda").manual_seed(29)
+    M = images * P
+    segs = []
+    for K in Ks:
+        a = (torch.randn(M, K, device="cuda", generator=g) * 1.5 + 0.3).bfloat16()
+        coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
+                            torch.randn(images, K, device="cuda", generator=g) * 0.5 + 0.5], dim=-1)
+        segs.append((a, coef, 2))
+    w = (torch.randn(Nc, sum(Ks), device="cuda", generator=g) / (sum(Ks) ** 0.5)).bfloat16().float()
+    out, stats = ops.gemm(segs, w, P, impl=1, out_f16=True)
+    assert out.dtype == torch.float16
+    ref = _gemm_ref(segs, w, P)
+    assert (out.float() - ref).abs().max().item() < 0.03 * ref.abs().max().item() + 0.02
+    rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel < 6e-3, rel
+    sref = _stats_ref(out.float(), P)   # statistics are defined on the stored values (squares rounded to fp16)
+    assert torch.allclose(stats[..., 0], sref[..., 0], rtol=2e-4, atol=2e-3 * P ** 0.5), (stats - sref)[..., 0].abs().max()
+    assert torch.allclose(stats[..., 1], sref[..., 1], rtol=5e-4, atol=1e-3), ((stats - sref)[..., 1].abs() / sref[..., 1]).max()
