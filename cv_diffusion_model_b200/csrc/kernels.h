@@ -53,6 +53,9 @@ void launch_upsample2x(const void* in, void* out, int N, int H, int W, int C, cu
 void launch_init_conv(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const float* w,
                       const float* bias, void* out, double* stats, int N, int H, int W, int Co, int bf16act,
                       cudaStream_t st);
+// packed-fp16 versions for the bf16 tensor-core plan (conv_edge.cu); false = shape not covered, caller falls back
+bool launch_init_conv_h2(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const float* w,
+                         const float* bias, void* out, double* stats, int N, int H, int W, int Co, cudaStream_t st);
 // final: GN+SiLU prologue, 3x3 conv to Cout (<=4), fp32 NCHW output; optional fused LCMScheduler.step.
 struct FinalStep {
   int enabled;           // 0: write eps only
@@ -64,6 +67,9 @@ struct FinalStep {
 };
 void launch_final_conv(const void* in, const float2* coef, const float* w, const float* bias, float* eps,
                        const FinalStep& step, int N, int H, int W, int Ci, int Co, int bf16act, cudaStream_t st);
+
+bool launch_final_conv_h2(const void* in, const float2* coef, const float* w, const float* bias, float* eps,
+                          const FinalStep& step, int N, int H, int W, int Ci, int Co, cudaStream_t st);
 
 // ---- a5: linear attention --------------------------------------------------------------------------
 // qkv NHWC [N][P][3*inner] (q | k | v, each heads*32); state [N][heads][32][33] fp64 (col 32 = k_sum), zeroed.

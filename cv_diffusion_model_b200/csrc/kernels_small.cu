@@ -128,55 +128,86 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 // Squeeze-and-Excitation gate (efficient_unet.py:96-100) as two batched row-GEMVs:
 //   hid[n][j]  = relu6(b1[j] + sum_c w1[j][c] * mean[n][c])          (mean = pooled sum * inv_count)
 //   gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * hid[n][j])         -> prologue coefficient (gate, 0)
-// One warp owns one weight row for a chunk of 16 images (the row stays in L1 while the images stream through), so
-// the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per 16 images instead of once per image.
+// A block stages the inputs of 4 images in shared memory; each of its warps walks 8 weight rows (a row is held in
+// registers while the 4 images are applied), so the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per
+// 4 images and the inputs once per 64 rows.
 template <bool kFirst>
 __global__ void __launch_bounds__(256) se_fc_kernel(const void* __restrict__ in_, float scale, const float* __restrict__ W,
                                                     const float* __restrict__ bias, void* __restrict__ out_, int N, int R,
                                                     int K) {
+  constexpr int IMGS = 4, ROWS_PER_WARP = 8;   // block = 4 images x 64 rows: inputs staged once, weights read once per 4 images
+  extern __shared__ __align__(16) float xin[];   // [IMGS][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  const int n0 = blockIdx.y * 16, n1 = min(N, n0 + 16);
-  if (r >= R) return;
-  const float* wr = W + (size_t)r * K;
-  const float b = bias[r];
-  for (int n = n0; n < n1; ++n) {
-    float acc = 0.f;
-    if ((K & 3) == 0) {
-      for (int k = lane * 4; k < K; k += 128) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
-        float x0, x1, x2, x3;
-        if (kFirst) {
-          const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(in_) + (size_t)n * K + k);
-          const double2 a = p[0], c = p[1];
-          x0 = (float)a.x * scale; x1 = (float)a.y * scale; x2 = (float)c.x * scale; x3 = (float)c.y * scale;
-        } else {
-          const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in_) + (size_t)n * K + k);
-          x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w;
+  const int n0 = blockIdx.y * IMGS, n1 = min(N, n0 + IMGS);
+  for (int i = 0; i < IMGS; ++i)
+    for (int k = threadIdx.x; k < K; k += 256) {
+      float v = 0.f;
+      if (n0 + i < n1)
+        v = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)(n0 + i) * K + k] * scale
+                   : reinterpret_cast<const float*>(in_)[(size_t)(n0 + i) * K + k];
+      xin[i * K + k] = v;
+    }
+  __syncthreads();
+  const bool vec = (K & 3) == 0;
+  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+    const int r = (blockIdx.x * 8 + warp) * ROWS_PER_WARP + rr;
+    if (r >= R) break;
+    const float* wr = W + (size_t)r * K;
+    float acc[IMGS];
+#pragma unroll
+    for (int i = 0; i < IMGS; ++i) acc[i] = 0.f;
+    if (vec) {
+      // 2048-wide slabs of the row: 16 independent 16-byte weight loads per lane in flight (the kernel is latency-bound)
+      for (int k0 = 0; k0 < K; k0 += 2048) {
+        float4 w4[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int k = k0 + c * 128 + lane * 4;
+          w4[c] = k < K ? *reinterpret_cast<const float4*>(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        acc = fmaf(w4.x, x0, acc); acc = fmaf(w4.y, x1, acc); acc = fmaf(w4.z, x2, acc); acc = fmaf(w4.w, x3, acc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int k = k0 + c * 128 + lane * 4;
+          if (k < K) {
+#pragma unroll
+            for (int i = 0; i < IMGS; ++i) {
+              const float4 x = *reinterpret_cast<const float4*>(xin + i * K + k);
+              acc[i] = fmaf(w4[c].x, x.x, acc[i]); acc[i] = fmaf(w4[c].y, x.y, acc[i]);
+              acc[i] = fmaf(w4[c].z, x.z, acc[i]); acc[i] = fmaf(w4[c].w, x.w, acc[i]);
+            }
+          }
+        }
       }
     } else {
       for (int k = lane; k < K; k += 32) {
-        const float x = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)n * K + k] * scale
-                               : reinterpret_cast<const float*>(in_)[(size_t)n * K + k];
-        acc = fmaf(wr[k], x, acc);
+        const float w = wr[k];
+#pragma unroll
+        for (int i = 0; i < IMGS; ++i) acc[i] = fmaf(w, xin[i * K + k], acc[i]);
       }
     }
+    const float b = bias[r];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      if (kFirst) reinterpret_cast<float*>(out_)[(size_t)n * R + r] = fminf(fmaxf(acc + b, 0.f), 6.f);
-      else reinterpret_cast<float2*>(out_)[(size_t)n * R + r] = make_float2(1.f / (1.f + expf(-(acc + b))), 0.f);
+    for (int i = 0; i < IMGS; ++i) {
+      float a = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && n0 + i < n1) {
+        if (kFirst) reinterpret_cast<float*>(out_)[(size_t)(n0 + i) * R + r] = fminf(fmaxf(a + b, 0.f), 6.f);
+        else reinterpret_cast<float2*>(out_)[(size_t)(n0 + i) * R + r] = make_float2(1.f / (1.f + expf(-(a + b))), 0.f);
+      }
     }
   }
 }
 
 void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st) {
-  const int chunks = (N + 15) / 16;
-  se_fc_kernel<true><<<dim3((SQ + 7) / 8, chunks), 256, 0, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
-  se_fc_kernel<false><<<dim3((C + 7) / 8, chunks), 256, 0, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
+  const int chunks = (N + 3) / 4;
+  const size_t sm1 = (size_t)4 * C * sizeof(float), sm2 = (size_t)4 * SQ * sizeof(float);
+  static size_t attr1 = 48 * 1024, attr2 = 48 * 1024;   // dynamic shared memory opted in so far
+  if (sm1 > attr1) { cudaFuncSetAttribute(se_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1); attr1 = sm1; }
+  if (sm2 > attr2) { cudaFuncSetAttribute(se_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); attr2 = sm2; }
+  se_fc_kernel<true><<<dim3((SQ + 63) / 64, chunks), 256, sm1, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
+  se_fc_kernel<false><<<dim3((C + 63) / 64, chunks), 256, sm2, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
 }
 
 // ------------------------------------------------------------------------------------------------

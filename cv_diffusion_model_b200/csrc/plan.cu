@@ -524,6 +524,8 @@ int build_plan(lcm_plan* p) {
     TensorP out = h;
     b.push("init_conv", "init_conv", (double)N * H * W * (Cin * 4.0 + Co * (double)p->esz), 18.0 * N * H * W * Cin * Co,
            [=](const RunCtx& cx, cudaStream_t st) {
+             if (p->tc && launch_init_conv_h2(cx.xa, cx.ca, cx.sa, cx.xb, cx.cb, cx.sb, p->wf(w_off), p->wf(b_off), cx.a + out->off,
+                                              (double*)(cx.z + out->stats_off), N, H, W, Co, st)) return;
              launch_init_conv(cx.xa, cx.ca, cx.sa, cx.xb, cx.cb, cx.sb, p->wf(w_off), p->wf(b_off), cx.a + out->off,
                               (double*)(cx.z + out->stats_off), N, H, W, Co, p->bf16, st);
            });
@@ -581,6 +583,8 @@ int build_plan(lcm_plan* p) {
     TensorP in = h;
     b.push("final_conv", "final_conv", (double)N * H * W * (Ci * (double)p->esz + Co * 4.0 * 3), 18.0 * N * H * W * Ci * Co,
            [=](const RunCtx& cx, cudaStream_t st) {
+             if (p->tc && launch_final_conv_h2(cx.a + in->off, (const float2*)(cx.f + coef), p->wf(w_off), p->wf(b_off), cx.eps,
+                                               cx.step, N, H, W, Ci, Co, st)) return;
              launch_final_conv(cx.a + in->off, (const float2*)(cx.f + coef), p->wf(w_off), p->wf(b_off), cx.eps, cx.step,
                                N, H, W, Ci, Co, p->bf16, st);
            });
