@@ -32,12 +32,32 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            bf16* __restrict__ out, double* __restrict__ stats, int H, int W) {
   constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 4;   // smem row: 34 used columns, padded to 36
-  __shared__ __align__(16) __half in_s[8][TH + 2][SW_];
+  __shared__ __align__(16) float in_s[2][8][TH + 2][SW_];    // double-buffered fp32 halo tile, filled with cp.async
   __shared__ __align__(16) __half w_s[72][CO];
   __shared__ float red[4][2 * CO];
   const int Cin = ca + cb;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int n = blockIdx.z, x0 = blockIdx.x * TW, yb = blockIdx.y * ROWS;
+  const int yend = min(yb + ROWS, H);
+  // stage the halo tile of rows [y0-1, y0+TH] asynchronously: one warp per (channel, row) line, 4-byte cp.async with
+  // zero fill outside the image — nothing is held in registers while the previous tile is being computed
+  auto stage = [&](int y0, int buf) {
+    for (int line = tid >> 5; line < Cin * (TH + 2); line += 4) {
+      const int ci = line / (TH + 2), r = line - ci * (TH + 2);
+      const int gy = y0 + r - 1;
+      const bool yok = gy >= 0 && gy < H;
+      const float* src = ci < ca ? xa + n * sa + ((long long)ci * H + (yok ? gy : 0)) * W
+                                 : xb + n * sb + ((long long)(ci - ca) * H + (yok ? gy : 0)) * W;
+      for (int c = tid & 31; c < TW + 2; c += 32) {
+        const int gx = x0 + c - 1;
+        const bool ok = yok && gx >= 0 && gx < W;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&in_s[buf][ci][r][c]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(yb, 0);
   for (int i = tid; i < 9 * Cin * CO; i += 128) w_s[i / CO][i % CO] = __float2half_rn(w[i]);
   __half2 bias2[CO / 2];
 #pragma unroll
@@ -46,26 +66,23 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
 #pragma unroll
   for (int c = 0; c < CO; ++c) { s[c] = 0.f; q[c] = 0.f; }
 
-  for (int y0 = yb; y0 < min(yb + ROWS, H); y0 += TH) {
-    __syncthreads();   // previous tile's reads of in_s are done (and w_s is written, first time round)
-    // one warp per (channel, row) line of 34 columns: no per-element index arithmetic
-    for (int line = tid >> 5; line < Cin * (TH + 2); line += 4) {
-      const int ci = line / (TH + 2), r = line - ci * (TH + 2);
-      const int gy = y0 + r - 1;
-      const float* src = ci < ca ? xa + n * sa + ((long long)ci * H + gy) * W : xb + n * sb + ((long long)(ci - ca) * H + gy) * W;
-      for (int c = tid & 31; c < TW + 2; c += 32) {
-        const int gx = x0 + c - 1;
-        in_s[ci][r][c] = __float2half_rn((gy >= 0 && gy < H && gx >= 0 && gx < W) ? src[gx] : 0.f);
-      }
+  int buf = 0;
+  for (int y0 = yb; y0 < yend; y0 += TH, buf ^= 1) {
+    if (y0 + TH < yend) {
+      stage(y0 + TH, buf ^ 1);   // that buffer was last read two tiles ago (barrier at the end of the previous tile)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();   // this tile's data (and, first time round, the weights) are visible to every thread
     __half2 a0[CO / 2], a1[CO / 2];
 #pragma unroll
     for (int j = 0; j < CO / 2; ++j) { a0[j] = bias2[j]; a1[j] = bias2[j]; }
     for (int dy = 0; dy < 3; ++dy) {
       for (int ci = 0; ci < Cin; ++ci) {
-        const __half2 c01 = *reinterpret_cast<const __half2*>(&in_s[ci][ty + dy][2 * tx]);
-        const __half2 c23 = *reinterpret_cast<const __half2*>(&in_s[ci][ty + dy][2 * tx + 2]);
+        const float2 f01 = *reinterpret_cast<const float2*>(&in_s[buf][ci][ty + dy][2 * tx]);
+        const float2 f23 = *reinterpret_cast<const float2*>(&in_s[buf][ci][ty + dy][2 * tx + 2]);
+        const __half2 c01 = __floats2half2_rn(f01.x, f01.y), c23 = __floats2half2_rn(f23.x, f23.y);
         const __half2 col[4] = {__low2half2(c01), __high2half2(c01), __low2half2(c23), __high2half2(c23)};
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -103,6 +120,7 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
         }
       }
     }
+    __syncthreads();   // everyone is done reading in_s[buf] before the next-but-one stage overwrites it
   }
   // ---- statistics: warp shuffle tree, fixed-order sum over the 4 warps, one fp64 atomic per (block, channel, moment)
 #pragma unroll

@@ -76,6 +76,9 @@ struct alignas(64) Tc2Params {
 __device__ long long g_timeline[64 * 16];   // LCM_TC_DEBUG & 64: per-tile clock64 stamps of block 0
 #define TSTAMP(slot) do { if (kDebug && (p.debug & 64) && blockIdx.x == 0 && it < 64) g_timeline[it * 16 + (slot)] = clock64(); } while (0)
 
+__device__ __forceinline__ __half2 h2bits(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t bits_of(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -177,7 +180,18 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         for (int s = 0; s < p.nseg; ++s) {
           if (p.seg[s].mode == XF_NONE) continue;
           const float2* src = p.seg[s].coef + (size_t)ti.img * p.seg[s].coef_ld + p.seg[s].coef_off;
-          for (int k = ptid; k < p.seg[s].K; k += kXfThreads) s_coef[p.coef_base[s] + k] = src[k];
+          if (p.seg[s].f16 && p.seg[s].mode == XF_SCALE) {
+            // fp16 operand with a pure scale: the A-side prologue is one HMUL2 per two channels; the packed gate
+            // pair of channels (k, k+1) travels in the unused b slot of entry k (k even)
+            for (int k = 2 * ptid; k < p.seg[s].K; k += 2 * kXfThreads) {
+              const float2 c0v = src[k], c1v = src[k + 1];
+              const __half2 gp = __floats2half2_rn(c0v.x, c1v.x);
+              s_coef[p.coef_base[s] + k] = make_float2(c0v.x, __uint_as_float(*reinterpret_cast<const uint32_t*>(&gp)));
+              s_coef[p.coef_base[s] + k + 1] = make_float2(c1v.x, 0.f);
+            }
+          } else {
+            for (int k = ptid; k < p.seg[s].K; k += kXfThreads) s_coef[p.coef_base[s] + k] = src[k];
+          }
         }
         bar_sync(1, kXfThreads);
         cur_img = ti.img;
@@ -208,7 +222,10 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 l[j] = f[j] - (h16 ? __half2float(__float2half_rn(f[j])) : __bfloat162float(__float2bfloat16_rn(f[j])));
               }
               st_s(b_smem + (uint32_t)u * 16u, h16 ? pack8h(f) : pack8(f));
-              st_s(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes + (uint32_t)u * 16u, h16 ? pack8h(l) : pack8(l));
+              // bf16 weights carry a low-order image so that W * gate keeps ~16 bits; fp16 weights (11 bits, finer than
+              // every bf16 operand around them) do not need one
+              if (p.lo_slot[ci] != 0xff)
+                st_s(sbase + p.bres_off + (uint32_t)(p.nchunks + p.lo_slot[ci]) * b_chunk_bytes + (uint32_t)u * 16u, pack8(l));
             }
           }
         }
@@ -255,6 +272,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 uint4 o;
                 if (dbg & 256) {
                   o = v[i];
+                } else if (kFast && sg.f16 && mode == XF_SCALE) {
+                  const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
+                  const __half2* hv = reinterpret_cast<const __half2*>(&v[i]);
+                  __half2 r0 = __hmul2(hv[0], h2bits(__float_as_uint(c4[0].y))), r1 = __hmul2(hv[1], h2bits(__float_as_uint(c4[1].y)));
+                  __half2 r2 = __hmul2(hv[2], h2bits(__float_as_uint(c4[2].y))), r3 = __hmul2(hv[3], h2bits(__float_as_uint(c4[3].y)));
+                  o = make_uint4(bits_of(r0), bits_of(r1), bits_of(r2), bits_of(r3));
                 } else if (kFast) {
                   o = apply_xform(v[i], s_coef + p.coef_base[sidx] + c0 + cu * 8, mode, sg.f16 != 0);
                 } else {
@@ -716,12 +739,12 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   int ngate = 0;
   for (int ci = 0; ci < nch; ++ci) {
     p.lo_slot[ci] = 0xff;
-    if (has_gate && g.seg[p.chunk[ci] & 0x7f].mode == XF_SCALE) p.lo_slot[ci] = (uint8_t)ngate++;
+    if (has_gate && g.seg[p.chunk[ci] & 0x7f].mode == XF_SCALE && !g.seg[p.chunk[ci] & 0x7f].f16) p.lo_slot[ci] = (uint8_t)ngate++;
   }
   static int no_wgate = -1;
   if (no_wgate < 0) { const char* e = getenv("LCM_NO_WGATE"); no_wgate = (e && atoi(e)) ? 1 : 0; }
   uint32_t bres = (uint32_t)nch * b_chunk;
-  p.resident = (bres <= 98304 && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
+  p.resident = (bres <= 131072 && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
   if (has_gate && p.resident && p.fast && !no_wgate) {
     const uint32_t bres2 = (uint32_t)(nch + ngate) * b_chunk;   // + low-order images of the gated chunks
     if (bres2 <= 131072 && base_fixed + stg_bytes + bres2 + 3 * kStageA2 <= kSmemLimit2) { p.wgate = 1; bres = bres2; }
