@@ -213,8 +213,17 @@ def main():
     top = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
     tk = by_kernel[top]
     achieved = tk["bytes"] / tk["n"] / (tk["ms"] / tk["n"] / 1e3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one representative launch)
+    traffic, traffic_of = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if top in tj:
+            traffic, traffic_of = tj[top]["dram_bytes_per_launch"], tj[top]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top, "launches_per_forward": tk["n"], "share_of_forward": tk["ms"] / fwd_ms,
-                "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+                "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic,
+                "traffic_capture": traffic_of, "algorithmic_bytes_per_launch_avg": tk["bytes"] / tk["n"],
                 "peak_source": peak_src,
                 "whole_model": {"algorithmic_gb_per_forward": eng.algorithmic_bytes / 1e9,
                                 "achieved_gbs": value / world * LCM_STEPS * eng.algorithmic_bytes / B / 1e9,

@@ -266,7 +266,7 @@ struct Builder {
             double bytes, double flops) {
     lcm_plan* pl = p; const int n = N;
     std::vector<SegSpec> sg = segs;
-    push(name, pl->tc ? "gemm_tc" : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
+    push(name, pl->tc ? (w.expand ? "gemm_expand" : "gemm_tc") : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
       GemmParams gp{};
       gp.nseg = (int)sg.size();
       for (int i = 0; i < gp.nseg; ++i) {
@@ -330,7 +330,7 @@ struct Builder {
     { PackJob j{}; j.kind = PACK_DW; j.dst = (void*)dw_off; j.R = Ch; p->add_weight(name + ".depthwise.weight", (int64_t)Ch * 9, j); }
     {
       lcm_plan* pl = p; const int n = N;
-      push(name + ".depthwise", "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
+      push(name + ".depthwise", hid16 ? "dwconv_stream" : "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
            [=](const RunCtx& c, cudaStream_t st) {
              if (hid16) {
                if (launch_dwconv_f16(c.a + h1->off, (const float2*)(c.f + coef2), pl->wf(dw_off), c.a + h2->off,
