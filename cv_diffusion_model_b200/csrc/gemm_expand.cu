@@ -1,35 +1,39 @@
 // Expand GEMM of the inverted-residual block (efficient_unet.py:174,207-209) on the tensor-core path:
 //
-//   h1[m][n] = sum_k relu6(a_k * x[m][k] + b_k) * W[n][k]        x: bf16 residual stream (1-2 concat segments)
+//   h1[m][n] = sum_k relu6(a_k * x[m][k] + b_k) * W[n][k]        x: bf16 residual stream (1-2 concat segments, K <= 128)
 //                                                                 h1: fp16 hidden tensor + per-(image, channel) sum / sum^2
 //
-// K is small (32...128) and N = 4K, so this op is a pure streaming problem — (K + N) * 2 bytes per pixel, ~40 FLOP/B —
-// and the only thing that can keep it off the HBM roofline is the per-element instruction count of the epilogue.
-// The general kernel (gemm_tc2.cu) spends ~9000 warp instructions per 128x128 tile, most of them in the CUDA-core
-// copy-out + column-statistics role; this kernel removes that role entirely:
+// K is small and N = 4K, so this op is a pure streaming problem — (K + N) * 2 bytes per pixel, ~40 FLOP/B — and what can
+// keep it off the HBM roofline is everything that is done per OUTPUT element.  The general kernel (gemm_tc2.cu) spends
+// ~9000 warp instructions per 128x128 tile in its copy-out + column-statistics roles; the first version of this kernel
+// (TMA-store staging + statistics MMAs over the staged tile and its square) was bound by shared-memory bandwidth.  This
+// version does NOTHING per output element except convert and store:
 //
-//   * statistics on the tensor core: the epilogue stages the fp16 tile AND its element-wise square in shared memory
-//     (128-byte swizzled [128 rows][64 cols] chunks); one more tcgen05.mma per 16 rows, D_stat[128][16] +=
-//     [x | x^2]^T (MN-major A operand straight from the staging chunks) * ones[16 rows][16], accumulates the 64 column
-//     sums and 64 sums of squares of the n-block in TMEM lanes 0-63 / 64-127.  They stay in TMEM across all tiles of an
-//     image and are flushed with ONE fp64 atomic per (CTA, image, channel, moment).
-//   * the global store is a TMA store of the same staging chunk: no per-element store instructions.
+//   * statistics from the INPUT side.  With A' = relu6(..)/6 (the MMA's A operand) and W6 = 6 W:
+//         sum_m out[m][n]   = W6[n] . S          S[k]     = sum_m A'[m][k]          (prologue warps, registers)
+//         sum_m out[m][n]^2 = W6[n]^T G W6[n]    G[k][k'] = sum_m A'[m][k] A'[m][k'] (one Gram MMA per 16 rows)
+//     The Gram MMA reads the activation chunks that are already in shared memory as MN-major operands for BOTH A and B
+//     (D[128][64 nch] += chunk^T chunk) and accumulates in TMEM over all tiles of an image; S and G are added to a small
+//     per-image scratch at image boundaries and `expand_stats_kernel` turns them into the usual (sum, sum^2) table.
+//     Cost per tile: 8 small MMAs and 2 x 16 KB of shared-memory reads per chunk, independent of N.
+//   * the epilogue is tcgen05.ld -> cvt.f16x2 -> a per-warp 32 x 128 B transpose through a private shared-memory patch
+//     (lane = row after tcgen05.ld; row-per-thread stores reach only 1-2.3 TB/s with 16-byte and 4.8 TB/s with 32-byte
+//     vectors — tests/diag/rowstore_bw.cu) -> coalesced 16-byte stores.  No block barrier, no fence, no TMA store.
 //   * prologue: relu6(a x + b) = 6 sat(a/6 x + b/6): one FFMA.SAT per element, the 6 is folded into the packed weights.
 //   * an m-tile (128 pixels) is multiplied by ALL n-blocks of the resident weights, so x is read exactly once.
 //
-// Roles (512 threads, one persistent CTA per SM):
-//   warps 0-3, 4-7  E0, E1  two epilogue groups, n-block g belongs to group g & 1 (its own accumulator and staging
-//                           buffer): tcgen05.ld 64 accumulator columns -> fp16 x, x^2 -> staging; the group's first
-//                           thread issues the TMA store.  One group alone is latency-bound (ld -> cvt -> sts -> fence
-//                           -> barrier chain), two overlap.
-//                           thread issues the TMA store AND the statistics MMAs of its n-block, so nothing else ever
-//                           waits for the staging tile.
-//   warp  8    MMA main MMAs (M=128, N=64, K=16), n-block after n-block
-//   warp  9    TMA weights once; activation chunks (128 rows x 64 channels, 128-byte swizzle) ring
-//   warps 10-15 XF in-place prologue on the landed chunk
+// Roles (512 threads = 16 warps, 4 per register-file partition; one persistent CTA per SM):
+//   warps 0-3, 4-7  E0, E1  each drains one 64-column half of every 128-column accumulator; group 0 also moves the
+//                           Gram matrix from TMEM to the scratch at image boundaries
+//   warp  8         MMA     main MMAs (M=128, N=128, K=16) n-block after n-block
+//   warp  9         TMA     weights once; activation chunks (128 rows x 64 channels, 128-byte swizzle) ring
+//   warp  10        GRAM    the tile's Gram MMAs (a second issuer: the issue code runs on the uniform datapath at
+//                           ~10 cycles per dependent instruction, one warp doing both was the critical path)
+//   warps 12-15     XF      in-place prologue on the landed chunk + column sums
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -44,27 +48,29 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreadsX = 512;   // 16 warps: 4 per register-file partition, 128 registers each
-constexpr int kXfBaseX = 320, kXfThreadsX = 192;
-constexpr int kMmaWarp = 8, kTmaWarp = 9, kXfWarp0 = 10;
+constexpr int kThreadsX = 512;
+constexpr int kXfBaseX = 384, kXfThreadsX = 128;
+constexpr int kMmaWarp = 8, kTmaWarp = 9, kGramWarp = 10, kXfWarp0 = 12;   // warp 11 idles
 constexpr uint32_t kChunkBytes = 16384;     // 128 rows x 64 16-bit elements
-constexpr uint32_t kWChunkBytes = 8192;     // 64 output channels x 64 k
+constexpr uint32_t kWChunkBytes = 16384;    // 128 output channels x 64 k
 constexpr uint32_t kSmemLimitX = 232448;
-constexpr int kMaxNB = 8;                   // n-blocks of 64 output channels
-constexpr int kMaxChunksX = 4;              // 64-wide K chunks per tile
-constexpr uint32_t kStatCol0 = 128;         // TMEM: columns 0-127 = two 64-column accumulators, then 16 per n-block
+constexpr int kMaxNB = 4;                   // n-blocks of 128 output channels (each drained as two 64-column halves)
+constexpr int kMaxChunksX = 2;              // 64-wide K chunks per tile (Gram matrix = one 128-lane TMEM block)
+constexpr uint32_t kGramCol0 = 256;         // TMEM: columns 0-255 = two 128-column accumulators, 256-383 = Gram matrix
+constexpr int kGramLd = 128;                // scratch: G[img][128][128] fp32, S[img][128] fp32
 
 struct XParams {
   CUtensorMap tmap_in[2];
-  CUtensorMap tmap_out;
   const float2* coef[2];
   int coef_ld[2], coef_off[2], segK[2];
   int nseg, nchunks, NB, stages;
-  const __half* W;          // packed [n-block][chunk][64 rows x 64 k] (128-byte swizzled rows), scaled by 6
-  double* stats;            // [images][Nc][2]
-  int m_tiles, P, Nc, ncoef;
-  uint32_t chunk[kMaxChunksX];   // seg | kvalid << 8 | c0 << 16 | coef base << 24
-  uint32_t w_off, stg_off, ones_off, coef_smem_off, misc_off;
+  const bf16* W;            // packed [n-block][chunk][128 rows x 64 k] (128-byte swizzled rows), scaled by 6
+  __half* out;
+  float* gram;              // [images][128][128]
+  float* colsum;            // [images][128]
+  int m_tiles, P, Nc;
+  uint32_t chunk[kMaxChunksX];   // seg | kvalid << 8 | c0/8 << 16 | coef base << 24
+  uint32_t w_off, stg_off, coef_smem_off, misc_off;
   int debug;
 };
 
@@ -74,28 +80,15 @@ __device__ __forceinline__ void tma_load_2d_x(uint32_t dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // MN-major operand, 128-byte swizzle: 64 elements (128 B) contiguous along MN, 8-row groups along K 1024 B apart,
 // 64-wide MN blocks `lbo` bytes apart
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// K-major, no swizzle: 8-row x 16-byte core matrices, 128 B each, consecutive along K then along the rows
-__device__ __forceinline__ uint64_t umma_desc_plain(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (8ull << 16) | (16ull << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 
 __device__ long long g_xtimeline[64 * 16];   // LCM_X_TIMELINE: clock64 stamps of block 0, first 64 tiles
@@ -114,32 +107,26 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (24 + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (26 + a); };
-  auto sfree_bar = [&](int b) { return bar0 + 8u * (30 + b); };
-  const uint32_t wres_bar = bar0 + 8u * 32;
-  const uint32_t sread_bar = bar0 + 8u * 33;   // statistics read out of TMEM (image flush)
+  const uint32_t wres_bar = bar0 + 8u * 28;
+  const uint32_t gdone_bar = bar0 + 8u * 29;   // Gram MMAs of a tile have completed (one phase per tile)
+  const uint32_t sread_bar = bar0 + 8u * 30;   // Gram matrix read out of TMEM (image flush)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.misc_off + 320);
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_smem_off);
 
   if (warp == kTmaWarp && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(xf_bar(s), kXfThreadsX); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128);
-      mbar_init(sfree_bar(a), 1);
-    }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(xf_bar(s), kXfThreadsX); mbar_init(empty_bar(s), 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     mbar_init(wres_bar, 1);
+    mbar_init(gdone_bar, 1);
     mbar_init(sread_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < p.nseg; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap_in[s])) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)) : "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  // ones operand of the statistics MMA: 512 B of fp16 1.0
-  if (tid < 128) reinterpret_cast<uint32_t*>(smem + p.ones_off)[tid] = 0x3C003C00u;
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,15 +135,34 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
   const int t_begin = (int)((long long)p.m_tiles * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)p.m_tiles * (blockIdx.x + 1) / gridDim.x);
   const int tiles_per_img = p.P >> 7;
+  const int kw = 64 * p.nchunks;   // Gram width
 
   if (warp >= kXfWarp0) {
-    // ================================ XF: relu6(a x + b) / 6 in place =====================================
+    // ================================ XF: relu6(a x + b) / 6 in place, column sums ==========================
     const int xt = tid - kXfBaseX;
+    // unit u = xt + 128 i: row = u >> 3, slot = u & 7 holds channel unit cu = slot ^ (row & 7); (row & 7) does not
+    // depend on i (128 = 16 rows), so a thread transforms the same 8 channels in all of its rows
+    const int cu = (xt & 7) ^ ((xt >> 3) & 7);
     int stage = 0; uint32_t phase = 0;
-    int cur_img = -1;
+    int img = t_begin / tiles_per_img, tin = t_begin - img * tiles_per_img;
+    int coef_img = -1;
+    float cs[kMaxChunksX][8];
+#pragma unroll
+    for (int c = 0; c < kMaxChunksX; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[c][j] = 0.f;
+    auto flush_cs = [&](int im) {
+#pragma unroll
+      for (int c = 0; c < kMaxChunksX; ++c) {
+        if (c < p.nchunks && cu * 8 < (int)((p.chunk[c] >> 8) & 0xff)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { atomicAdd(&p.colsum[(size_t)im * kGramLd + c * 64 + cu * 8 + j], cs[c][j]); cs[c][j] = 0.f; }
+        }
+      }
+    };
     for (int t = t_begin; t < t_end; ++t) {
-      const int img = t / tiles_per_img;
-      if (img != cur_img) {
+      if (img != coef_img) {
+        if (coef_img >= 0) flush_cs(coef_img);
         bar_sync(1, kXfThreadsX);   // everyone is done with the previous image's coefficients
         for (int s = 0, base = 0; s < p.nseg; base += p.segK[s], ++s) {
           const float2* src = p.coef[s] + (size_t)img * p.coef_ld[s] + p.coef_off[s];
@@ -166,15 +172,14 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
           }
         }
         bar_sync(1, kXfThreadsX);
-        cur_img = img;
+        coef_img = img;
       }
-      for (int ci = 0; ci < p.nchunks; ++ci) {
+#pragma unroll
+      for (int ci = 0; ci < kMaxChunksX; ++ci) {
+        if (ci >= p.nchunks) break;
         const uint32_t cd = p.chunk[ci];
         const int kvalid = (cd >> 8) & 0xff, cbase = cd >> 24;
         const uint32_t a_smem = sbase + (uint32_t)stage * kChunkBytes;
-        // unit u = xt + 192 i: row = u >> 3, slot = u & 7 holds channel unit cu = slot ^ (row & 7); (row & 7) does not
-        // depend on i (192 = 24 rows), so a thread transforms the same 8 channels in all of its rows
-        const int cu = (xt & 7) ^ ((xt >> 3) & 7);
         const bool act = cu * 8 < kvalid;
         float2 ab[8];
         if (act) {
@@ -185,18 +190,22 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
         mbar_wait(raw_bar(stage), phase);
         if (ci == 0 && xt == 0) XSTAMP(t - t_begin, 1);
         if (act) {
-          uint4 v[6];
+          uint4 v[8];
 #pragma unroll
-          for (int i = 0; i < 6; ++i)
-            if (xt + i * kXfThreadsX < 1024) v[i] = lds128(a_smem + (uint32_t)(xt + i * kXfThreadsX) * 16u);
+          for (int i = 0; i < 8; ++i) v[i] = lds128(a_smem + (uint32_t)(xt + i * kXfThreadsX) * 16u);
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            if (xt + i * kXfThreadsX < 1024) {
+          for (int i = 0; i < 8; ++i) {
+            {
               float f[8];
               unpack8(v[i], f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = __saturatef(fmaf(ab[j].x, f[j], ab[j].y));
-              sts128(a_smem + (uint32_t)(xt + i * kXfThreadsX) * 16u, pack8(f));
+              const uint4 pk = pack8(f);
+              sts128(a_smem + (uint32_t)(xt + i * kXfThreadsX) * 16u, pk);
+              // column sums of exactly what the tensor core multiplies (the bf16-rounded values), so that S and G
+              // describe the same matrix
+              cs[ci][0] += bf16lo(pk.x); cs[ci][1] += bf16hi(pk.x); cs[ci][2] += bf16lo(pk.y); cs[ci][3] += bf16hi(pk.y);
+              cs[ci][4] += bf16lo(pk.z); cs[ci][5] += bf16hi(pk.z); cs[ci][6] += bf16lo(pk.w); cs[ci][7] += bf16hi(pk.w);
             }
           }
           fence_proxy_async();
@@ -205,7 +214,9 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
         if (ci == p.nchunks - 1 && xt == 0) XSTAMP(t - t_begin, 2);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++tin == tiles_per_img) { tin = 0; ++img; }
     }
+    if (coef_img >= 0) flush_cs(coef_img);
   } else if (warp == kTmaWarp) {
     // ================================ TMA: weights once, activation chunks ================================
     if (elect_one()) {
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     for (int t = t_begin; t < t_end; ++t) {
       for (int ci = 0; ci < p.nchunks; ++ci) {
         const uint32_t cd = p.chunk[ci];
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
         if (ci == 0 && lane == 0) XSTAMP(t - t_begin, 0);
         if (elect_one()) {
           mbar_expect_tx(raw_bar(stage), kChunkBytes);
@@ -231,9 +242,12 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     }
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ============================================================
-    // D = f32, A/B = bf16 (main) ; M = 128, N = 64
-    const uint32_t idesc_main = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | (8u << 24);
+    // main: D = f32, A/B = bf16, both K-major; M = 128, N = 128
+    const uint32_t idesc_main = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (8u << 24);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int ks0 = (int)((p.chunk[0] >> 8) & 0xff) >> 4;                          // K steps of 16 per chunk
+    const int ks1 = p.nchunks > 1 ? (int)((p.chunk[1] >> 8) & 0xff) >> 4 : 0;
+    const uint64_t wd0 = umma_desc(sbase + p.w_off);
     mbar_wait(wres_bar, 0);
     int stage = 0; uint32_t phase = 0;      // activation ring position of the CURRENT tile's first chunk
     int g = 0;                               // n-blocks issued so far (accumulator = g & 1)
@@ -248,137 +262,225 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
       }
       tc_fence_after();
       if (lane == 0) XSTAMP(t - t_begin, 3);
+      // The issue code runs on the uniform datapath, where every dependent instruction costs several cycles: keep it
+      // to constant-offset descriptor adds and predicated MMAs (the generic loop version took ~600 cycles per n-block).
+      const uint64_t ad0 = umma_desc(sbase + (uint32_t)stage * kChunkBytes);   // chunk ci at + ci * (16384 >> 4)
       for (int j = 0; j < p.NB; ++j, ++g) {
         const int acc = g & 1;
         mbar_wait(tempty_bar(acc), ((uint32_t)(g >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
-          int s2 = stage;
-          for (int ci = 0; ci < p.nchunks; ++ci) {
-            const int ksteps = (int)((p.chunk[ci] >> 8) & 0xff) >> 4;
-            const uint64_t ad = umma_desc(sbase + (uint32_t)s2 * kChunkBytes);
-            const uint64_t bd = umma_desc(sbase + p.w_off + (uint32_t)(j * p.nchunks + ci) * kWChunkBytes);
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(tmem_u + (uint32_t)acc * 64u, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_main, (ci | k) != 0 ? 1u : 0u);
-            if (++s2 == p.stages) s2 = 0;
-          }
+          const uint64_t bd0 = wd0 + (uint64_t)(j * p.nchunks) * (kWChunkBytes >> 4);
+          const uint32_t d = tmem_u + (uint32_t)acc * 128u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ks0) umma_bf16(d, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc_main, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ks1) umma_bf16(d, ad0 + (uint64_t)((kChunkBytes >> 4) + 2 * k), bd0 + (uint64_t)((kWChunkBytes >> 4) + 2 * k), idesc_main, 1u);
           umma_commit(tfull_bar(acc));
-          if (j == p.NB - 1) {   // last reader of this tile's activation chunks: hand the stages back
-            int s3 = stage;
-            for (int ci = 0; ci < p.nchunks; ++ci) { umma_commit(empty_bar(s3)); if (++s3 == p.stages) s3 = 0; }
-          }
         }
         __syncwarp();
+        if (lane == 0 && j < 2) XSTAMP(t - t_begin, 8 + j);
       }
+      if (elect_one())
+        for (int ci = 0; ci < p.nchunks; ++ci) umma_commit(empty_bar(stage + ci));   // one of the two readers of the tile's chunks
+      __syncwarp();
       if (lane == 0) XSTAMP(t - t_begin, 4);
-      for (int ci = 0; ci < p.nchunks; ++ci) if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      stage += p.nchunks;
+      if (stage == p.stages) { stage = 0; phase ^= 1u; }
     }
+  } else if (warp == kGramWarp) {
+    // ================================ Gram issuer =============================================================
+    // A and B are the SAME activation chunk(s) read MN-major (bits 15, 16); M = 128, N = kw; the matrix accumulates in
+    // TMEM over the tiles of one image
+    const uint32_t idesc_gram = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kw >> 3) << 17) | (8u << 24);
+    const uint32_t gram_lbo = p.nchunks == 2 ? kChunkBytes : 0u;   // one chunk: MN block 1 aliases block 0 (lanes 64-127 unused)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0; uint32_t phase = 0;
+    int tin = t_begin % tiles_per_img;
+    uint32_t sread_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      {
+        int s2 = stage; uint32_t ph2 = phase;
+        for (int ci = 0; ci < p.nchunks; ++ci) {
+          mbar_wait(xf_bar(s2), ph2);
+          if (++s2 == p.stages) { s2 = 0; ph2 ^= 1u; }
+        }
+      }
+      const bool first_tile = t == t_begin || tin == 0;
+      if (first_tile && t != t_begin) { mbar_wait(sread_bar, sread_phase); sread_phase ^= 1u; }
+      tc_fence_after();
+      if (lane == 0) XSTAMP(t - t_begin, 13);
+      if (elect_one()) {
+        const uint64_t d0 = umma_desc_mn(sbase + (uint32_t)stage * kChunkBytes, gram_lbo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_u + kGramCol0, d0 + (uint64_t)(k * (2048 >> 4)), d0 + (uint64_t)(k * (2048 >> 4)), idesc_gram, (first_tile && k == 0) ? 0u : 1u);
+        umma_commit(gdone_bar);
+        for (int ci = 0; ci < p.nchunks; ++ci) umma_commit(empty_bar(stage + ci));   // the other reader of the tile's chunks
+      }
+      __syncwarp();
+      if (lane == 0) XSTAMP(t - t_begin, 14);
+      stage += p.nchunks;
+      if (stage == p.stages) { stage = 0; phase ^= 1u; }
+      if (++tin == tiles_per_img) tin = 0;
+    }
+  } else if (warp == 11) {
+    // idle
   } else {
-    // ================================ E0 / E1: accumulator -> fp16 x, x^2 -> staging -> TMA store ============
-    // the warp index is broadcast so that the compiler keeps everything derived from it (group, loop counters, TMA /
-    // MMA operands) in uniform registers: issuing tcgen05.mma from per-thread registers costs ~150 cycles each (R2UR)
+    // ================================ E0 / E1: accumulator -> fp16 -> global ================================
+    // the warp index is broadcast so that the compiler keeps everything derived from it in uniform registers
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    const int grp = warp_u >> 2;               // owns n-blocks g with (g & 1) == grp: accumulator grp, staging buffer grp
+    const int grp = warp_u >> 2;               // owns n-blocks g with (g & 1) == grp: accumulator grp
     const int ew = warp_u & 3;                 // TMEM lane quadrant = warp % 4
     const int et = ew * 32 + lane;
-    const int r7 = et & 7;
-    const uint32_t row_off = (uint32_t)et * 128u + ((uint32_t)r7 << 4);   // XOR with (unit << 4) gives the swizzled slot
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-    const uint32_t xs0 = sbase + p.stg_off + (uint32_t)grp * 2u * kChunkBytes;
     const int total_g = (t_end - t_begin) * p.NB;
     int cur_img = -1;
-    // statistics MMA (issued by the group's first thread right after the staging tile is complete):
-    // A/B = f16, A is MN-major (bit 15), M = 128, N = 16
-    const uint32_t idesc_stat = (1u << 4) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | (8u << 24);
-    const uint64_t ones_desc = umma_desc_plain(sbase + p.ones_off);
-    uint32_t sread_phase = 0;     // image flushes waited for so far (leaders only)
-    int waited_t = -1;
-    // image flush (group 0 only): each group's statistics MMAs complete in order, so all of them up to n-block `gl`
-    // have completed once the last one of either group (gl and gl - 1) has
-    auto flush = [&](int img, int gl) {
-      mbar_wait(sfree_bar(gl & 1), (uint32_t)(gl >> 1) & 1u);
-      if (gl > 0) mbar_wait(sfree_bar((gl - 1) & 1), (uint32_t)((gl - 1) >> 1) & 1u);
+    // image flush (group 0): Gram matrix TMEM -> scratch.  `lt` = CTA-local index of the image's last tile; gdone
+    // completes one phase per tile and cannot run ahead of this wait (the next image's first Gram MMA waits for sread)
+    auto flush = [&](int im, int lt) {
+      mbar_wait(gdone_bar, (uint32_t)lt & 1u);
       tc_fence_after();
-      const int which = et >> 6, col = et & 63;
-      for (int j = 0; j < p.NB; ++j) {
-        uint32_t v;
-        tmem_ld1(lane_base + kStatCol0 + 16u * j, v);
-        tmem_wait_ld();
-        atomicAdd(&p.stats[((size_t)img * p.Nc + j * 64 + col) * 2 + which], (double)__uint_as_float(v));
+      if (ew * 32 < kw) {
+        float* grow = p.gram + ((size_t)im * kGramLd + et) * kGramLd;
+        for (int c = 0; c < kw; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_base + kGramCol0 + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(grow + c + i, __uint_as_float(r[i]));
+        }
       }
       tc_fence_before();
       mbar_arrive(sread_bar);
     };
-    int t = t_begin, j = grp;
+    int t = t_begin, j = 0;
     int img = t_begin / tiles_per_img, tin = t_begin - img * tiles_per_img;   // image of tile t, tile index inside it
-    auto advance = [&]() { while (j >= p.NB) { j -= p.NB; ++t; if (++tin == tiles_per_img) { tin = 0; ++img; } } };
-    advance();
-    for (int g = grp; g < total_g; g += 2) {
-      if (grp == 0 && img != cur_img) { if (cur_img >= 0) flush(cur_img, (t - t_begin) * p.NB - 1); cur_img = img; }
-      const uint32_t use = (uint32_t)(g >> 1) & 1u;
-      mbar_wait(tfull_bar(grp), use);
+    // every 128-column accumulator is drained by both groups: group grp takes columns [64 grp, 64 grp + 64)
+    for (int g = 0; g < total_g; ++g) {
+      // (t - tin) is the first tile of the current image: the previous image ended one tile before it
+      if (grp == 0 && img != cur_img) { if (cur_img >= 0) flush(cur_img, t - tin - 1 - t_begin); cur_img = img; }
+      const int acc = g & 1;
+      mbar_wait(tfull_bar(acc), (uint32_t)(g >> 1) & 1u);
       if (et == 0 && j < 2) XSTAMP(t - t_begin, 5 + 5 * j);
       tc_fence_after();
-      const uint32_t taddr = lane_base + (uint32_t)grp * 64u;
+      const uint32_t taddr = lane_base + (uint32_t)acc * 128u + (uint32_t)grp * 64u;
       uint32_t r[4][16];
       tmem_ld16(taddr, r[0]); tmem_ld16(taddr + 16, r[1]); tmem_ld16(taddr + 32, r[2]); tmem_ld16(taddr + 48, r[3]);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(tempty_bar(grp));                    // accumulator drained
+      mbar_arrive(tempty_bar(acc));                    // this group's half of the accumulator is drained
       if (et == 0 && j < 2) XSTAMP(t - t_begin, 6 + 5 * j);
-      if (ew == 0 && elect_one()) bulk_wait_read<0>(); // this group's previous store has read the staging buffer
-      mbar_wait(sfree_bar(grp), use ^ 1u);             // ... and so has its statistics MMA
-      bar_sync(3 + grp, 128);
-      if (et == 0 && j < 2) XSTAMP(t - t_begin, 7 + 5 * j);
+      // lane = row, so a thread holds 128 contiguous bytes of ITS row; stored like that a warp instruction touches 32
+      // different lines (measured: ~1 TB/s with 16-byte, ~4.8 TB/s with 32-byte stores).  Each warp transposes its
+      // 32 x 128 B block through a private 4 KB shared-memory patch (XOR-swizzled 16-byte units, conflict-free both
+      // ways, warp-level sync only) so that every store instruction writes 4 complete 128-byte lines.
+      {
+        const uint32_t patch = sbase + p.stg_off + (uint32_t)warp_u * 4096u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t x[4], sq[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            x[e] = pack_f16(__uint_as_float(r[q][h * 8 + 2 * e]), __uint_as_float(r[q][h * 8 + 2 * e + 1]));
-            const __half2 hx = *reinterpret_cast<__half2*>(&x[e]);
-            const __half2 hs = __hmul2(hx, hx);
-            sq[e] = *reinterpret_cast<const uint32_t*>(&hs);
-          }
-          const uint32_t a = (xs0 + row_off) ^ ((uint32_t)(q * 2 + h) << 4);
-          sts128(a, make_uint4(x[0], x[1], x[2], x[3]));
-          sts128(a + kChunkBytes, make_uint4(sq[0], sq[1], sq[2], sq[3]));
-        }
-      }
-      fence_proxy_async();
-      bar_sync(3 + grp, 128);
-      if (et == 0 && j < 2) XSTAMP(t - t_begin, 8 + 5 * j);
-      if (ew == 0) {   // the group's first warp, in warp-uniform control flow; one elected lane issues
-        if (elect_one()) { tma_store_2d(&p.tmap_out, xs0, j * 64, t * 128); bulk_commit(); }
-        // the statistics columns of an n-block accumulate over the tiles of one image: the first tile of an image
-        // (in this CTA's range) overwrites them — after the previous image's sums have been read out of TMEM
-        const bool first_tile = t == t_begin || tin == 0;
-        if (first_tile && t != t_begin && t != waited_t) { mbar_wait(sread_bar, sread_phase); sread_phase ^= 1u; waited_t = t; }
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem_base + kStatCol0 + 16u * j, umma_desc_mn(xs0 + (uint32_t)k * 2048u, kChunkBytes), ones_desc, idesc_stat,
-                      (first_tile && k == 0) ? 0u : 1u);
-          umma_commit(sfree_bar(grp));
+        for (int u = 0; u < 8; ++u) {
+          const int q = u >> 1, h = (u & 1) * 8;
+          sts128(patch + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4),
+                 make_uint4(pack_f16(__uint_as_float(r[q][h + 0]), __uint_as_float(r[q][h + 1])),
+                            pack_f16(__uint_as_float(r[q][h + 2]), __uint_as_float(r[q][h + 3])),
+                            pack_f16(__uint_as_float(r[q][h + 4]), __uint_as_float(r[q][h + 5])),
+                            pack_f16(__uint_as_float(r[q][h + 6]), __uint_as_float(r[q][h + 7]))));
         }
         __syncwarp();
-        if (lane == 0 && j < 2) XSTAMP(t - t_begin, 9 + 5 * j);
+        const int unit = lane & 7, rsub = lane >> 3;
+        __half* obase = p.out + ((size_t)t * 128 + ew * 32 + rsub) * p.Nc + j * 128 + grp * 64 + unit * 8;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + rsub;
+          v[i] = lds128(patch + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(obase + (size_t)(i * 4) * p.Nc) = v[i];
+        __syncwarp();   // the patch is free again
       }
-      j += 2;
-      advance();
+      if (et == 0 && j < 2) XSTAMP(t - t_begin, 7 + 5 * j);
+      if (++j == p.NB) { j = 0; ++t; if (++tin == tiles_per_img) { tin = 0; ++img; } }
     }
-    if (grp == 0 && cur_img >= 0) flush(cur_img, total_g - 1);
-    if (ew == 0 && elect_one()) bulk_wait_all();
+    if (grp == 0 && cur_img >= 0) flush(cur_img, t_end - 1 - t_begin);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (S, G, W6) -> per-(image, channel) sum and sum of squares of the expand output.  grid = (images, Nc / 32), 128 threads:
+// thread = (output channel n, quarter of the k range).  The channel's weight row sits in registers (de-swizzled from the
+// packed tcgen05 image), G in shared memory (broadcast LDS.128); products are summed in fp32 runs of 16, beyond in fp64.
+template <int KW>
+__global__ void __launch_bounds__(128) expand_stats_kernel(const float* __restrict__ gram, const float* __restrict__ colsum,
+                                                           const bf16* __restrict__ W, double* __restrict__ stats, int Nc,
+                                                           int nchunks) {
+  extern __shared__ __align__(16) float gs[];   // G[KW][KW], S[KW], Wt[KW][32], partial[4][32][2] (double)
+  float* ss = gs + KW * KW;
+  float* wt = ss + KW;
+  double* part = reinterpret_cast<double*>(wt + KW * 32);
+  const int img = blockIdx.x, tid = threadIdx.x, nl = tid & 31, kq = tid >> 5, n = blockIdx.y * 32 + nl;
+  const float* g = gram + (size_t)img * kGramLd * kGramLd;
+  for (int i = tid; i < KW * KW / 4; i += 128) {
+    const int row = (i * 4) / KW, col = (i * 4) % KW;
+    reinterpret_cast<float4*>(gs)[i] = *reinterpret_cast<const float4*>(g + row * kGramLd + col);
+  }
+  for (int i = tid; i < KW; i += 128) ss[i] = colsum[(size_t)img * kGramLd + i];
+  float w[KW];
+  {
+    const int jb = n >> 7, r = n & 127;
+#pragma unroll
+    for (int c = 0; c < KW / 64; ++c) {
+      const uint4* row = reinterpret_cast<const uint4*>(W + ((size_t)(jb * nchunks + c) * 128 + r) * 64);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 v = row[u ^ (r & 7)];   // logical unit u sits in slot u ^ (r & 7)
+        float f[8];
+        tc::unpack8(v, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[c * 64 + u * 8 + e] = f[e];
+      }
+    }
+  }
+  if (kq == 0) {
+#pragma unroll
+    for (int k = 0; k < KW; ++k) wt[k * 32 + nl] = w[k];
+  }
+  __syncthreads();
+  double s = 0.0, q = 0.0;
+  for (int k = kq * (KW / 4); k < (kq + 1) * (KW / 4); ++k) {
+    const float4* grow = reinterpret_cast<const float4*>(gs + k * KW);
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < KW / 16; ++b) {
+      float a = 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 g4 = grow[b * 4 + v];
+        a = fmaf(g4.x, w[b * 16 + v * 4 + 0], a); a = fmaf(g4.y, w[b * 16 + v * 4 + 1], a);
+        a = fmaf(g4.z, w[b * 16 + v * 4 + 2], a); a = fmaf(g4.w, w[b * 16 + v * 4 + 3], a);
+      }
+      t += (double)a;
+    }
+    const double wk = (double)wt[k * 32 + nl];
+    q += wk * t;
+    s += wk * (double)ss[k];
+  }
+  part[(kq * 32 + nl) * 2] = s;
+  part[(kq * 32 + nl) * 2 + 1] = q;
+  __syncthreads();
+  if (tid < 64) {
+    const int c = tid >> 1, m = tid & 1;
+    const double v = (part[(0 * 32 + c) * 2 + m] + part[(1 * 32 + c) * 2 + m]) + (part[(2 * 32 + c) * 2 + m] + part[(3 * 32 + c) * 2 + m]);
+    stats[((size_t)img * Nc + blockIdx.y * 32 + c) * 2 + m] += v;   // exclusive owner of this entry (the table is zeroed per forward)
   }
 }
 
@@ -411,28 +513,27 @@ bool matrix_map(const void* ptr, long long M, int K, int ld, int dtype, CUtensor
   return true;
 }
 
-struct XLayout { int nchunks, NB, stages; uint32_t w_off, stg_off, ones_off, coef_off, misc_off, total; };
+struct XLayout { int nchunks, NB, stages; uint32_t w_off, stg_off, coef_off, misc_off, total; };
 
 bool plan_layout(int nseg, const int* segK, int Nc, XLayout* L) {
   int nch = 0, ncoef = 0;
   for (int s = 0; s < nseg; ++s) {
-    if (segK[s] % 16 || segK[s] < 16 || segK[s] > 248) return false;   // kvalid is stored in 8 bits
+    if (segK[s] % 16 || segK[s] < 16 || segK[s] > 64 * kMaxChunksX) return false;
     nch += (segK[s] + 63) / 64;
     ncoef += segK[s];
   }
-  if (nch < 1 || nch > kMaxChunksX || Nc % 64 || Nc / 64 > kMaxNB || Nc < 64) return false;
-  if (ncoef > 255) return false;   // coefficient base is stored in 8 bits
-  L->nchunks = nch; L->NB = Nc / 64;
+  if (nch < 1 || nch > kMaxChunksX || Nc % 128 || Nc / 128 > kMaxNB || Nc < 128) return false;
+  L->nchunks = nch; L->NB = Nc / 128;
   const uint32_t wbytes = (uint32_t)L->NB * nch * kWChunkBytes;
-  const uint32_t fixed = wbytes + 4u * kChunkBytes /* staging: 2 x (x, x^2) */ + 1024 /* ones */ + 2048 /* coef */ + 1024 /* misc */ + 1024 /* align */;
-  if (fixed + (uint32_t)(nch + 1) * kChunkBytes > kSmemLimitX) return false;
+  const uint32_t fixed = wbytes + 32768 /* epilogue transpose patches */ + 2048 /* coef */ + 1024 /* misc */ + 1024 /* align */;
+  if (fixed + (uint32_t)(2 * nch) * kChunkBytes > kSmemLimitX) return false;
   int stages = (int)((kSmemLimitX - fixed) / kChunkBytes);
   if (stages > 8) stages = 8;
+  stages -= stages % nch;   // a tile's chunks never wrap around the ring
   L->stages = stages;
   uint32_t off = (uint32_t)stages * kChunkBytes;
   L->w_off = off; off += wbytes;
-  L->stg_off = off; off += 4u * kChunkBytes;
-  L->ones_off = off; off += 1024;
+  L->stg_off = off; off += 32768;
   L->coef_off = off; off += 2048;
   L->misc_off = off; off += 1024;
   L->total = off + 1024;
@@ -453,9 +554,12 @@ bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P) {
   return plan_layout(nseg, segK, Nc, &L);
 }
 
-// W: fp16... no: bf16 image packed with block_n = 64 and the x6 scale (PackJob::scale) — see plan.cu / ops_api.cu
-int launch_gemm_expand(const GemmParams& g, int num_sms, cudaStream_t st) {
-  if (g.nseg < 1 || g.nseg > 2 || !g.out_f16 || !g.stats || g.P % 128 || g.M % 128 || g.M <= 0 || g.M > 0x7fffff00LL) return -1;
+size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd * kGramLd + kGramLd) * sizeof(float); }
+
+// W: bf16 image packed with block_n = 64 and the x6 scale (PackJob::scale) — see plan.cu / ops_api.cu.
+// scratch: gemm_expand_scratch_bytes(images) bytes, contents irrelevant (zeroed here, on the stream).
+int launch_gemm_expand(const GemmParams& g, void* scratch, int num_sms, cudaStream_t st) {
+  if (g.nseg < 1 || g.nseg > 2 || !g.out_f16 || !g.stats || !scratch || g.P % 128 || g.M % g.P || g.M <= 0 || g.M > 0x7fffff00LL) return -1;
   int segK[2] = {0, 0};
   for (int s = 0; s < g.nseg; ++s) {
     if (g.seg[s].mode != XF_AFFINE_RELU6 || g.seg[s].f16 || !g.seg[s].coef || g.seg[s].ld % 8) return -1;
@@ -463,13 +567,16 @@ int launch_gemm_expand(const GemmParams& g, int num_sms, cudaStream_t st) {
   }
   XLayout L;
   if (!plan_layout(g.nseg, segK, g.Nc, &L)) return -1;
+  const int images = (int)(g.M / g.P);
   XParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = g.nseg; p.nchunks = L.nchunks; p.NB = L.NB; p.stages = L.stages;
-  p.W = reinterpret_cast<const __half*>(g.W);
-  p.stats = g.stats;
+  p.W = reinterpret_cast<const bf16*>(g.W);
+  p.out = reinterpret_cast<__half*>(g.out);
+  p.gram = reinterpret_cast<float*>(scratch);
+  p.colsum = p.gram + (size_t)images * kGramLd * kGramLd;
   p.m_tiles = (int)(g.M / 128); p.P = g.P; p.Nc = g.Nc;
-  p.w_off = L.w_off; p.stg_off = L.stg_off; p.ones_off = L.ones_off; p.coef_smem_off = L.coef_off; p.misc_off = L.misc_off;
+  p.w_off = L.w_off; p.stg_off = L.stg_off; p.coef_smem_off = L.coef_off; p.misc_off = L.misc_off;
   int nch = 0, cbase = 0;
   for (int s = 0; s < g.nseg; ++s) {
     p.coef[s] = g.seg[s].coef; p.coef_ld[s] = g.seg[s].coef_ld; p.coef_off[s] = g.seg[s].coef_off; p.segK[s] = g.seg[s].K;
@@ -480,19 +587,25 @@ int launch_gemm_expand(const GemmParams& g, int num_sms, cudaStream_t st) {
     }
     cbase += g.seg[s].K;
   }
-  p.ncoef = cbase;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_X_TIMELINE"); dbg = (e && atoi(e)) ? 1 : 0; } p.debug = dbg; }
-  if (!matrix_map(g.out, g.M, g.Nc, g.Nc, TMAP_F16, &p.tmap_out)) return -3;
   static bool attr_done = false;
   {
     std::lock_guard<std::mutex> lk(g_x_mu);
     if (!attr_done) {
       if (cudaFuncSetAttribute(gemm_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitX) != cudaSuccess) return -2;
+      if (cudaFuncSetAttribute(expand_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 128 + 128 * 32 + 512) * 4) != cudaSuccess) return -2;
+      if (cudaFuncSetAttribute(expand_stats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 64 + 64 * 32 + 512) * 4) != cudaSuccess) return -2;
       attr_done = true;
     }
   }
+  if (cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(images), st) != cudaSuccess) return -2;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   gemm_expand_kernel<<<grid, kThreadsX, L.total, st>>>(p);
+  const dim3 sg(images, g.Nc / 32);
+  if (L.nchunks == 1)
+    expand_stats_kernel<64><<<sg, 128, (64 * 64 + 64 + 64 * 32 + 512) * 4, st>>>(p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
+  else
+    expand_stats_kernel<128><<<sg, 128, (128 * 128 + 128 + 128 * 32 + 512) * 4, st>>>(p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
   return 0;
 }
 

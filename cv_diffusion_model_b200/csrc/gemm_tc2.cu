@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
           const uint32_t a_smem = sbase + stage * p.stage_bytes;
-          mbar_wait(empty_bar(stage), ring.phase ^ 1u);
+          mbar_wait_relaxed(empty_bar(stage), ring.phase ^ 1u);
           if (ci == 0) TSTAMP(0);
           const bool load_a = !conv && !(dbg & 1);
           if (elect_one()) {

@@ -419,7 +419,9 @@ bool g_attr_set = false;
 }  // namespace
 
 int gemm_tc_pick_block_n(int Nc) {
-  for (int bn = 256; bn >= 16; bn -= 16)
+  static int forced = -1;   // experiment switch: LCM_BLOCK_N=<n> caps the N tile
+  if (forced < 0) { const char* e = getenv("LCM_BLOCK_N"); forced = e ? atoi(e) : 0; }
+  for (int bn = (forced >= 16 && forced <= 256) ? forced / 16 * 16 : 256; bn >= 16; bn -= 16)
     if (Nc % bn == 0) return bn;
   return 0;
 }

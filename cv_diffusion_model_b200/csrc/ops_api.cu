@@ -53,7 +53,7 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
     for (int i = 0; i < nseg; ++i) { segK[i] = segs[i].K; expand = expand && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6 && !segs[i].f16; }
     expand = expand && gemm_expand_supported(nseg, segK, Nc, P) && M % 128 == 0;
   }
-  const int block_n = tc ? (expand ? 64 : gemm_tc_pick_block_n(Nc)) : 0;
+  const int block_n = tc ? (expand ? 128 : gemm_tc_pick_block_n(Nc)) : 0;
   const size_t wbytes = tc ? (size_t)Nc * Kpad * 2 : (size_t)Nc * Ktot * (bf ? 2 : 4);
   void* wbuf = nullptr;
   if (cudaMalloc(&wbuf, wbytes) != cudaSuccess) return LCM_ERR_CUDA;
@@ -74,15 +74,19 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int rc = 0;
+  void* xscratch = nullptr;
+  if (expand && cudaMalloc(&xscratch, gemm_expand_scratch_bytes((int)(M / P))) != cudaSuccess) { cudaFree(wbuf); return LCM_ERR_CUDA; }
   Timer t(st, ms_out, repeat);
   for (int r = 0; r < repeat && rc == 0; ++r) {
-    if (expand) rc = launch_gemm_expand(gp, sms, st);
+    if (expand && repeat > 1 && stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)(M / P) * Nc * 2 * sizeof(double), st);   // the finalisation kernel owns its entries
+    if (expand) rc = launch_gemm_expand(gp, xscratch, sms, st);
     else if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
     else launch_gemm_simt(gp, bf, st);
   }
   t.stop();
   int rc2 = finish(st);
   cudaFree(wbuf);
+  if (xscratch) cudaFree(xscratch);
   return rc ? LCM_ERR_INVALID : rc2;
 }
 

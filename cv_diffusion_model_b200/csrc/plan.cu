@@ -144,6 +144,7 @@ struct lcm_plan {
 
   int film_rows = 0;
   size_t film_f_off = 0, silu_f_off = 0;
+  size_t xscratch_f_off = 0;   // Gram / column-sum scratch shared by all expand-kernel launches (stream-ordered)
 
   std::vector<Op> ops;
   std::map<std::string, TensorP> tap_map;
@@ -190,7 +191,7 @@ namespace {
 struct GemmW {
   size_t off = 0;
   int Nc = 0, Ktot = 0, Kpad = 0, block_n = 0;
-  bool expand = false;   // served by gemm_expand.cu: block_n = 64, weights scaled by 6
+  bool expand = false;   // served by gemm_expand.cu: block_n = 128, weights scaled by 6
   std::vector<int> seg_off, seg_pad_off;
 };
 
@@ -224,7 +225,7 @@ struct Builder {
       g.Ktot += k;
       g.Kpad += (k + 63) / 64 * 64;
     }
-    if (p->tc) { g.block_n = g.expand ? 64 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
+    if (p->tc) { g.block_n = g.expand ? 128 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
     else g.off = p->walloc((size_t)Nc * g.Ktot * p->esz);
     return g;
   }
@@ -287,7 +288,7 @@ struct Builder {
       gp.M = (long long)n * gp.P;
       gp.Nc = w.Nc;
       gp.out_f16 = out->f16 ? 1 : 0;
-      if (pl->tc && w.expand) { if (launch_gemm_expand(gp, pl->num_sms, st)) *c.launch_err = 1; }
+      if (pl->tc && w.expand) { if (launch_gemm_expand(gp, c.f + pl->xscratch_f_off, pl->num_sms, st)) *c.launch_err = 1; }
       else if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });
@@ -321,6 +322,7 @@ struct Builder {
         col += x.part[i]->C;
       }
       gemm(name + ".expand", segs, we, h1, true, (Ci + Ch) * N * P * es + (double)Ci * Ch * es, 2.0 * N * P * Ci * Ch);
+      if (we.expand) p->ops.back().launches = 2;   // GEMM + statistics finalisation
     }
     // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
     const size_t coef2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
@@ -500,6 +502,7 @@ int build_plan(lcm_plan* p) {
   };
   const int ted = c.time_embed_dim, base = c.base_channels;
 
+  if (p->tc) p->xscratch_f_off = p->falloc(gemm_expand_scratch_bytes(N));
   // a2: time embedding (efficient_unet.py:550)
   {
     const size_t w1 = p->add_copy("time_mlp.1.weight", (int64_t)ted * base), b1 = p->add_copy("time_mlp.1.bias", ted);

@@ -20,11 +20,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait suspends the thread until the phase completes or a time limit expires; the hint raises that limit so
-// that a waiting role costs (almost) no issue slots — with the default limit, spinning waiters executed a
-// quarter of all instructions of the GEMM kernel (ncu, round 1).
-constexpr uint32_t kSuspendHintNs = 200000;
+// try_wait suspends the thread until the phase completes or a (short, implementation-defined) time limit expires.
+// Measured on B200 (round 1): with a suspend-time HINT ptxas emits TRYWAIT + NANOSLEEP.SYNCS <hint>, and a thread that
+// went to sleep wakes up several hundred cycles after the arrive — fine for a producer that waits for a free slot,
+// ruinous on a dependent chain (the expand kernel's MMA warp spent ~600 cycles per hop).  So: plain try_wait
+// (spinning, ~60 cycles wake-up) on latency-critical waits, the hinted form only where nobody waits for the waiter.
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -57,6 +70,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);   // ~2 s: a protocol bug, not a slow producer
+  }
+}
+// for waiters nobody waits for (producers waiting for a free slot): sleeps instead of spinning
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_relaxed(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

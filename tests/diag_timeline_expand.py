@@ -28,7 +28,7 @@ out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True, out_f16=Tru
 buf = (C.c_longlong * 1024)()
 native.lib().lcm_debug_timeline(buf, -1024)
 t0 = min(buf[i] for i in range(16) if buf[i] > 0)
-names = ["tma_issue", "xf_raw", "xf_done", "mma_xf", "mma_done", "e_tfull0", "e_ld0", "e_bar0", "e_stg0", "e_mma0", "e_tfull1", "e_ld1", "e_bar1", "e_stg1", "e_mma1"]
+names = ["tma_issue", "xf_raw", "xf_done", "mma_xf", "mma_done", "e_tfull0", "e_ld0", "e_st0", "mma_j0", "mma_j1", "e_tfull1", "e_ld1", "e_st1", "gram_start", "gram_done"]
 print(f"{case}: {ms*1e3:.1f} us;  cycles relative to first stamp")
 print("tile " + " ".join(f"{n:>9s}" for n in names))
 for it in range(0, 48):

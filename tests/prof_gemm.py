@@ -18,6 +18,12 @@ CASES = {
     "project_d2": (32, 16384, [768, 128, 64], 64, [4, 0, 0], [1, 0, 0], 0),
     "expand_e1": (32, 16384, [64], 256, [2], [0], 1),
     "expand_m": (64, 1024, [256], 1024, [2], [0], 1),
+    "expand_d1": (64, 4096, [256, 128], 1536, [2, 2], [0, 0], 1),
+    "expand_d0": (64, 1024, [256, 256], 2048, [2, 2], [0, 0], 1),
+    "project_d1": (64, 4096, [1536, 256, 128], 128, [4, 0, 0], [1, 0, 0], 0),
+    "project_d0": (64, 1024, [2048, 256, 256], 256, [4, 0, 0], [1, 0, 0], 0),
+    "expand_e2": (64, 4096, [128], 512, [2], [0], 1),
+    "project_e2": (64, 4096, [512, 128], 128, [4, 0], [1, 0], 0),
     "project_m": (64, 1024, [1024, 256], 256, [4, 0], [1, 0], 0),
 }
 images, P, Ks, Nc, modes, h16, o16 = CASES[sys.argv[1] if len(sys.argv) > 1 else "expand0"]

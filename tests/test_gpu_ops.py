@@ -205,7 +205,12 @@ def test_gemm_f16_segments(images, P, Ks, h16, Nc, modes, out_f16):
     rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     assert rel < (8e-3 if not out_f16 else 6e-3), rel
     sref = _stats_ref(out.float(), P)
-    assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3), (stats - sref).abs().max()
+    if out_f16:   # may be served by the expand kernel, whose statistics come from the input side (see test_gemm_expand_kernel)
+        e0 = ((stats - sref)[..., 0].abs() / (sref[..., 1].sqrt() * P ** 0.5 + 1e-6)).max().item()
+        e1 = ((stats - sref)[..., 1].abs() / sref[..., 1]).max().item()
+        assert e0 < 1e-3 and e1 < 2e-3, (e0, e1)
+    else:
+        assert torch.allclose(stats, sref, rtol=1e-4, atol=1e-3), (stats - sref).abs().max()
 
 
 EXPAND_CASES = [  # (images, P, [K...], Nc): bf16 segments, relu6 prologue, fp16 output -> gemm_expand.cu (P % 128 == 0)
@@ -214,9 +219,12 @@ EXPAND_CASES = [  # (images, P, [K...], Nc): bf16 segments, relu6 prologue, fp16
     (5, 128 * 37, [32], 128),        # many tiles per CTA, image boundaries inside a CTA's range
     (2, 1024, [64, 32], 384),        # concat expand of decoder level 3 (K = 96, six n-blocks)
     (3, 640, [96], 384),
-    (2, 512, [128], 512),            # weights too large to stay resident -> general kernel
+    (2, 512, [128], 512),
     (2, 384, [16], 64),
     (200, 128, [32], 128),           # more images than a CTA has tiles
+    (2, 65536, [32], 128),           # production image size: 512 tiles accumulate in TMEM before the flush
+    (2, 16384, [64, 32], 384),
+    (3, 4096, [128], 512),           # K = 128, eight n-blocks, 128 KB of resident weights
 ]
 
 
@@ -241,6 +249,9 @@ def test_gemm_expand_kernel(images, P, Ks, Nc):
     assert (out.float() - ref).abs().max().item() < 0.03 * ref.abs().max().item() + 0.02
     rel = ((out.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     assert rel < 6e-3, rel
-    sref = _stats_ref(out.float(), P)   # statistics are defined on the stored values (squares rounded to fp16)
-    assert torch.allclose(stats[..., 0], sref[..., 0], rtol=2e-4, atol=2e-3 * P ** 0.5), (stats - sref)[..., 0].abs().max()
-    assert torch.allclose(stats[..., 1], sref[..., 1], rtol=5e-4, atol=1e-3), ((stats - sref)[..., 1].abs() / sref[..., 1]).max()
+    # statistics: computed from the input side (column sums and Gram matrix of the prologue output) in exact
+    # arithmetic they equal the sums over the fp32 accumulators; the stored values differ by fp16 rounding only
+    sref = _stats_ref(out.float(), P)
+    e0 = ((stats - sref)[..., 0].abs() / (sref[..., 1].sqrt() * P ** 0.5 + 1e-6)).max().item()   # |dSum| / (rms * P)
+    e1 = ((stats - sref)[..., 1].abs() / sref[..., 1]).max().item()
+    assert e0 < 1e-3 and e1 < 2e-3, (e0, e1)
