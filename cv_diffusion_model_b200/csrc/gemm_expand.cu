@@ -57,7 +57,7 @@ constexpr uint32_t kSmemLimitX = 232448;
 constexpr int kMaxNB = 4;                   // n-blocks of 128 output channels (each drained as two 64-column halves)
 constexpr int kMaxChunksX = 2;              // 64-wide K chunks per tile (Gram matrix = one 128-lane TMEM block)
 constexpr uint32_t kGramCol0 = 256;         // TMEM: columns 0-255 = two 128-column accumulators, 256-383 = Gram matrix
-constexpr int kGramLd = 128;                // scratch: G[img][128][128] fp32, S[img][128] fp32
+constexpr int kGramLd = 128;                // scratch: G[img][128][128], S[img][128] (fp64)
 
 struct XParams {
   CUtensorMap tmap_in[2];
@@ -66,8 +66,8 @@ struct XParams {
   int nseg, nchunks, NB, stages;
   const bf16* W;            // packed [n-block][chunk][128 rows x 64 k] (128-byte swizzled rows), scaled by 6
   __half* out;
-  float* gram;              // [images][128][128]
-  float* colsum;            // [images][128]
+  double* gram;             // [images][128][128]  fp64: a few fp32 partial sums per entry add exactly, in any order
+  double* colsum;           // [images][128]
   int m_tiles, P, Nc;
   uint32_t chunk[kMaxChunksX];   // seg | kvalid << 8 | c0/8 << 16 | coef base << 24
   uint32_t w_off, stg_off, coef_smem_off, misc_off;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
       for (int c = 0; c < kMaxChunksX; ++c) {
         if (c < p.nchunks && cu * 8 < (int)((p.chunk[c] >> 8) & 0xff)) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { atomicAdd(&p.colsum[(size_t)im * kGramLd + c * 64 + cu * 8 + j], cs[c][j]); cs[c][j] = 0.f; }
+          for (int j = 0; j < 8; ++j) { atomicAdd(&p.colsum[(size_t)im * kGramLd + c * 64 + cu * 8 + j], (double)cs[c][j]); cs[c][j] = 0.f; }
         }
       }
     };
@@ -344,13 +344,13 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
       mbar_wait(gdone_bar, (uint32_t)lt & 1u);
       tc_fence_after();
       if (ew * 32 < kw) {
-        float* grow = p.gram + ((size_t)im * kGramLd + et) * kGramLd;
+        double* grow = p.gram + ((size_t)im * kGramLd + et) * kGramLd;
         for (int c = 0; c < kw; c += 16) {
           uint32_t r[16];
           tmem_ld16(lane_base + kGramCol0 + c, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(grow + c + i, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; ++i) atomicAdd(grow + c + i, (double)__uint_as_float(r[i]));
         }
       }
       tc_fence_before();
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
 // thread = (output channel n, quarter of the k range).  The channel's weight row sits in registers (de-swizzled from the
 // packed tcgen05 image), G in shared memory (broadcast LDS.128); products are summed in fp32 runs of 16, beyond in fp64.
 template <int KW>
-__global__ void __launch_bounds__(128) expand_stats_kernel(const float* __restrict__ gram, const float* __restrict__ colsum,
+__global__ void __launch_bounds__(128) expand_stats_kernel(const double* __restrict__ gram, const double* __restrict__ colsum,
                                                            const bf16* __restrict__ W, double* __restrict__ stats, int Nc,
                                                            int nchunks) {
   extern __shared__ __align__(16) float gs[];   // G[KW][KW], S[KW], Wt[KW][32], partial[4][32][2] (double)
@@ -428,12 +428,13 @@ __global__ void __launch_bounds__(128) expand_stats_kernel(const float* __restri
   float* wt = ss + KW;
   double* part = reinterpret_cast<double*>(wt + KW * 32);
   const int img = blockIdx.x, tid = threadIdx.x, nl = tid & 31, kq = tid >> 5, n = blockIdx.y * 32 + nl;
-  const float* g = gram + (size_t)img * kGramLd * kGramLd;
-  for (int i = tid; i < KW * KW / 4; i += 128) {
-    const int row = (i * 4) / KW, col = (i * 4) % KW;
-    reinterpret_cast<float4*>(gs)[i] = *reinterpret_cast<const float4*>(g + row * kGramLd + col);
+  const double* g = gram + (size_t)img * kGramLd * kGramLd;
+  for (int i = tid; i < KW * KW / 2; i += 128) {
+    const int row = (i * 2) / KW, col = (i * 2) % KW;
+    const double2 v = *reinterpret_cast<const double2*>(g + row * kGramLd + col);
+    reinterpret_cast<float2*>(gs)[i] = make_float2((float)v.x, (float)v.y);
   }
-  for (int i = tid; i < KW; i += 128) ss[i] = colsum[(size_t)img * kGramLd + i];
+  for (int i = tid; i < KW; i += 128) ss[i] = (float)colsum[(size_t)img * kGramLd + i];
   float w[KW];
   {
     const int jb = n >> 7, r = n & 127;
@@ -554,7 +555,7 @@ bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P) {
   return plan_layout(nseg, segK, Nc, &L);
 }
 
-size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd * kGramLd + kGramLd) * sizeof(float); }
+size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd * kGramLd + kGramLd) * sizeof(double); }
 
 // W: bf16 image packed with block_n = 64 and the x6 scale (PackJob::scale) — see plan.cu / ops_api.cu.
 // scratch: gemm_expand_scratch_bytes(images) bytes, contents irrelevant (zeroed here, on the stream).
@@ -573,7 +574,7 @@ int launch_gemm_expand(const GemmParams& g, void* scratch, int num_sms, cudaStre
   p.nseg = g.nseg; p.nchunks = L.nchunks; p.NB = L.NB; p.stages = L.stages;
   p.W = reinterpret_cast<const bf16*>(g.W);
   p.out = reinterpret_cast<__half*>(g.out);
-  p.gram = reinterpret_cast<float*>(scratch);
+  p.gram = reinterpret_cast<double*>(scratch);
   p.colsum = p.gram + (size_t)images * kGramLd * kGramLd;
   p.m_tiles = (int)(g.M / 128); p.P = g.P; p.Nc = g.Nc;
   p.w_off = L.w_off; p.stg_off = L.stg_off; p.coef_smem_off = L.coef_off; p.misc_off = L.misc_off;

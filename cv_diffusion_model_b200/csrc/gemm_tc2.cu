@@ -37,8 +37,6 @@
 
 namespace lcm {
 
-int launch_gemm_tc_v1(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st);
-
 namespace {
 
 using namespace tc;
@@ -131,7 +129,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   if (warp == 5 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(raw_bar(s), 1);
-      mbar_init(xf_bar(s), 128);
+      mbar_init(xf_bar(s), conv ? 128 : kXfThreads);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -190,7 +188,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               s_coef[p.coef_base[s] + k + 1] = make_float2(c1v.x, 0.f);
             }
           } else {
-            for (int k = ptid; k < p.seg[s].K; k += kXfThreads) s_coef[p.coef_base[s] + k] = src[k];
+            const float sc = p.seg[s].mode == XF_AFFINE_RELU6 ? (1.f / 6.f) : 1.f;   // relu6 as 6 sat(.): see apply_xform
+            for (int k = ptid; k < p.seg[s].K; k += kXfThreads) { const float2 c = src[k]; s_coef[p.coef_base[s] + k] = make_float2(c.x * sc, c.y * sc); }
           }
         }
         bar_sync(1, kXfThreads);
@@ -252,50 +251,60 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         if constexpr (!conv) {
           int mode = p.conv_tma ? (int)XF_NONE : p.seg[sidx].mode;
           if (p.wgate && mode == XF_SCALE) mode = XF_NONE;
-          par ^= 1;
-          if (par != (group ^ 1)) continue;       // chunks alternate between the two groups
+          // all 256 prologue threads work on every chunk (4 units each): with few pipeline stages the LATENCY of a
+          // chunk through this role matters, not just its throughput
           // Every chunk passes through this stage so that xf_bar completes exactly one phase per use of the
           // stage (an mbarrier must never run two phases ahead of its waiter); operands that need no
           // transform (residual / skip input) are only handed on.
           mbar_wait(raw_bar(stage), ring.phase);  // TMA bytes landed (swizzled: unit (row, cu) sits at slot cu ^ (row & 7))
-          if (ci == 0 && gt == 0) TSTAMP(1);
+          if (ci == 0 && ptid == 0) TSTAMP(1);
           if (mode != XF_NONE && !(dbg & 16)) {
             const GemmSeg& sg = p.seg[sidx];
-            uint4 v[8];
+            // unit u = ptid + 256 i: row = u >> 3, smem slot = u & 7 holds channel unit cu = slot ^ (row & 7).  256 units
+            // are 32 rows, so (row & 7) — and with it cu — is the same for all 4 units of a thread: its 8 channels'
+            // coefficients are loaded ONCE per chunk into registers (they used to be re-read from shared memory per
+            // unit with 4-way bank conflicts: ~5000 cycles per chunk, the bottleneck of every K >= 128 expand GEMM).
+            const int cu = (ptid & 7) ^ ((ptid >> 3) & 7);
+            if (cu < upr) {
+              uint4 v[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = ld_s(a_smem + (uint32_t)(gt + i * 128) * 16u);
+              for (int i = 0; i < 4; ++i) v[i] = ld_s(a_smem + (uint32_t)(ptid + i * 256) * 16u);
+              if (kFast && sg.f16 && mode == XF_SCALE) {
+                const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
+                const __half2 g0 = h2bits(__float_as_uint(c4[0].y)), g1 = h2bits(__float_as_uint(c4[1].y));
+                const __half2 g2 = h2bits(__float_as_uint(c4[2].y)), g3 = h2bits(__float_as_uint(c4[3].y));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int u = gt + i * 128;
-              const int row = u >> 3, cu = (u & 7) ^ (row & 7);
-              if (cu < upr) {
-                uint4 o;
-                if (dbg & 256) {
-                  o = v[i];
-                } else if (kFast && sg.f16 && mode == XF_SCALE) {
-                  const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
+                for (int i = 0; i < 4; ++i) {
                   const __half2* hv = reinterpret_cast<const __half2*>(&v[i]);
-                  __half2 r0 = __hmul2(hv[0], h2bits(__float_as_uint(c4[0].y))), r1 = __hmul2(hv[1], h2bits(__float_as_uint(c4[1].y)));
-                  __half2 r2 = __hmul2(hv[2], h2bits(__float_as_uint(c4[2].y))), r3 = __hmul2(hv[3], h2bits(__float_as_uint(c4[3].y)));
-                  o = make_uint4(bits_of(r0), bits_of(r1), bits_of(r2), bits_of(r3));
-                } else if (kFast) {
-                  o = apply_xform(v[i], s_coef + p.coef_base[sidx] + c0 + cu * 8, mode, sg.f16 != 0);
-                } else {
+                  st_s(a_smem + (uint32_t)(ptid + i * 256) * 16u,
+                       make_uint4(bits_of(__hmul2(hv[0], g0)), bits_of(__hmul2(hv[1], g1)), bits_of(__hmul2(hv[2], g2)), bits_of(__hmul2(hv[3], g3))));
+                }
+              } else if (kFast) {
+                __align__(16) float2 ab[8];
+                const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float4 c = c4[j]; ab[2 * j] = make_float2(c.x, c.y); ab[2 * j + 1] = make_float2(c.z, c.w); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  st_s(a_smem + (uint32_t)(ptid + i * 256) * 16u, (dbg & 256) ? v[i] : apply_xform(v[i], ab, mode, sg.f16 != 0, true));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int row = (ptid + i * 256) >> 3;
                   const int mrow = min(m0 + row, M - 1);
                   const int img = mrow / p.P;
                   __align__(16) float2 ab[8];
                   const float2* src = sg.coef + (size_t)img * sg.coef_ld + sg.coef_off + c0 + cu * 8;
 #pragma unroll
                   for (int j = 0; j < 8; ++j) ab[j] = src[j];
-                  o = apply_xform(v[i], ab, mode, sg.f16 != 0);
+                  st_s(a_smem + (uint32_t)(ptid + i * 256) * 16u, apply_xform(v[i], ab, mode, sg.f16 != 0, false));
                 }
-                st_s(a_smem + (uint32_t)u * 16u, o);
               }
             }
             if (!(dbg & 128)) fence_proxy_async();
           }
           mbar_arrive(xf_bar(stage));
-          if (ci == 0 && gt == 0) TSTAMP(2);
+          if (ci == 0 && ptid == 0) TSTAMP(2);
         } else {
           par ^= 1;
           if (par != (group ^ 1)) continue;
@@ -659,15 +668,19 @@ bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const c
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int gemm_tc_pick_block_n(int Nc) {
+  static int forced = -1;   // experiment switch: LCM_BLOCK_N=<n> caps the N tile
+  if (forced < 0) { const char* e = getenv("LCM_BLOCK_N"); forced = e ? atoi(e) : 0; }
+  for (int bn = (forced >= 16 && forced <= 256) ? forced / 16 * 16 : 256; bn >= 16; bn -= 16)
+    if (Nc % bn == 0) return bn;
+  return 0;
+}
+
 int gemm_tc_read_timeline(long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_timeline, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : -1;
 }
 
 int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num_sms, cudaStream_t st) {
-  static int use_v1 = -1;
-  if (use_v1 < 0) { const char* e = getenv("LCM_TC_V1"); use_v1 = (e && atoi(e)) ? 1 : 0; }
-  if (use_v1) return launch_gemm_tc_v1(g, cg, block_n, num_sms, st);
-
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   if (block_n < 16 || block_n > 256 || block_n % 16 || g.Nc % block_n) return -1;

@@ -63,7 +63,7 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
     if (segs[i].f16 && !tc) { cudaFree(wbuf); return LCM_ERR_INVALID; }
     j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = segs[i].f16 ? 2 : (bf ? 1 : 0); j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
     j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = tc ? Kpad : Ktot; j.off = tc ? poff[i] : off[i]; j.block_n = block_n;
-    j.scale = expand ? 6.f : 0.f;
+    j.scale = (tc && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6) ? 6.f : 0.f;   // relu6 prologue = 6 sat(.) on the tcgen05 path
     launch_pack(j, w_dev, st);
     gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
     gp.seg[i].coef = (const float2*)segs[i].coef; gp.seg[i].coef_ld = segs[i].K; gp.seg[i].coef_off = 0;

@@ -191,7 +191,8 @@ namespace {
 struct GemmW {
   size_t off = 0;
   int Nc = 0, Ktot = 0, Kpad = 0, block_n = 0;
-  bool expand = false;   // served by gemm_expand.cu: block_n = 128, weights scaled by 6
+  bool expand = false;   // served by gemm_expand.cu: block_n = 128
+  bool relu6 = false;    // tcgen05 path, relu6 prologue as 6 sat(.): weights scaled by 6
   std::vector<int> seg_off, seg_pad_off;
 };
 
@@ -219,6 +220,7 @@ struct Builder {
     GemmW g;
     g.Nc = Nc;
     g.expand = p->tc && expand_P > 0 && gemm_expand_supported((int)segK.size(), segK.data(), Nc, expand_P);
+    g.relu6 = p->tc && expand_P > 0;
     for (int k : segK) {
       g.seg_off.push_back(g.Ktot);
       g.seg_pad_off.push_back(g.Kpad);
@@ -240,7 +242,7 @@ struct Builder {
     j.ld = p->tc ? g.Kpad : g.Ktot;
     j.off = p->tc ? g.seg_pad_off[seg] : g.seg_off[seg];
     j.block_n = g.block_n;
-    j.scale = g.expand ? 6.f : 0.f;
+    j.scale = g.relu6 ? 6.f : 0.f;
     return j;
   }
 

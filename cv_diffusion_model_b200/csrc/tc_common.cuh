@@ -162,16 +162,27 @@ __device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
 // 16 bytes of activations through the prologue: coef = 8 x (a, b).  XF_AFFINE and XF_AFFINE_RELU6 share one
 // instruction stream (clamp bounds are +-inf for the plain affine) to keep the code small; SiLU is only
 // used by the final conv, which has its own kernel.
-__device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mode, bool f16 = false) {
+// On the tcgen05 path relu6(a x + b) is computed as sat(a/6 x + b/6) in [0, 1] (one FFMA.SAT) and the factor 6 lives in
+// the packed weights of that segment (PackJob::scale).  `prescaled`: the coefficients already carry the 1/6.
+__device__ __forceinline__ uint4 apply_xform(uint4 raw, const float2* ab, int mode, bool f16 = false, bool prescaled = false) {
   float f[8];
   if (f16) unpack8h(raw, f); else unpack8(raw, f);
   const float4* c4 = reinterpret_cast<const float4*>(ab);
-  const float lo = mode == XF_AFFINE_RELU6 ? 0.f : -3.0e38f, hi = mode == XF_AFFINE_RELU6 ? 6.f : 3.0e38f;
+  if (mode == XF_AFFINE_RELU6) {
+    const float k = prescaled ? 1.f : (1.f / 6.f);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 c = c4[j];
-    f[2 * j] = fminf(fmaxf(fmaf(c.x, f[2 * j], c.y), lo), hi);
-    f[2 * j + 1] = fminf(fmaxf(fmaf(c.z, f[2 * j + 1], c.w), lo), hi);
+    for (int j = 0; j < 4; ++j) {
+      const float4 c = c4[j];
+      f[2 * j] = __saturatef(fmaf(c.x * k, f[2 * j], c.y * k));
+      f[2 * j + 1] = __saturatef(fmaf(c.z * k, f[2 * j + 1], c.w * k));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 c = c4[j];
+      f[2 * j] = fmaf(c.x, f[2 * j], c.y);
+      f[2 * j + 1] = fmaf(c.z, f[2 * j + 1], c.w);
+    }
   }
   return f16 ? pack8h(f) : pack8(f);
 }

@@ -9,20 +9,26 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cv_diffusion_model_b200 import native, ops  # noqa: E402
 
-images, P, Ks, Nc, modes = 64, 65536, [32], 128, [2]
-if len(sys.argv) > 1 and sys.argv[1] == "project":
-    Ks, Nc, modes = [128, 32], 32, [1, 0]
+CASES = {
+    "expand0": (64, 65536, [32], 128, [2], [0], 1),
+    "project0": (64, 65536, [128, 32], 32, [4, 0], [1, 0], 0),
+    "expand_d1": (64, 4096, [256, 128], 1536, [2, 2], [0, 0], 1),
+    "expand_d2": (32, 16384, [128, 64], 768, [2, 2], [0, 0], 1),
+    "expand_m": (64, 1024, [256], 1024, [2], [0], 1),
+    "project_m": (64, 1024, [1024, 256], 256, [4, 0], [1, 0], 0),
+}
+images, P, Ks, Nc, modes, h16, o16 = CASES[sys.argv[1] if len(sys.argv) > 1 else "expand0"]
 g = torch.Generator(device="cuda").manual_seed(7)
 M = images * P
 segs = []
-for K, mode in zip(Ks, modes):
-    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+for K, mode, is16 in zip(Ks, modes, h16):
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.float16 if is16 else torch.bfloat16)
     coef = torch.stack([torch.rand(images, K, device="cuda", generator=g) + 0.5,
-                        torch.randn(images, K, device="cuda", generator=g) * 0.3], -1) if mode else None
+                        torch.randn(images, K, device="cuda", generator=g) * (0.0 if mode == 4 else 0.3)], -1) if mode else None
     segs.append((a, coef, mode))
 w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / sum(Ks) ** 0.5
-ops.gemm(segs, w, P, impl=1)
-out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True)
+ops.gemm(segs, w, P, impl=1, out_f16=bool(o16))
+out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True, out_f16=bool(o16))
 buf = (C.c_longlong * 1024)()
 native.lib().lcm_debug_timeline(buf, 1024)
 t0 = min(buf[i] for i in range(16) if buf[i] > 0)
