@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             // coefficients are loaded ONCE per chunk into registers (they used to be re-read from shared memory per
             // unit with 4-way bank conflicts: ~5000 cycles per chunk, the bottleneck of every K >= 128 expand GEMM).
             const int cu = (ptid & 7) ^ ((ptid >> 3) & 7);
+            if (ci == 0 && ptid == 0) TSTAMP(11);
             if (cu < upr) {
               uint4 v[4];
 #pragma unroll
@@ -301,7 +302,9 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 }
               }
             }
+            if (ci == 0 && ptid == 0) TSTAMP(12);
             if (!(dbg & 128)) fence_proxy_async();
+            if (ci == 0 && ptid == 0) TSTAMP(13);
           }
           mbar_arrive(xf_bar(stage));
           if (ci == 0 && ptid == 0) TSTAMP(2);

@@ -590,36 +590,53 @@ void launch_affine_residual(const void* u, const float2* coef, const void* x, vo
 // Bilinear x2 upsampling (F.interpolate(scale_factor=2, mode='bilinear', align_corners=False),
 // efficient_unet.py:383) materialised in bf16 NHWC.  Used by the tensor-core path: the up-convolution then
 // becomes a stride-1 conv whose operand tiles are plain TMA boxes (zero fill = padding); the blend is done once
-// per output pixel instead of once per tap.  Memory-bound: one thread = one output pixel x 8 channels.
+// per output pixel instead of once per tap.  Memory-bound.
+// One thread = one INPUT pixel x 8 channels: its 3x3 neighbourhood (9 loads, mostly L1 hits) yields the 2x2 output
+// quad.  With scale 2 and align_corners=False every output is a fixed (1/4, 3/4) blend: rows {y-1, y} for the even
+// output row, {y, y+1} for the odd one (indices clamped at the border, which reproduces PyTorch's max(src, 0) / min
+// clamping exactly), same along x.  Horizontal blends are shared by the two output rows.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W,
                                                          int C, long long total) {
   const int cvecs = C >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvecs);
     long long q = i / cvecs;
-    const int ux = (int)(q % (2 * W));
-    q /= (2 * W);
-    const int uy = (int)(q % (2 * H));
-    const long long n = q / (2 * H);
-    const float sy = fmaxf(uy * 0.5f - 0.25f, 0.f), sx = fmaxf(ux * 0.5f - 0.25f, 0.f);
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = sy - y0, lx = sx - x0;
+    const int x = (int)(q % W);
+    q /= W;
+    const int y = (int)(q % H);
+    const long long n = q / H;
+    const int ym = max(y - 1, 0), yp = min(y + 1, H - 1), xm = max(x - 1, 0), xp = min(x + 1, W - 1);
     const bf16* b = in + n * (long long)H * W * C + cv * 8;
-    float a[8], bb[8], c[8], d[8], o[8];
-    Vec8<bf16>::load(b + ((long long)y0 * W + x0) * C, a);
-    Vec8<bf16>::load(b + ((long long)y0 * W + x1) * C, bb);
-    Vec8<bf16>::load(b + ((long long)y1 * W + x0) * C, c);
-    Vec8<bf16>::load(b + ((long long)y1 * W + x1) * C, d);
+    float l[3][8], r[3][8];   // per input row: left output column (0.25 x-1 + 0.75 x), right (0.75 x + 0.25 x+1)
+    const int ys[3] = {ym, y, yp};
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * bb[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
-    Vec8<bf16>::store(out + i * 8, o);
+    for (int k = 0; k < 3; ++k) {
+      float a[8], c[8], d[8];
+      Vec8<bf16>::load(b + ((long long)ys[k] * W + xm) * C, a);
+      Vec8<bf16>::load(b + ((long long)ys[k] * W + x) * C, c);
+      Vec8<bf16>::load(b + ((long long)ys[k] * W + xp) * C, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { l[k][j] = 0.25f * a[j] + 0.75f * c[j]; r[k][j] = 0.75f * c[j] + 0.25f * d[j]; }
+    }
+    bf16* o = out + ((n * 2 * H + 2 * y) * 2 * W + 2 * x) * (long long)C + cv * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.25f * l[0][j] + 0.75f * l[1][j];
+    Vec8<bf16>::store(o, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.25f * r[0][j] + 0.75f * r[1][j];
+    Vec8<bf16>::store(o + C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.75f * l[1][j] + 0.25f * l[2][j];
+    Vec8<bf16>::store(o + (long long)2 * W * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.75f * r[1][j] + 0.25f * r[2][j];
+    Vec8<bf16>::store(o + (long long)2 * W * C + C, v);
   }
 }
 
 void launch_upsample2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
-  const long long total = (long long)N * 2 * H * 2 * W * (C / 8);
+  const long long total = (long long)N * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   upsample2x_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)in, (bf16*)out, H, W, C, total);

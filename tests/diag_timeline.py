@@ -32,7 +32,7 @@ out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True, out_f16=boo
 buf = (C.c_longlong * 1024)()
 native.lib().lcm_debug_timeline(buf, 1024)
 t0 = min(buf[i] for i in range(16) if buf[i] > 0)
-names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done"]
+names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done", "xf_cu", "xf_sts", "xf_fence"]
 print(f"{ms*1e3:.1f} us;  cycles relative to first stamp")
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for it in range(0, 40):
