@@ -30,14 +30,16 @@ template <int CO>
 __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restrict__ xa, int ca, long long sa,
                                                            const float* __restrict__ xb, int cb, long long sb,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
-                                                           bf16* __restrict__ out, double* __restrict__ stats, int H, int W) {
+                                                           bf16* __restrict__ out, double* __restrict__ stats, int H, int W,
+                                                           int CoT, int nblk) {
+  // CoT = total output channels; blockIdx.z = image * nblk + channel block (CO channels each: 48 = 3 x 16, 64 = 2 x 32)
   constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 4;   // smem row: 34 used columns, padded to 36
   __shared__ __align__(16) float in_s[2][8][TH + 2][SW_];    // double-buffered fp32 halo tile, filled with cp.async
   __shared__ __align__(16) __half w_s[72][CO];
   __shared__ float red[4][2 * CO];
   const int Cin = ca + cb;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int n = blockIdx.z, x0 = blockIdx.x * TW, yb = blockIdx.y * ROWS;
+  const int n = blockIdx.z / nblk, co0 = (blockIdx.z % nblk) * CO, x0 = blockIdx.x * TW, yb = blockIdx.y * ROWS;
   const int yend = min(yb + ROWS, H);
   // stage the halo tile of rows [y0-1, y0+TH] asynchronously: one warp per (channel, row) line, 4-byte cp.async with
   // zero fill outside the image — nothing is held in registers while the previous tile is being computed
@@ -58,10 +60,10 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage(yb, 0);
-  for (int i = tid; i < 9 * Cin * CO; i += 128) w_s[i / CO][i % CO] = __float2half_rn(w[i]);
+  for (int i = tid; i < 9 * Cin * CO; i += 128) w_s[i / CO][i % CO] = __float2half_rn(w[(size_t)(i / CO) * CoT + co0 + i % CO]);
   __half2 bias2[CO / 2];
 #pragma unroll
-  for (int j = 0; j < CO / 2; ++j) bias2[j] = __floats2half2_rn(bias[2 * j], bias[2 * j + 1]);
+  for (int j = 0; j < CO / 2; ++j) bias2[j] = __floats2half2_rn(bias[co0 + 2 * j], bias[co0 + 2 * j + 1]);
   float s[CO], q[CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) { s[c] = 0.f; q[c] = 0.f; }
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
         if (gx + px < W) {
-          bf16* o = out + (((size_t)n * H + gy) * W + gx + px) * CO;
+          bf16* o = out + (((size_t)n * H + gy) * W + gx + px) * CoT + co0;
 #pragma unroll
           for (int v = 0; v < CO / 8; ++v) {
             uint32_t pk[4];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
   if (tid < 2 * CO) {
     const float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     const int c = tid < CO ? tid : tid - CO;
-    atomicAdd(&stats[((size_t)n * CO + c) * 2 + (tid < CO ? 0 : 1)], (double)v);
+    atomicAdd(&stats[((size_t)n * CoT + co0 + c) * 2 + (tid < CO ? 0 : 1)], (double)v);
   }
 }
 
@@ -255,10 +257,11 @@ __global__ void __launch_bounds__(128) final_conv_h2_kernel(const bf16* __restri
 
 bool launch_init_conv_h2(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const float* w,
                          const float* bias, void* out, double* stats, int N, int H, int W, int Co, cudaStream_t st) {
-  if (ca + cb > 8 || (Co != 16 && Co != 32)) return false;
-  dim3 grid((W + 31) / 32, (H + 63) / 64, N);
-  if (Co == 32) init_conv_h2_kernel<32><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W);
-  else init_conv_h2_kernel<16><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W);
+  if (ca + cb > 8 || (Co != 16 && Co != 32 && Co != 48 && Co != 64)) return false;
+  const int CO = Co % 32 == 0 ? 32 : 16, nblk = Co / CO;
+  dim3 grid((W + 31) / 32, (H + 63) / 64, N * nblk);
+  if (CO == 32) init_conv_h2_kernel<32><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
+  else init_conv_h2_kernel<16><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
   return true;
 }
 
