@@ -368,11 +368,20 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       TileIter ti; ti.init(t_begin, m_tiles, p.P);
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
+      int last_stage = -1; uint32_t last_phase = 0;   // ring slot / phase of the last activation chunk issued
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
         if (p.resident) {
+          // conv + resident weights: this warp issues nothing per tile, so it follows the MMA warp tile by tile (a
+          // parity wait is only meaningful when the waiter is less than one phase behind)
+          if (conv && it > 0) mbar_wait(tfull_bar(acc), aphase);
           if (ti.n_tile != cur_nt || (p.wgate && ti.img != cur_img)) {
-            if (it > 0) mbar_wait(tfull_bar(acc), aphase);   // MMAs of the previous tile done: old weights dead
+            // The previous tile's MMAs must be done before its weights are overwritten.  This warp runs up to `stages`
+            // chunks (several tiles when K is small) ahead of the MMA warp, so it must NOT wait on tfull with a parity:
+            // two phases behind looks like "done" (that was a race on the K = 160 project GEMMs).  The empty barrier of
+            // the last chunk it issued is exact: it is committed after that tile's last MMA, and this warp is never
+            // more than one phase away from it.
+            if (!conv && last_stage >= 0) mbar_wait(empty_bar(last_stage), last_phase);
             if (elect_one()) {
               mbar_expect_tx(bres_bar, (uint32_t)p.nchunks * b_chunk_bytes);
               for (int ci = 0; ci < p.nchunks; ++ci)
@@ -408,6 +417,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               bulk_g2s(a_smem + kStageA2, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, raw_bar(stage));
           }
           __syncwarp();
+          last_stage = stage; last_phase = ring.phase;
         }
       }
     }
