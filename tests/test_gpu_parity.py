@@ -224,8 +224,9 @@ def test_production_size_reproducible_and_parity():
     torch.manual_seed(5)
     noi8 = torch.stack([torch.randn(8, 3, 256, 256) for _ in range(3)])
     a = pipe.enhance(low8.cuda(), latents=lat8.cuda(), noises=noi8.cuda())
-    b_ = pipe.enhance(low8.cuda(), latents=lat8.cuda(), noises=noi8.cuda())
-    assert torch.equal(a, b_)
+    for _ in range(3):   # the third call onwards replays the captured CUDA graph of the loop (engine.py)
+        b_ = pipe.enhance(low8.cuda(), latents=lat8.cuda(), noises=noi8.cuda())
+        assert torch.equal(a, b_)
     # parity at batch 2 (the oracle runs on the host cores: ~10 s)
     low, lat0, noises = low8[:2].contiguous(), lat8[:2].contiguous(), noi8[:, :2].contiguous()
     res = pipe.enhance(low.cuda(), latents=lat0.cuda(), noises=noises.cuda(), return_intermediate=True)
