@@ -128,25 +128,27 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 // Squeeze-and-Excitation gate (efficient_unet.py:96-100) as two batched row-GEMVs:
 //   hid[n][j]  = relu6(b1[j] + sum_c w1[j][c] * mean[n][c])          (mean = pooled sum * inv_count)
 //   gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * hid[n][j])         -> prologue coefficient (gate, 0)
-// A block stages the inputs of 4 images in shared memory; each of its warps walks 8 weight rows (a row is held in
-// registers while the 4 images are applied), so the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per
-// 4 images and the inputs once per 64 rows.
+// A block stages the inputs of 16 images in shared memory; each of its warps walks 2 weight rows (a row is held in
+// registers while the 16 images are applied), so the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per
+// 16 images and the inputs once per 16 rows.
 template <bool kFirst>
 __global__ void __launch_bounds__(256) se_fc_kernel(const void* __restrict__ in_, float scale, const float* __restrict__ W,
                                                     const float* __restrict__ bias, void* __restrict__ out_, int N, int R,
                                                     int K) {
-  constexpr int IMGS = 4, ROWS_PER_WARP = 8;   // block = 4 images x 64 rows: inputs staged once, weights read once per 4 images
+  constexpr int IMGS = 16, ROWS_PER_WARP = 2;   // block = 16 images x 16 rows: weights are read once per 16 images
+                                                 // (they are the traffic: 2 x 4 MB at the 2048-wide blocks), inputs once per 16 rows
   extern __shared__ __align__(16) float xin[];   // [IMGS][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * IMGS, n1 = min(N, n0 + IMGS);
-  for (int i = 0; i < IMGS; ++i)
-    for (int k = threadIdx.x; k < K; k += 256) {
-      float v = 0.f;
-      if (n0 + i < n1)
-        v = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)(n0 + i) * K + k] * scale
-                   : reinterpret_cast<const float*>(in_)[(size_t)(n0 + i) * K + k];
-      xin[i * K + k] = v;
-    }
+  const int nimg = n1 - n0;
+#pragma unroll 8
+  for (int idx = threadIdx.x; idx < IMGS * K; idx += 256) {   // flat and unrolled: 8 independent loads in flight per thread
+    float v = 0.f;
+    if (idx < nimg * K)
+      v = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)n0 * K + idx] * scale
+                 : reinterpret_cast<const float*>(in_)[(size_t)n0 * K + idx];
+    xin[idx] = v;
+  }
   __syncthreads();
   const bool vec = (K & 3) == 0;
   for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
@@ -201,13 +203,13 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const void* __restrict__ in_
 
 void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st) {
-  const int chunks = (N + 3) / 4;
-  const size_t sm1 = (size_t)4 * C * sizeof(float), sm2 = (size_t)4 * SQ * sizeof(float);
+  const int chunks = (N + 15) / 16;
+  const size_t sm1 = (size_t)16 * C * sizeof(float), sm2 = (size_t)16 * SQ * sizeof(float);
   static size_t attr1 = 48 * 1024, attr2 = 48 * 1024;   // dynamic shared memory opted in so far
   if (sm1 > attr1) { cudaFuncSetAttribute(se_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1); attr1 = sm1; }
   if (sm2 > attr2) { cudaFuncSetAttribute(se_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); attr2 = sm2; }
-  se_fc_kernel<true><<<dim3((SQ + 63) / 64, chunks), 256, sm1, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
-  se_fc_kernel<false><<<dim3((C + 63) / 64, chunks), 256, sm2, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
+  se_fc_kernel<true><<<dim3((SQ + 15) / 16, chunks), 256, sm1, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
+  se_fc_kernel<false><<<dim3((C + 15) / 16, chunks), 256, sm2, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
 }
 
 // ------------------------------------------------------------------------------------------------
