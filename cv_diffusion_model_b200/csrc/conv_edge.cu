@@ -22,27 +22,37 @@ __device__ __forceinline__ __half2 h2(uint32_t u) { return *reinterpret_cast<__h
 __device__ __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// init_conv: block = 128 threads = 32 x 8 pixel tile, two horizontally adjacent pixels per thread, all CO outputs
-// in registers as half2 pairs; the block walks 64 rows so that weights / statistics are set up once per 2048 pixels.
-// Per tap and input channel: CO/8 broadcast LDS.128 of weights feed CO HFMA2 (both pixels).  54 terms per output are
-// accumulated in fp16: the result is rounded to bf16 (8 bits) anyway.
+// init_conv as an implicit GEMM on mma.sync (m16n8k16, fp16 operands, fp32 accumulation): K = 9 * Cin <= 80, N = CO.
+// The packed-HFMA2 version was instruction-bound (ncu: 57 % issue utilisation at 3 blocks per SM, ~2000 thread
+// instructions per pixel); here a warp spends 8 LDS.32 + 4 cvt + CO/8 HMMA per 16 pixels and K step.  tcgen05 is the
+// wrong tool for a 54-deep contraction over fp32 NCHW inputs: the operand would have to be im2col'ed through shared
+// memory in the UMMA layout first.
+//   block = 128 threads = 32 x 8 pixel tile (warp = 2 rows = four 16-pixel m-tiles), walks 64 rows; the fp32 NCHW halo
+//   tile is staged with 4-byte cp.async (double-buffered, zero fill outside the image); A fragments are gathered from it
+//   with per-thread precomputed (channel, tap) offsets; B fragments (weights) live in registers for the whole block.
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <int CO>
-__global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restrict__ xa, int ca, long long sa,
-                                                           const float* __restrict__ xb, int cb, long long sb,
-                                                           const float* __restrict__ w, const float* __restrict__ bias,
-                                                           bf16* __restrict__ out, double* __restrict__ stats, int H, int W,
-                                                           int CoT, int nblk) {
+__global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restrict__ xa, int ca, long long sa,
+                                                            const float* __restrict__ xb, int cb, long long sb,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            bf16* __restrict__ out, double* __restrict__ stats, int H, int W,
+                                                            int CoT, int nblk) {
   // CoT = total output channels; blockIdx.z = image * nblk + channel block (CO channels each: 48 = 3 x 16, 64 = 2 x 32)
   constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 4;   // smem row: 34 used columns, padded to 36
-  __shared__ __align__(16) float in_s[2][8][TH + 2][SW_];    // double-buffered fp32 halo tile, filled with cp.async
-  __shared__ __align__(16) __half w_s[72][CO];
+  constexpr int CH_PITCH = (TH + 2) * SW_;                  // floats per input channel plane
+  constexpr int NT = CO / 8, KS = 5, PPITCH = CO * 2 + 16;  // n-tiles, max K steps, output patch row pitch (bytes)
+  __shared__ __align__(16) float in_s[2][8 * CH_PITCH];     // double-buffered fp32 halo tile, filled with cp.async
+  __shared__ __align__(16) uint8_t patch[4][16 * PPITCH];   // per warp: 16 pixels x CO bf16, transposed for 16-byte stores
   __shared__ float red[4][2 * CO];
-  const int Cin = ca + cb;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int Cin = ca + cb, K = 9 * Cin, ksteps = (K + 15) / 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int n = blockIdx.z / nblk, co0 = (blockIdx.z % nblk) * CO, x0 = blockIdx.x * TW, yb = blockIdx.y * ROWS;
   const int yend = min(yb + ROWS, H);
-  // stage the halo tile of rows [y0-1, y0+TH] asynchronously: one warp per (channel, row) line, 4-byte cp.async with
-  // zero fill outside the image — nothing is held in registers while the previous tile is being computed
   auto stage = [&](int y0, int buf) {
     for (int line = tid >> 5; line < Cin * (TH + 2); line += 4) {
       const int ci = line / (TH + 2), r = line - ci * (TH + 2);
@@ -53,20 +63,42 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
       for (int c = tid & 31; c < TW + 2; c += 32) {
         const int gx = x0 + c - 1;
         const bool ok = yok && gx >= 0 && gx < W;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&in_s[buf][ci][r][c]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&in_s[buf][ci * CH_PITCH + r * SW_ + c]);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   stage(yb, 0);
-  for (int i = tid; i < 9 * Cin * CO; i += 128) w_s[i / CO][i % CO] = __float2half_rn(w[(size_t)(i / CO) * CoT + co0 + i % CO]);
-  __half2 bias2[CO / 2];
+  // k = tap * Cin + ci (the packed weight order).  This thread's fragment columns: k0 = 16 ks + 2t + {0, 1, 8, 9}
+  int koff[KS][4];
+  uint32_t bfr[KS][NT][2];
 #pragma unroll
-  for (int j = 0; j < CO / 2; ++j) bias2[j] = __floats2half2_rn(bias[co0 + 2 * j], bias[co0 + 2 * j + 1]);
-  float s[CO], q[CO];
+  for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-  for (int c = 0; c < CO; ++c) { s[c] = 0.f; q[c] = 0.f; }
+    for (int q = 0; q < 4; ++q) {
+      const int k = ks * 16 + 2 * t + (q & 1) + (q >> 1) * 8;
+      const int tap = k / Cin, ci = k - tap * Cin;
+      koff[ks][q] = k < K ? ci * CH_PITCH + (tap / 3) * SW_ + tap % 3 : 0;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = co0 + nt * 8 + g;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = ks * 16 + 2 * t + hh * 8;
+        const float w0 = k < K ? w[(size_t)k * CoT + col] : 0.f, w1 = k + 1 < K ? w[(size_t)(k + 1) * CoT + col] : 0.f;
+        const __half2 hw = __floats2half2_rn(w0, w1);
+        bfr[ks][nt][hh] = u32(hw);
+      }
+    }
+  }
+  float bia[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { bia[nt][0] = bias[co0 + nt * 8 + 2 * t]; bia[nt][1] = bias[co0 + nt * 8 + 2 * t + 1]; }
+  float s[NT][2], q2[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = q2[nt][0] = q2[nt][1] = 0.f; }
 
   int buf = 0;
   for (int y0 = yb; y0 < yend; y0 += TH, buf ^= 1) {
@@ -76,61 +108,68 @@ __global__ void __launch_bounds__(128) init_conv_h2_kernel(const float* __restri
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();   // this tile's data (and, first time round, the weights) are visible to every thread
-    __half2 a0[CO / 2], a1[CO / 2];
+    __syncthreads();
+    const float* tile = in_s[buf];
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      const int row = 2 * warp + (mt >> 1), xh = (mt & 1) * 16;
+      const int base = row * SW_ + xh + g;
+      float c[NT][4];
 #pragma unroll
-    for (int j = 0; j < CO / 2; ++j) { a0[j] = bias2[j]; a1[j] = bias2[j]; }
-    for (int dy = 0; dy < 3; ++dy) {
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float2 f01 = *reinterpret_cast<const float2*>(&in_s[buf][ci][ty + dy][2 * tx]);
-        const float2 f23 = *reinterpret_cast<const float2*>(&in_s[buf][ci][ty + dy][2 * tx + 2]);
-        const __half2 c01 = __floats2half2_rn(f01.x, f01.y), c23 = __floats2half2_rn(f23.x, f23.y);
-        const __half2 col[4] = {__low2half2(c01), __high2half2(c01), __low2half2(c23), __high2half2(c23)};
+      for (int nt = 0; nt < NT; ++nt) { c[nt][0] = c[nt][2] = bia[nt][0]; c[nt][1] = c[nt][3] = bia[nt][1]; }
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const uint4* wr = reinterpret_cast<const uint4*>(&w_s[(dy * 3 + dx) * Cin + ci][0]);
+      for (int ks = 0; ks < KS; ++ks) {
+        if (ks < ksteps) {
+          uint32_t a[4];
+          a[0] = u32(__floats2half2_rn(tile[base + koff[ks][0]], tile[base + koff[ks][1]]));
+          a[1] = u32(__floats2half2_rn(tile[base + 8 + koff[ks][0]], tile[base + 8 + koff[ks][1]]));
+          a[2] = u32(__floats2half2_rn(tile[base + koff[ks][2]], tile[base + koff[ks][3]]));
+          a[3] = u32(__floats2half2_rn(tile[base + 8 + koff[ks][2]], tile[base + 8 + koff[ks][3]]));
 #pragma unroll
-          for (int v = 0; v < CO / 8; ++v) {
-            const uint4 w4 = wr[v];
-            a0[4 * v + 0] = __hfma2(h2(w4.x), col[dx], a0[4 * v + 0]); a1[4 * v + 0] = __hfma2(h2(w4.x), col[dx + 1], a1[4 * v + 0]);
-            a0[4 * v + 1] = __hfma2(h2(w4.y), col[dx], a0[4 * v + 1]); a1[4 * v + 1] = __hfma2(h2(w4.y), col[dx + 1], a1[4 * v + 1]);
-            a0[4 * v + 2] = __hfma2(h2(w4.z), col[dx], a0[4 * v + 2]); a1[4 * v + 2] = __hfma2(h2(w4.z), col[dx + 1], a1[4 * v + 2]);
-            a0[4 * v + 3] = __hfma2(h2(w4.w), col[dx], a0[4 * v + 3]); a1[4 * v + 3] = __hfma2(h2(w4.w), col[dx + 1], a1[4 * v + 3]);
-          }
+          for (int nt = 0; nt < NT; ++nt) mma_16816(c[nt], a, bfr[ks][nt][0], bfr[ks][nt][1]);
         }
       }
-    }
-    const int gy = y0 + ty, gx = x0 + 2 * tx;
-    if (gy < H) {
+      // ---- epilogue: bf16, statistics of the stored values, transpose through the warp's patch, 16-byte stores ----
+      const int gy = y0 + row;
+      const bool v0 = gy < H && x0 + xh + g < W, v1 = gy < H && x0 + xh + g + 8 < W;
+      uint8_t* pw = patch[warp];
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        if (gx + px < W) {
-          bf16* o = out + (((size_t)n * H + gy) * W + gx + px) * CoT + co0;
-#pragma unroll
-          for (int v = 0; v < CO / 8; ++v) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(px ? a1[4 * v + e] : a0[4 * v + e]);
-              pk[e] = pack_bf16(f.x, f.y);
-              const float r0 = bf16lo(pk[e]), r1 = bf16hi(pk[e]);   // statistics of the stored values
-              s[8 * v + 2 * e] += r0; q[8 * v + 2 * e] = fmaf(r0, r0, q[8 * v + 2 * e]);
-              s[8 * v + 2 * e + 1] += r1; q[8 * v + 2 * e + 1] = fmaf(r1, r1, q[8 * v + 2 * e + 1]);
-            }
-            *reinterpret_cast<uint4*>(o + 8 * v) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t p0 = pack_bf16(c[nt][0], c[nt][1]), p1 = pack_bf16(c[nt][2], c[nt][3]);
+        *reinterpret_cast<uint32_t*>(pw + g * PPITCH + nt * 16 + t * 4) = p0;
+        *reinterpret_cast<uint32_t*>(pw + (g + 8) * PPITCH + nt * 16 + t * 4) = p1;
+        if (v0) {
+          const float r0 = bf16lo(p0), r1 = bf16hi(p0);
+          s[nt][0] += r0; q2[nt][0] = fmaf(r0, r0, q2[nt][0]); s[nt][1] += r1; q2[nt][1] = fmaf(r1, r1, q2[nt][1]);
+        }
+        if (v1) {
+          const float r0 = bf16lo(p1), r1 = bf16hi(p1);
+          s[nt][0] += r0; q2[nt][0] = fmaf(r0, r0, q2[nt][0]); s[nt][1] += r1; q2[nt][1] = fmaf(r1, r1, q2[nt][1]);
         }
       }
+      __syncwarp();
+      constexpr int UPP = CO / 8;   // 16-byte units per pixel
+#pragma unroll
+      for (int i = lane; i < 16 * UPP; i += 32) {
+        const int px = i / UPP, unit = i % UPP;
+        if (gy < H && x0 + xh + px < W) {
+          const uint4 v = *reinterpret_cast<const uint4*>(pw + px * PPITCH + unit * 16);
+          *reinterpret_cast<uint4*>(out + (((size_t)n * H + gy) * W + x0 + xh + px) * CoT + co0 + unit * 8) = v;
+        }
+      }
+      __syncwarp();
     }
     __syncthreads();   // everyone is done reading in_s[buf] before the next-but-one stage overwrites it
   }
-  // ---- statistics: warp shuffle tree, fixed-order sum over the 4 warps, one fp64 atomic per (block, channel, moment)
+  // ---- statistics: reduce over the 8 row lanes (g), fixed-order sum over the 4 warps, one fp64 atomic per channel ----
 #pragma unroll
-  for (int c = 0; c < CO; ++c) {
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s[c] += __shfl_xor_sync(0xffffffffu, s[c], o); q[c] += __shfl_xor_sync(0xffffffffu, q[c], o); }
-    if ((tid & 31) == 0) { red[tid >> 5][c] = s[c]; red[tid >> 5][CO + c] = q[c]; }
-  }
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { s[nt][j] += __shfl_xor_sync(0xffffffffu, s[nt][j], o); q2[nt][j] += __shfl_xor_sync(0xffffffffu, q2[nt][j], o); }
+      if (g == 0) { red[warp][nt * 8 + 2 * t + j] = s[nt][j]; red[warp][CO + nt * 8 + 2 * t + j] = q2[nt][j]; }
+    }
   __syncthreads();
   if (tid < 2 * CO) {
     const float v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
@@ -260,8 +299,8 @@ bool launch_init_conv_h2(const float* xa, int ca, long long sa, const float* xb,
   if (ca + cb > 8 || (Co != 16 && Co != 32 && Co != 48 && Co != 64)) return false;
   const int CO = Co % 32 == 0 ? 32 : 16, nblk = Co / CO;
   dim3 grid((W + 31) / 32, (H + 63) / 64, N * nblk);
-  if (CO == 32) init_conv_h2_kernel<32><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
-  else init_conv_h2_kernel<16><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
+  if (CO == 32) init_conv_mma_kernel<32><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
+  else init_conv_mma_kernel<16><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
   return true;
 }
 
