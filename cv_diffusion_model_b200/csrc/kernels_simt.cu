@@ -467,30 +467,36 @@ __device__ __forceinline__ float phi(float x) { return x > 0.f ? x + 1.f : expf(
 template <typename T>
 __global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv, double* __restrict__ state, int P,
                                                       int heads) {
+  // a block reduces up to 256 positions (4 tiles of 64) in registers before touching the fp64 state: 4x fewer
+  // atomics than one tile per block (1024 positions per block left too few blocks in flight: measured slower)
   __shared__ float ks[64][33], vs[64][33];
-  const int n = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * 64;
+  const int n = blockIdx.z, h = blockIdx.y;
   const int inner = heads * 32, ld = 3 * inner;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 64 * 32; i += 256) {
-    const int pp = i >> 5, d = i & 31;
-    const int p = p0 + pp;
-    float k = 0.f, v = 0.f;
-    if (p < P) {
-      const T* row = qkv + ((size_t)n * P + p) * ld;
-      k = phi(to_f<T>(row[inner + h * 32 + d]));
-      v = to_f<T>(row[2 * inner + h * 32 + d]);
-    }
-    ks[pp][d] = k;   // zero (not phi(0)=1) beyond P so that padding does not contribute
-    vs[pp][d] = v;
-  }
-  __syncthreads();
   const int d = tid >> 3, e0 = (tid & 7) * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, ksum = 0.f;
-  for (int pp = 0; pp < 64; ++pp) {
-    const float k = ks[pp][d];
-    ksum += k;
+  const int pend = min(P, (int)(blockIdx.x + 1) * 256);
+  for (int p0 = blockIdx.x * 256; p0 < pend; p0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 32; i += 256) {
+      const int pp = i >> 5, dd = i & 31;
+      const int p = p0 + pp;
+      float k = 0.f, v = 0.f;
+      if (p < P) {
+        const T* row = qkv + ((size_t)n * P + p) * ld;
+        k = phi(to_f<T>(row[inner + h * 32 + dd]));
+        v = to_f<T>(row[2 * inner + h * 32 + dd]);
+      }
+      ks[pp][dd] = k;   // zero (not phi(0)=1) beyond P so that padding does not contribute
+      vs[pp][dd] = v;
+    }
+    __syncthreads();
+    for (int pp = 0; pp < 64; ++pp) {
+      const float k = ks[pp][d];
+      ksum += k;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = fmaf(k, vs[pp][e0 + j], acc[j]);
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(k, vs[pp][e0 + j], acc[j]);
+    }
   }
   double* s = state + (((size_t)n * heads + h) * 32 + d) * 33;
 #pragma unroll
@@ -529,7 +535,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ q
 }
 
 void launch_attn_kv(const void* qkv, double* state, int N, int P, int heads, int bf16act, cudaStream_t st) {
-  dim3 grid((P + 63) / 64, heads, N);
+  dim3 grid((P + 255) / 256, heads, N);
   if (bf16act) attn_kv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, state, P, heads);
   else attn_kv_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, state, P, heads);
 }

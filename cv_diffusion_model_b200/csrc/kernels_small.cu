@@ -50,33 +50,63 @@ void launch_time_embed(const long long* t_dev, long long t_scalar, int N, int ba
 }
 
 // ------------------------------------------------------------------------------------------------
-// All blocks' FiLM projections (efficient_unet.py:189-192,215): one warp per output row, looping
-// over the batch with the weight row held in registers.
-__global__ void film_kernel(const float* __restrict__ s, const float* __restrict__ W, const float* __restrict__ b,
-                            float* __restrict__ out, int N, int rows, int ted) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float w[16];  // ted <= 512
-  const int per = (ted + 31) / 32;
+// All blocks' FiLM projections (efficient_unet.py:189-192,215) as one small GEMM out[n][r] = b[r] + W[r][:] . s[n][:]
+// (rows = 2 x sum of hidden widths ~ 30 000, ted = 128, N = 64).  Block = 64 rows x up to 64 images: the activations
+// (transposed, [k][image]) and the weight tile are staged in shared memory per 128-wide k slab; a warp owns 8 rows,
+// lane = image (and image + 32), four rows at a time: 4 broadcast + 2 strided LDS feed 8 FMAs, no shuffles.
+__global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ s, const float* __restrict__ W, const float* __restrict__ b,
+                                                   float* __restrict__ out, int N, int rows, int ted) {
+  constexpr int KS = 64;                   // k slab
+  __shared__ float st[KS][64 + 1];         // [k][image]; reused as the [image][row] output tile
+  __shared__ float ws[64][KS + 4];         // [row][k]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[8][2];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) w[j] = (j < per && j * 32 + lane < ted) ? W[(size_t)row * ted + j * 32 + lane] : 0.f;
-  const float bias = b[row];
-  for (int n = 0; n < N; ++n) {
-    float acc = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.f;
+  for (int k0 = 0; k0 < ted; k0 += KS) {
+    const int kw = min(KS, ted - k0);
+    __syncthreads();
+    for (int i = tid; i < 64 * KS; i += 256) {
+      const int n = i / KS, k = i % KS;
+      st[k][n] = (n0 + n < N && k < kw) ? s[(size_t)(n0 + n) * ted + k0 + k] : 0.f;
+      ws[n][k] = (r0 + n < rows && k < kw) ? W[(size_t)(r0 + n) * ted + k0 + k] : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < per && j * 32 + lane < ted) acc = fmaf(w[j], s[(size_t)n * ted + j * 32 + lane], acc);
+    for (int half = 0; half < 2; ++half) {
+      const float* w0 = ws[warp * 8 + half * 4];
+#pragma unroll 4
+      for (int k = 0; k < KS; ++k) {
+        const float x0 = st[k][lane], x1 = st[k][lane + 32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[(size_t)n * rows + row] = acc + bias;
+        for (int i = 0; i < 4; ++i) {
+          const float wv = w0[i * (KS + 4) + k];
+          acc[half * 4 + i][0] = fmaf(wv, x0, acc[half * 4 + i][0]);
+          acc[half * 4 + i][1] = fmaf(wv, x1, acc[half * 4 + i][1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float (*ot)[64 + 1] = st;                // [image][row] (64 x 65 floats fit in st)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = warp * 8 + i;
+    const float bias = r0 + r < rows ? b[r0 + r] : 0.f;
+    ot[lane][r] = acc[i][0] + bias;
+    ot[lane + 32][r] = acc[i][1] + bias;
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * 64; i += 256) {
+    const int n = i >> 6, r = i & 63;
+    if (n0 + n < N && r0 + r < rows) out[(size_t)(n0 + n) * rows + r0 + r] = ot[n][r];
   }
 }
 
 void launch_film(const float* silu_temb, const float* W, const float* b, float* out, int N, int rows, int ted,
                  cudaStream_t st) {
-  const int warps = 8;
-  film_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(silu_temb, W, b, out, N, rows, ted);
+  film_kernel<<<dim3((rows + 63) / 64, (N + 63) / 64), 256, 0, st>>>(silu_temb, W, b, out, N, rows, ted);
 }
 
 // ------------------------------------------------------------------------------------------------
