@@ -1,6 +1,7 @@
-// The two dense 3x3 convolutions at the edges of the UNet on the bf16 tensor-core plan, as CUDA-core kernels built
-// around packed fp16 math (HFMA2: two MACs per instruction).  Both are tiny in FLOPs but move full-resolution
-// tensors, so the goal is simply to stay out of the way of the HBM stream:
+// The two dense 3x3 convolutions at the edges of the UNet on the bf16 tensor-core plan.  Both are tiny in FLOPs but move
+// full-resolution tensors, so the goal is simply to stay out of the way of the HBM stream.  init_conv is an implicit GEMM
+// on mma.sync (legacy HMMA path: ~0.15 ms of tensor time for its 17 GFLOP, measured), final_conv packed-fp16 CUDA-core
+// math (its N = 3 wastes 5/8 of an m16n8k16 tile: the mma.sync version measured slower, 0.37 vs 0.32 ms):
 //
 //   init_conv  (efficient_unet.py:420,553 fused with the conditioning concat, low_light_diffusion.py:222):
 //              fp32 NCHW latents + condition (6 channels) -> bf16 NHWC C0 channels + GroupNorm statistics
