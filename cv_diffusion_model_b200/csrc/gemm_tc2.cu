@@ -44,6 +44,7 @@ using namespace tc;
 constexpr int kThreads2 = 704;
 constexpr int kE2Base = 192, kE2Threads = 256, kXfBase = 448, kXfThreads = 256;
 constexpr uint32_t kStageA2 = 16384;
+constexpr uint32_t kHaloBytes = 130u * 3u * 128u, kHaloStage = 51200;   // [3 rows][130 px][64 ch] bf16, stage rounded to 1 KB
 constexpr int kMaxChunks2 = 160;
 constexpr uint32_t kSmemLimit2 = 232448;
 constexpr uint32_t kMisc2 = 4096 + 16384;
@@ -65,6 +66,8 @@ struct alignas(64) Tc2Params {
   int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
   int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
+  int conv_halo, achunks; // halo mode: ONE [64 ch][130 px][3 rows] load per tile and 64-channel chunk serves all 9 taps
+                          // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
         int ty0 = 0, tx0 = 0;               // conv_tma: first pixel of this tile inside its image
         if (p.conv_tma) { ty0 = ti.rem / p.Win; tx0 = ti.rem - ty0 * p.Win; }
-        for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
+        for (int ci = 0; ci < p.achunks; ++ci, ring.advance()) {
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
           const uint32_t a_smem = sbase + stage * p.stage_bytes;
@@ -404,9 +407,11 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (ci == 0) TSTAMP(0);
           const bool load_a = !conv && !(dbg & 1);
           if (elect_one()) {
-            mbar_expect_tx(raw_bar(stage), (load_a ? kStageA2 : 0u) + (p.resident ? 0u : b_chunk_bytes));
+            mbar_expect_tx(raw_bar(stage), (load_a ? (p.conv_halo ? kHaloBytes : kStageA2) : 0u) + (p.resident ? 0u : b_chunk_bytes));
             if (load_a) {
-              if (p.conv_tma) {
+              if (p.conv_halo) {
+                tma_load_4d(a_smem, &p.tmap[0], ci * 64, tx0 - 1, ty0 - 1, ti.img, raw_bar(stage));
+              } else if (p.conv_tma) {
                 const int tap = cd & 0x7f, ky = tap / 3, kx = tap - ky * 3;
                 tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), tx0 + kx - 1, ty0 + ky - 1, ti.img, raw_bar(stage));
               } else {
@@ -444,6 +449,34 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         TSTAMP(3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
+        if (p.conv_halo) {
+          // one halo stage per 64-channel chunk; tap (ky, kx) is the same buffer read from pixel (ky * 130 + kx) on —
+          // a shift by whole 128-byte rows inside the SWIZZLE_128B pattern the TMA wrote
+          const int nchh = p.achunks;
+          for (int ci = 0; ci < nchh; ++ci, ring.advance()) {
+            const int stage = ring.stage;
+            mbar_wait(raw_bar(stage), ring.phase);
+            if (ci == 0) TSTAMP(4);
+            tc_fence_after();
+            const int ksteps = (int)((p.chunk[ci] >> 8) & 0xff) >> 4;
+            const uint32_t a_base = sbase + stage * p.stage_bytes;
+            if (elect_one()) {
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * 130 + tap % 3) * 128u;
+                // start address shifted by whole 128-B rows: the swizzle phase follows the absolute smem
+                // address (measured: base_offset must stay 0, setting (addr>>7)&7 double-counts the shift)
+                const uint64_t ad = umma_desc(a_addr);
+                const uint64_t bd = umma_desc(sbase + p.bres_off + (uint32_t)(tap * nchh + ci) * b_chunk_bytes);
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_b, (ci | tap | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty_bar(stage));
+              if (ci == nchh - 1) umma_commit(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (ci == nchh - 1) TSTAMP(5);
+          }
+        } else
         for (int ci = 0; ci < p.nchunks; ++ci, ring.advance()) {
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
@@ -741,6 +774,16 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
         p.conv_tma = 1;
         p.box_w = bw;
         p.conv_mode = -1;   // runs the TMA-fed (non-gather) kernel variant
+        // halo mode: tile = 128 pixels of one image row, weights of all 9 taps resident next to >= 2 halo stages
+        static int no_halo = -1;
+        if (no_halo < 0) { const char* e = getenv("LCM_CONV_NO_HALO"); no_halo = (e && atoi(e)) ? 1 : 0; }
+        const int nchh = (cg.Ci + 63) / 64;
+        const uint32_t wres = 9u * nchh * (uint32_t)block_n * 128u;
+        const uint32_t stg1 = (128u * ((uint32_t)block_n * 2u + 16u) + 1023u) & ~1023u;
+        if (!no_halo && bw == 128 && wres <= 131072 && kMisc2 + 2048 + stg1 + wres + 2 * kHaloStage <= kSmemLimit2) {
+          if (!image_map(g.seg[0].A, (int)imgs, H, W, cg.Ci, 130, 3, &p.tmap[0])) return -3;
+          p.conv_halo = 1;
+        }
       }
     }
     for (int tap = 0; tap < 9; ++tap)
@@ -751,6 +794,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
       }
   }
   p.nchunks = nch;
+  p.achunks = p.conv_halo ? (cg.Ci + 63) / 64 : nch;
   p.ncoef = ncoef;
   bool has_gate = false;
   if (p.conv_mode < 0 && !p.conv_tma)
@@ -782,7 +826,8 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
       raw &= g.seg[s2].mode == XF_NONE || (p.wgate && g.seg[s2].mode == XF_SCALE);
     p.all_raw = raw ? 1 : 0;
   }
-  p.stage_bytes = kStageA2 + (p.resident ? 0u : b_chunk);
+  p.stage_bytes = p.conv_halo ? kHaloStage : kStageA2 + (p.resident ? 0u : b_chunk);
+  if (p.conv_halo && !p.resident) return -1;
   const uint32_t used1 = base_fixed + stg_bytes + (p.resident ? bres : 0u);
   p.nbuf = (used1 + stg_bytes + 4 * p.stage_bytes <= kSmemLimit2) ? 2 : 1;
   const uint32_t used = used1 + (p.nbuf == 2 ? stg_bytes : 0u);

@@ -96,7 +96,7 @@ def test_gemm(images, P, Ks, Nc, modes, dtype, impl):
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("N,H,W,Ci,Co", [(2, 16, 16, 32, 32), (1, 8, 12, 64, 64), (2, 8, 8, 128, 128), (1, 8, 8, 48, 48),
                                         (1, 4, 4, 256, 256), (1, 16, 32, 64, 64), (2, 32, 32, 128, 128), (3, 2, 128, 32, 32),
-                                        (1, 4, 256, 96, 96)])
+                                        (1, 4, 256, 96, 96), (2, 8, 128, 64, 64), (1, 6, 256, 64, 64), (2, 4, 384, 16, 16)])
 def test_conv3x3(N, H, W, Ci, Co, mode, dtype, impl):
     from cv_diffusion_model_b200 import ops
     if impl == 1 and os.environ.get("LCM_SKIP_TC"):
