@@ -37,9 +37,10 @@ void launch_dwconv(const void* in, const float2* coef, const float* w, void* out
 int launch_dwconv_f16(const void* in, const float2* coef, const float* w, void* out, double* pool, int N, int H, int W,
                       int C, int num_sms, cudaStream_t st);
 
-// ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0); hid = scratch [N][SQ] (2 launches) -----
-void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
-                    const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st);
+// ---- a4.5: SE gate: sigmoid(fc2(relu6(fc1(mean)))) -> coef (gate, 0); one launch (8-CTA clusters, 8 images each).
+// Returns non-zero when the layer does not fit (shared memory).
+int launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st);
 
 // ---- a3/a6/a7: dense 3x3 convs ------------------------------------------------------------------
 enum Conv3Mode : int { CONV_S1 = 0, CONV_S2 = 1, CONV_UP2 = 2 };

@@ -155,91 +155,130 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Squeeze-and-Excitation gate (efficient_unet.py:96-100) as two batched row-GEMVs:
+// Squeeze-and-Excitation gate (efficient_unet.py:96-100) as two batched row-GEMVs in ONE launch:
 //   hid[n][j]  = relu6(b1[j] + sum_c w1[j][c] * mean[n][c])          (mean = pooled sum * inv_count)
 //   gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * hid[n][j])         -> prologue coefficient (gate, 0)
-// A block stages the inputs of 16 images in shared memory; each of its warps walks 2 weight rows (a row is held in
-// registers while the 16 images are applied), so the FC weights — 2 x 4 MB at the 2048-wide blocks — are read once per
-// 16 images and the inputs once per 16 rows.
-template <bool kFirst>
-__global__ void __launch_bounds__(256) se_fc_kernel(const void* __restrict__ in_, float scale, const float* __restrict__ W,
-                                                    const float* __restrict__ bias, void* __restrict__ out_, int N, int R,
-                                                    int K) {
-  constexpr int IMGS = 16, ROWS_PER_WARP = 2;   // block = 16 images x 16 rows: weights are read once per 16 images
-                                                 // (they are the traffic: 2 x 4 MB at the 2048-wide blocks), inputs once per 16 rows
-  extern __shared__ __align__(16) float xin[];   // [IMGS][K]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * IMGS, n1 = min(N, n0 + IMGS);
-  const int nimg = n1 - n0;
-#pragma unroll 8
-  for (int idx = threadIdx.x; idx < IMGS * K; idx += 256) {   // flat and unrolled: 8 independent loads in flight per thread
-    float v = 0.f;
-    if (idx < nimg * K)
-      v = kFirst ? (float)reinterpret_cast<const double*>(in_)[(size_t)n0 * K + idx] * scale
-                 : reinterpret_cast<const float*>(in_)[(size_t)n0 * K + idx];
-    xin[idx] = v;
-  }
-  __syncthreads();
-  const bool vec = (K & 3) == 0;
-  for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-    const int r = (blockIdx.x * 8 + warp) * ROWS_PER_WARP + rr;
-    if (r >= R) break;
-    const float* wr = W + (size_t)r * K;
-    float acc[IMGS];
+// The gate sits on the serial chain depthwise -> gate -> project of every block, so what it costs is latency, not
+// bandwidth (two dependent launches used to cost ~32 us per block inside the graph, 0.7 ms per forward).
+// A thread-block CLUSTER of 8 CTAs owns 8 images: each CTA stages the 8 pooled vectors, computes 1/8 of the hidden
+// rows, the slices are exchanged through distributed shared memory, then each CTA computes 1/8 of the gate rows.
+// A weight row is split over just enough lanes (float4 per lane), several rows per warp when rows are short.
+constexpr int SE_IMG = 8, SE_CL = 8, SE_THREADS = 512;
+
+template <class Emit>
+__device__ __forceinline__ void se_fc_rows(const float* __restrict__ W, const float* __restrict__ xs, int K, int r0, int r1,
+                                           Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = SE_THREADS / 32;
+  if ((K & 3) == 0) {
+    const int units = K >> 2;
+    int lpr = 32;
+    while (lpr > 1 && (lpr >> 1) >= units) lpr >>= 1;
+    const int rpp = 32 / lpr, sub = lane / lpr, sl = lane - sub * lpr;
+    for (int rb = r0 + warp * rpp; rb < r1; rb += nw * rpp) {
+      const int r = rb + sub;
+      float acc[SE_IMG];
 #pragma unroll
-    for (int i = 0; i < IMGS; ++i) acc[i] = 0.f;
-    if (vec) {
-      // 2048-wide slabs of the row: 16 independent 16-byte weight loads per lane in flight (the kernel is latency-bound)
-      for (int k0 = 0; k0 < K; k0 += 2048) {
-        float4 w4[16];
+      for (int i = 0; i < SE_IMG; ++i) acc[i] = 0.f;
+      if (r < r1) {
+        const float4* wr = reinterpret_cast<const float4*>(W + (size_t)r * K);
+#pragma unroll 4
+        for (int u = sl; u < units; u += lpr) {
+          const float4 w = __ldg(wr + u);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int k = k0 + c * 128 + lane * 4;
-          w4[c] = k < K ? *reinterpret_cast<const float4*>(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int k = k0 + c * 128 + lane * 4;
-          if (k < K) {
-#pragma unroll
-            for (int i = 0; i < IMGS; ++i) {
-              const float4 x = *reinterpret_cast<const float4*>(xin + i * K + k);
-              acc[i] = fmaf(w4[c].x, x.x, acc[i]); acc[i] = fmaf(w4[c].y, x.y, acc[i]);
-              acc[i] = fmaf(w4[c].z, x.z, acc[i]); acc[i] = fmaf(w4[c].w, x.w, acc[i]);
-            }
+          for (int i = 0; i < SE_IMG; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(xs + i * K + u * 4);
+            acc[i] = fmaf(w.x, x.x, acc[i]); acc[i] = fmaf(w.y, x.y, acc[i]);
+            acc[i] = fmaf(w.z, x.z, acc[i]); acc[i] = fmaf(w.w, x.w, acc[i]);
           }
         }
       }
-    } else {
-      for (int k = lane; k < K; k += 32) {
-        const float w = wr[k];
+      for (int o = lpr >> 1; o > 0; o >>= 1) {
 #pragma unroll
-        for (int i = 0; i < IMGS; ++i) acc[i] = fmaf(w, xin[i * K + k], acc[i]);
+        for (int i = 0; i < SE_IMG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
       }
+      if (r < r1 && sl == 0) emit(r, acc);
     }
-    const float b = bias[r];
+  } else {
+    for (int r = r0 + warp; r < r1; r += nw) {
+      float acc[SE_IMG];
 #pragma unroll
-    for (int i = 0; i < IMGS; ++i) {
-      float a = acc[i];
+      for (int i = 0; i < SE_IMG; ++i) acc[i] = 0.f;
+      for (int k = lane; k < K; k += 32) {
+        const float w = __ldg(W + (size_t)r * K + k);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0 && n0 + i < n1) {
-        if (kFirst) reinterpret_cast<float*>(out_)[(size_t)(n0 + i) * R + r] = fminf(fmaxf(a + b, 0.f), 6.f);
-        else reinterpret_cast<float2*>(out_)[(size_t)(n0 + i) * R + r] = make_float2(1.f / (1.f + expf(-(a + b))), 0.f);
+        for (int i = 0; i < SE_IMG; ++i) acc[i] = fmaf(w, xs[i * K + k], acc[i]);
       }
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < SE_IMG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      }
+      if (lane == 0) emit(r, acc);
     }
   }
 }
 
-void launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
-                    const float* b2, float* hid, float2* coef, int N, int C, int SQ, cudaStream_t st) {
-  const int chunks = (N + 15) / 16;
-  const size_t sm1 = (size_t)16 * C * sizeof(float), sm2 = (size_t)16 * SQ * sizeof(float);
-  static size_t attr1 = 48 * 1024, attr2 = 48 * 1024;   // dynamic shared memory opted in so far
-  if (sm1 > attr1) { cudaFuncSetAttribute(se_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1); attr1 = sm1; }
-  if (sm2 > attr2) { cudaFuncSetAttribute(se_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); attr2 = sm2; }
-  se_fc_kernel<true><<<dim3((SQ + 15) / 16, chunks), 256, sm1, st>>>(pool, inv_count, w1, b1, hid, N, SQ, C);
-  se_fc_kernel<false><<<dim3((C + 15) / 16, chunks), 256, sm2, st>>>(hid, 1.f, w2, b2, coef, N, C, SQ);
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(SE_THREADS)
+se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __restrict__ w1, const float* __restrict__ b1,
+               const float* __restrict__ w2, const float* __restrict__ b2, float2* __restrict__ coef, int N, int C, int SQ) {
+  extern __shared__ __align__(16) float se_sm[];
+  const int sqr = (SQ + SE_CL - 1) / SE_CL;         // hidden rows per CTA
+  float* xs = se_sm;                                // [SE_IMG][C] pooled means
+  float* hid = xs + SE_IMG * C;                     // [SE_IMG][SQ] all hidden rows (after the exchange)
+  float* mine = hid + SE_IMG * SQ;                  // [SE_IMG][sqr] this CTA's slice
+  const uint32_t rank = cluster_ctarank();
+  const int n0 = (blockIdx.x / SE_CL) * SE_IMG, nimg = min(SE_IMG, N - n0);
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < SE_IMG * C; idx += SE_THREADS)
+    xs[idx] = idx < nimg * C ? (float)pool[(size_t)n0 * C + idx] * inv_count : 0.f;
+  __syncthreads();
+  const int h0 = (int)rank * sqr, h1 = min(SQ, h0 + sqr);
+  se_fc_rows(w1, xs, C, h0, h1, [&](int r, const float* acc) {
+    const float b = b1[r];
+#pragma unroll
+    for (int i = 0; i < SE_IMG; ++i) mine[i * sqr + (r - h0)] = fminf(fmaxf(acc[i] + b, 0.f), 6.f);
+  });
+  cluster_sync_all();
+  for (int idx = threadIdx.x; idx < SE_IMG * SQ; idx += SE_THREADS) {
+    const int i = idx / SQ, j = idx - i * SQ;
+    const int src = j / sqr;
+    hid[idx] = ld_dsmem(mine + i * sqr + (j - src * sqr), (uint32_t)src);
+  }
+  cluster_sync_all();   // every peer has finished reading this CTA's slice (and hid is complete CTA-wide)
+  const int cr = (C + SE_CL - 1) / SE_CL;
+  const int c0 = (int)rank * cr, c1 = min(C, c0 + cr);
+  se_fc_rows(w2, hid, SQ, c0, c1, [&](int r, const float* acc) {
+    const float b = b2[r];
+#pragma unroll
+    for (int i = 0; i < SE_IMG; ++i)
+      if (i < nimg) coef[(size_t)(n0 + i) * C + r] = make_float2(1.f / (1.f + expf(-(acc[i] + b))), 0.f);
+  });
+}
+
+int launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st) {
+  const int sqr = (SQ + SE_CL - 1) / SE_CL;
+  const size_t sm = ((size_t)SE_IMG * C + (size_t)SE_IMG * SQ + (size_t)SE_IMG * sqr) * sizeof(float);
+  if (sm > 200 * 1024) return 1;
+  static size_t attr = 48 * 1024;   // dynamic shared memory opted in so far
+  if (sm > attr) {
+    if (cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 1;
+    attr = sm;
+  }
+  const int clusters = (N + SE_IMG - 1) / SE_IMG;
+  se_gate_kernel<<<clusters * SE_CL, SE_THREADS, sm, st>>>(pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
