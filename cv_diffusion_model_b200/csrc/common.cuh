@@ -8,6 +8,34 @@ namespace lcm {
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A forward is ~190 short dependent launches; with plain stream order every boundary pays the launch latency, the
+// block scheduling and the next kernel's prologue (barrier init, TMEM allocation, tensor-map fetch) after the previous
+// grid has drained.  Every kernel of the path therefore (1) calls pdl_trigger() once its own prologue is done, which lets
+// the NEXT grid's blocks become resident as this grid's blocks retire, and (2) calls pdl_wait() before its first access
+// to global memory: it returns when the previous grid has completed and its writes are visible.  Both are no-ops for a
+// launch without the attribute, so the same kernels run under ops_api / the SIMT plan unchanged.
+// LCM_NO_PDL=1 launches everything with plain stream order (A/B timing, debugging).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // plan.cu
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
+
 // ---- prologue transform applied to an activation element as it is read -------------------------
 enum XformMode : int {
   XF_NONE = 0,         // y = x

@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restr
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             bf16* __restrict__ out, double* __restrict__ stats, int H, int W,
                                                             int CoT, int nblk) {
+  pdl_wait();
+  pdl_trigger();
   // CoT = total output channels; blockIdx.z = image * nblk + channel block (CO channels each: 48 = 3 x 16, 64 = 2 x 32)
   constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 4;   // smem row: 34 used columns, padded to 36
   constexpr int CH_PITCH = (TH + 2) * SW_;                  // floats per input channel plane
@@ -189,6 +191,8 @@ template <int CI>
 __global__ void __launch_bounds__(128) final_conv_h2_kernel(const bf16* __restrict__ in, const float2* __restrict__ coef,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             float* __restrict__ eps, FinalStep step, int H, int W, int Co) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int TW = 64, TH = 8, PW = TW + 2, PH = TH + 2;
   extern __shared__ __align__(16) uint8_t fsm_raw[];
   constexpr int NCH = CI / 8;
@@ -300,8 +304,8 @@ bool launch_init_conv_h2(const float* xa, int ca, long long sa, const float* xb,
   if (ca + cb > 8 || (Co != 16 && Co != 32 && Co != 48 && Co != 64)) return false;
   const int CO = Co % 32 == 0 ? 32 : 16, nblk = Co / CO;
   dim3 grid((W + 31) / 32, (H + 63) / 64, N * nblk);
-  if (CO == 32) init_conv_mma_kernel<32><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
-  else init_conv_mma_kernel<16><<<grid, 128, 0, st>>>(xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
+  if (CO == 32) launch_pdl(init_conv_mma_kernel<32>, grid, dim3(128), 0, st, xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
+  else launch_pdl(init_conv_mma_kernel<16>, grid, dim3(128), 0, st, xa, ca, sa, xb, cb, sb, w, bias, (bf16*)out, stats, H, W, Co, nblk);
   return true;
 }
 
@@ -311,17 +315,17 @@ bool launch_final_conv_h2(const void* in, const float2* coef, const float* w, co
   dim3 grid((W + 63) / 64, (H + 7) / 8, N);
   const size_t smem = ((size_t)10 * 66 * Ci + 9 * Ci * 3) * sizeof(__half);
   switch (Ci) {
-    case 16: final_conv_h2_kernel<16><<<grid, 128, smem, st>>>((const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
-    case 32: final_conv_h2_kernel<32><<<grid, 128, smem, st>>>((const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
+    case 16: launch_pdl(final_conv_h2_kernel<16>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
+    case 32: launch_pdl(final_conv_h2_kernel<32>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     case 48: {
       static bool done = false;
       if (!done) { cudaFuncSetAttribute(final_conv_h2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-      final_conv_h2_kernel<48><<<grid, 128, smem, st>>>((const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
+      launch_pdl(final_conv_h2_kernel<48>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     }
     default: {
       static bool done = false;
       if (!done) { cudaFuncSetAttribute(final_conv_h2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-      final_conv_h2_kernel<64><<<grid, 128, smem, st>>>((const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
+      launch_pdl(final_conv_h2_kernel<64>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     }
   }
   return true;

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(STRIPS * 32, 512 / (STRIPS * 32)) dwconv_strea
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap)) : "memory");
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
 
   // ---- producer (thread 0, interleaved with its consumer work): keep the ring full -----------------------
   // Its state lives in shared memory so that it costs the 255 other threads (and the hot loop) no registers.
@@ -320,7 +322,7 @@ int launch_strips(DwParams& p, int num_sms, cudaStream_t st) {
   p.segsY = (p.H + hseg - 1) / hseg;
   p.items = items_for(hseg);
   const int grid = p.items < max_ctas ? p.items : max_ctas;
-  fn<<<grid, threads, smem, st>>>(p);
+  launch_pdl(fn, dim3(grid), dim3(threads), smem, st, p);
   return 0;
 }
 

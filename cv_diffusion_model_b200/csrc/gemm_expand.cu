@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   const int t_begin = (int)((long long)p.m_tiles * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)p.m_tiles * (blockIdx.x + 1) / gridDim.x);
@@ -429,6 +431,8 @@ __global__ void __launch_bounds__(128) expand_stats_kernel(const double* __restr
   double* part = reinterpret_cast<double*>(wt + KW * 32);
   const int img = blockIdx.x, tid = threadIdx.x, nl = tid & 31, kq = tid >> 5, n = blockIdx.y * 32 + nl;
   const double* g = gram + (size_t)img * kGramLd * kGramLd;
+  pdl_wait();
+  pdl_trigger();
   for (int i = tid; i < KW * KW / 2; i += 128) {
     const int row = (i * 2) / KW, col = (i * 2) % KW;
     const double2 v = *reinterpret_cast<const double2*>(g + row * kGramLd + col);
@@ -558,8 +562,9 @@ bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P) {
 size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd * kGramLd + kGramLd) * sizeof(double); }
 
 // W: bf16 image packed with block_n = 64 and the x6 scale (PackJob::scale) — see plan.cu / ops_api.cu.
-// scratch: gemm_expand_scratch_bytes(images) bytes, contents irrelevant (zeroed here, on the stream).
-int launch_gemm_expand(const GemmParams& g, void* scratch, int num_sms, cudaStream_t st) {
+// scratch: gemm_expand_scratch_bytes(images) bytes; zero_scratch: clear it here, on the stream (the plan hands in a slice
+// of its zeroed region instead, which keeps a memset node out of every block of the graph).
+int launch_gemm_expand(const GemmParams& g, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st) {
   if (g.nseg < 1 || g.nseg > 2 || !g.out_f16 || !g.stats || !scratch || g.P % 128 || g.M % g.P || g.M <= 0 || g.M > 0x7fffff00LL) return -1;
   int segK[2] = {0, 0};
   for (int s = 0; s < g.nseg; ++s) {
@@ -599,14 +604,18 @@ int launch_gemm_expand(const GemmParams& g, void* scratch, int num_sms, cudaStre
       attr_done = true;
     }
   }
-  if (cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(images), st) != cudaSuccess) return -2;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
-  gemm_expand_kernel<<<grid, kThreadsX, L.total, st>>>(p);
+  if (zero_scratch) {
+    if (cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(images), st) != cudaSuccess) return -2;
+    gemm_expand_kernel<<<grid, kThreadsX, L.total, st>>>(p);
+  } else {
+    launch_pdl(gemm_expand_kernel, dim3(grid), dim3(kThreadsX), L.total, st, p);
+  }
   const dim3 sg(images, g.Nc / 32);
   if (L.nchunks == 1)
-    expand_stats_kernel<64><<<sg, 128, (64 * 64 + 64 + 64 * 32 + 512) * 4, st>>>(p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
+    launch_pdl(expand_stats_kernel<64>, sg, dim3(128), (size_t)(64 * 64 + 64 + 64 * 32 + 512) * 4, st, p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
   else
-    expand_stats_kernel<128><<<sg, 128, (128 * 128 + 128 + 128 * 32 + 512) * 4, st>>>(p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
+    launch_pdl(expand_stats_kernel<128>, sg, dim3(128), (size_t)(128 * 128 + 128 + 128 * 32 + 512) * 4, st, p.gram, p.colsum, p.W, g.stats, g.Nc, L.nchunks);
   return 0;
 }
 

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above is CTA-local; from here on the previous kernel's output is read
+  pdl_trigger();
 
   const int m_tiles = (int)p.m_tiles;
   const long long total_tiles = p.m_tiles * p.n_tiles;
@@ -861,7 +863,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
       attr_done[(void*)fn] = true;
     }
   }
-  fn<<<grid, kThreads2, smem_bytes, st>>>(p);
+  launch_pdl(fn, dim3(grid), dim3(kThreads2), smem_bytes, st, p);
   return 0;
 }
 

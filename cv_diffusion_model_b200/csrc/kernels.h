@@ -137,8 +137,8 @@ int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_
 // Expand GEMM specialisation (gemm_expand.cu): bf16 segments with relu6(a x + b) prologue, fp16 output + statistics,
 // weights packed with block_n = 128 and scale = 6.  `supported` is a pure shape test (plan time).
 bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P);
-size_t gemm_expand_scratch_bytes(int images);   // Gram / column-sum scratch (contents irrelevant; zeroed on the stream)
-int launch_gemm_expand(const GemmParams& p, void* scratch, int num_sms, cudaStream_t st);
+size_t gemm_expand_scratch_bytes(int images);   // Gram / column-sum scratch; must be zero at launch (zero_scratch: cleared on the stream)
+int launch_gemm_expand(const GemmParams& p, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st);
 int gemm_expand_read_timeline(long long* host, int n);   // debug: LCM_X_TIMELINE=1
 int gemm_tc_pick_block_n(int Nc);
 int gemm_tc_read_timeline(long long* host, int n);   // debug: per-tile clock stamps of block 0 (LCM_TC_DEBUG & 64)

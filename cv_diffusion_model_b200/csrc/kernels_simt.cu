@@ -467,6 +467,8 @@ __device__ __forceinline__ float phi(float x) { return x > 0.f ? x + 1.f : expf(
 template <typename T>
 __global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv, double* __restrict__ state, int P,
                                                       int heads) {
+  pdl_wait();
+  pdl_trigger();
   // a block reduces up to 256 positions (4 tiles of 64) in registers before touching the fp64 state: 4x fewer
   // atomics than one tile per block (1024 positions per block left too few blocks in flight: measured slower)
   __shared__ float ks[64][33], vs[64][33];
@@ -508,6 +510,8 @@ __global__ void __launch_bounds__(256) attn_kv_kernel(const T* __restrict__ qkv,
 template <typename T>
 __global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ qkv, const double* __restrict__ state,
                                                          T* __restrict__ out, int P, int heads) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float kv[32][33];
   __shared__ float qs[64][33];
   const int n = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * 64;
@@ -536,14 +540,14 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const T* __restrict__ q
 
 void launch_attn_kv(const void* qkv, double* state, int N, int P, int heads, int bf16act, cudaStream_t st) {
   dim3 grid((P + 255) / 256, heads, N);
-  if (bf16act) attn_kv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, state, P, heads);
-  else attn_kv_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, state, P, heads);
+  if (bf16act) launch_pdl(attn_kv_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)qkv, state, P, heads);
+  else launch_pdl(attn_kv_kernel<float>, grid, dim3(256), 0, st, (const float*)qkv, state, P, heads);
 }
 void launch_attn_apply(const void* qkv, const double* state, void* out, int N, int P, int heads, int bf16act,
                        cudaStream_t st) {
   dim3 grid((P + 63) / 64, heads, N);
-  if (bf16act) attn_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, state, (bf16*)out, P, heads);
-  else attn_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, state, (float*)out, P, heads);
+  if (bf16act) launch_pdl(attn_apply_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)qkv, state, (bf16*)out, P, heads);
+  else launch_pdl(attn_apply_kernel<float>, grid, dim3(256), 0, st, (const float*)qkv, state, (float*)out, P, heads);
 }
 
 // =================================================================================================
@@ -553,6 +557,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) affine_residual_kernel(const T* __restrict__ u, const float2* __restrict__ coef,
                                                               const T* __restrict__ x, T* __restrict__ y,
                                                               double* __restrict__ stats, int P, int C) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y, p0 = blockIdx.x * 64;
   const int cvecs = C / 8;
   for (int cv = threadIdx.x; cv < cvecs; cv += blockDim.x) {
@@ -588,8 +594,8 @@ void launch_affine_residual(const void* u, const float2* coef, const void* x, vo
                             int C, int bf16act, cudaStream_t st) {
   dim3 grid((P + 63) / 64, N);
   int threads = C / 8 < 32 ? 32 : (C / 8 > 256 ? 256 : ((C / 8 + 31) / 32) * 32);
-  if (bf16act) affine_residual_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)u, coef, (const bf16*)x, (bf16*)y, stats, P, C);
-  else affine_residual_kernel<float><<<grid, threads, 0, st>>>((const float*)u, coef, (const float*)x, (float*)y, stats, P, C);
+  if (bf16act) launch_pdl(affine_residual_kernel<bf16>, dim3(grid), dim3(threads), 0, st, (const bf16*)u, coef, (const bf16*)x, (bf16*)y, stats, P, C);
+  else launch_pdl(affine_residual_kernel<float>, dim3(grid), dim3(threads), 0, st, (const float*)u, coef, (const float*)x, (float*)y, stats, P, C);
 }
 
 // =================================================================================================
@@ -603,6 +609,8 @@ void launch_affine_residual(const void* u, const float2* coef, const void* x, vo
 // clamping exactly), same along x.  Horizontal blends are shared by the two output rows.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W,
                                                          int C, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const int cvecs = C >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvecs);
@@ -645,7 +653,7 @@ void launch_upsample2x(const void* in, void* out, int N, int H, int W, int C, cu
   const long long total = (long long)N * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
-  upsample2x_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)in, (bf16*)out, H, W, C, total);
+  launch_pdl(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, st, (const bf16*)in, (bf16*)out, H, W, C, total);
 }
 
 }  // namespace lcm

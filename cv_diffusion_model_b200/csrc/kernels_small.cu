@@ -56,6 +56,8 @@ void launch_time_embed(const long long* t_dev, long long t_scalar, int N, int ba
 // lane = image (and image + 32), four rows at a time: 4 broadcast + 2 strided LDS feed 8 FMAs, no shuffles.
 __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ s, const float* __restrict__ W, const float* __restrict__ b,
                                                    float* __restrict__ out, int N, int rows, int ted) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int KS = 64;                   // k slab
   __shared__ float st[KS][64 + 1];         // [k][image]; reused as the [image][row] output tile
   __shared__ float ws[64][KS + 4];         // [row][k]
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ s, 
 
 void launch_film(const float* silu_temb, const float* W, const float* b, float* out, int N, int rows, int ted,
                  cudaStream_t st) {
-  film_kernel<<<dim3((rows + 63) / 64, (N + 63) / 64), 256, 0, st>>>(silu_temb, W, b, out, N, rows, ted);
+  launch_pdl(film_kernel, dim3((rows + 63) / 64, (N + 63) / 64), dim3(256), 0, st, silu_temb, W, b, out, N, rows, ted);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +118,8 @@ __global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const doub
                                int groups, double count, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                                float2* __restrict__ coef) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.x;
   const int C = C0 + C1;
@@ -151,7 +155,7 @@ __global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const doub
 void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
                     const float* gamma, const float* beta, const float* film, int film_ld, float2* coef, int N,
                     cudaStream_t st) {
-  gn_coef_kernel<<<N, 256, 0, st>>>(stats0, C0, stats1, C1, groups, count, gamma, beta, film, film_ld, coef);
+  launch_pdl(gn_coef_kernel, dim3(N), dim3(256), 0, st, stats0, C0, stats1, C1, groups, count, gamma, beta, film, film_ld, coef);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -239,11 +243,25 @@ se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __
   float* mine = hid + SE_IMG * SQ;                  // [SE_IMG][sqr] this CTA's slice
   const uint32_t rank = cluster_ctarank();
   const int n0 = (blockIdx.x / SE_CL) * SE_IMG, nimg = min(SE_IMG, N - n0);
+  const int h0 = (int)rank * sqr, h1 = min(SQ, h0 + sqr);
+  const int cr = (C + SE_CL - 1) / SE_CL;
+  const int c0 = (int)rank * cr, c1 = min(C, c0 + cr);
+  // the FC weights do not depend on the previous kernel: pull this CTA's rows towards L2 while the depthwise conv
+  // that feeds the pool is still draining (activations of GBs pass through L2 between two uses of these weights)
+  {
+    const char* a = reinterpret_cast<const char*>(w1 + (size_t)h0 * C);
+    const long long na = (long long)max(h1 - h0, 0) * C * 4;
+    for (long long o = (long long)threadIdx.x * 128; o < na; o += SE_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+    const char* b = reinterpret_cast<const char*>(w2 + (size_t)c0 * SQ);
+    const long long nb = (long long)max(c1 - c0, 0) * SQ * 4;
+    for (long long o = (long long)threadIdx.x * 128; o < nb; o += SE_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+  }
+  pdl_wait();
+  pdl_trigger();
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < SE_IMG * C; idx += SE_THREADS)
     xs[idx] = idx < nimg * C ? (float)pool[(size_t)n0 * C + idx] * inv_count : 0.f;
   __syncthreads();
-  const int h0 = (int)rank * sqr, h1 = min(SQ, h0 + sqr);
   se_fc_rows(w1, xs, C, h0, h1, [&](int r, const float* acc) {
     const float b = b1[r];
 #pragma unroll
@@ -256,8 +274,6 @@ se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __
     hid[idx] = ld_dsmem(mine + i * sqr + (j - src * sqr), (uint32_t)src);
   }
   cluster_sync_all();   // every peer has finished reading this CTA's slice (and hid is complete CTA-wide)
-  const int cr = (C + SE_CL - 1) / SE_CL;
-  const int c0 = (int)rank * cr, c1 = min(C, c0 + cr);
   se_fc_rows(w2, hid, SQ, c0, c1, [&](int r, const float* acc) {
     const float b = b2[r];
 #pragma unroll
@@ -277,7 +293,7 @@ int launch_se_gate(const double* pool, float inv_count, const float* w1, const f
     attr = sm;
   }
   const int clusters = (N + SE_IMG - 1) / SE_IMG;
-  se_gate_kernel<<<clusters * SE_CL, SE_THREADS, sm, st>>>(pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ);
+  launch_pdl(se_gate_kernel, dim3(clusters * SE_CL), dim3(SE_THREADS), sm, st, pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ);
   return 0;
 }
 

@@ -79,7 +79,7 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   Timer t(st, ms_out, repeat);
   for (int r = 0; r < repeat && rc == 0; ++r) {
     if (expand && repeat > 1 && stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)(M / P) * Nc * 2 * sizeof(double), st);   // the finalisation kernel owns its entries
-    if (expand) rc = launch_gemm_expand(gp, xscratch, sms, st);
+    if (expand) rc = launch_gemm_expand(gp, xscratch, true, sms, st);
     else if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
     else launch_gemm_simt(gp, bf, st);
   }

@@ -24,6 +24,13 @@
 
 using namespace lcm;
 
+namespace lcm {
+bool pdl_enabled() {
+  static const bool on = !getenv("LCM_NO_PDL");
+  return on;
+}
+}  // namespace lcm
+
 namespace {
 
 thread_local std::string g_err;
@@ -144,7 +151,6 @@ struct lcm_plan {
 
   int film_rows = 0;
   size_t film_f_off = 0, silu_f_off = 0;
-  size_t xscratch_f_off = 0;   // Gram / column-sum scratch shared by all expand-kernel launches (stream-ordered)
 
   std::vector<Op> ops;
   std::map<std::string, TensorP> tap_map;
@@ -269,6 +275,8 @@ struct Builder {
             double bytes, double flops) {
     lcm_plan* pl = p; const int n = N;
     std::vector<SegSpec> sg = segs;
+    // Gram / column-sum scratch of the expand kernel: a slice of the region zeroed at the start of the forward
+    const size_t xs = (pl->tc && w.expand) ? p->zalloc(gemm_expand_scratch_bytes(N)) : 0;
     push(name, pl->tc ? (w.expand ? "gemm_expand" : "gemm_tc") : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
       GemmParams gp{};
       gp.nseg = (int)sg.size();
@@ -290,7 +298,7 @@ struct Builder {
       gp.M = (long long)n * gp.P;
       gp.Nc = w.Nc;
       gp.out_f16 = out->f16 ? 1 : 0;
-      if (pl->tc && w.expand) { if (launch_gemm_expand(gp, c.f + pl->xscratch_f_off, pl->num_sms, st)) *c.launch_err = 1; }
+      if (pl->tc && w.expand) { if (launch_gemm_expand(gp, c.z + xs, false, pl->num_sms, st)) *c.launch_err = 1; }
       else if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });
@@ -502,7 +510,6 @@ int build_plan(lcm_plan* p) {
   };
   const int ted = c.time_embed_dim, base = c.base_channels;
 
-  if (p->tc) p->xscratch_f_off = p->falloc(gemm_expand_scratch_bytes(N));
   // a2: time embedding (efficient_unet.py:550)
   {
     const size_t w1 = p->add_copy("time_mlp.1.weight", (int64_t)ted * base), b1 = p->add_copy("time_mlp.1.bias", ted);

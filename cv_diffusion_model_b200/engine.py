@@ -6,6 +6,7 @@ FLOP of the hot path is executed by ``liblcmunet.so`` through the C ABI (include
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -51,7 +52,6 @@ class Engine:
         self.workspace = torch.empty(self.lib.lcm_plan_workspace_bytes(handle), dtype=torch.uint8, device=self.device)
         self._weight_version = None
         self._graphs: Dict[tuple, dict] = {}
-        import os
         self._use_graph = not os.environ.get("LCM_NO_GRAPH")
         self.upload_weights()
 
@@ -143,9 +143,14 @@ class Engine:
             ent["tr"] = torch.empty(steps, b, 3, h, w, dtype=torch.float32, device=latents.device) if trace else None
             with torch.cuda.device(self.device):
                 g = torch.cuda.CUDAGraph()
+                dump = os.environ.get("LCM_GRAPH_DUMP")     # diagnostic: write the captured graph as a dot file
+                if dump:
+                    g.enable_debug_mode()
                 with torch.cuda.graph(g):
                     call(ent["cond"], ent["lat"], ent["noises"], ent["out"], ent["tr"])
             ent["graph"] = g
+            if dump:
+                g.debug_dump(dump)
         if ent is not None and ent["graph"] is not None:
             ent["cond"].copy_(cond)
             ent["lat"].copy_(latents)
