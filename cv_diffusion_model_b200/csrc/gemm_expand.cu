@@ -547,6 +547,8 @@ bool plan_layout(int nseg, const int* segK, int Nc, XLayout* L) {
 
 }  // namespace
 
+bool tmap_rows128(const void* ptr, long long M, int K, int ld, int dtype, CUtensorMap* out) { return matrix_map(ptr, M, K, ld, dtype, out); }
+
 int gemm_expand_read_timeline(long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_xtimeline, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : -1;
 }

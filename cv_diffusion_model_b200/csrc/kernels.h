@@ -139,6 +139,11 @@ int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_
 bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P);
 size_t gemm_expand_scratch_bytes(int images);   // Gram / column-sum scratch; must be zero at launch (zero_scratch: cleared on the stream)
 int launch_gemm_expand(const GemmParams& p, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st);
+// gemm_wide.cu: the same operation for 128 <= K <= 448 (activation tile stationary, weights streamed; statistics from the
+// epilogue, accumulated into p.stats).  Weights packed like gemm_expand's (block_n = 128, x6).
+bool gemm_wide_supported(int nseg, const int* segK, int Nc, int P);
+int launch_gemm_wide(const GemmParams& p, int num_sms, cudaStream_t st);
+int gemm_wide_read_profile(long long* host8);   // LCM_W_DEBUG & 16
 int gemm_expand_read_timeline(long long* host, int n);   // debug: LCM_X_TIMELINE=1
 int gemm_tc_pick_block_n(int Nc);
 int gemm_tc_read_timeline(long long* host, int n);   // debug: per-tile clock stamps of block 0 (LCM_TC_DEBUG & 64)

@@ -32,7 +32,10 @@ int finish(cudaStream_t st) {
 
 extern "C" {
 
-int lcm_debug_timeline(long long* host, int n) { return n < 0 ? gemm_expand_read_timeline(host, -n) : gemm_tc_read_timeline(host, n); }
+int lcm_debug_timeline(long long* host, int n) {
+  if (n == 8) return gemm_wide_read_profile(host);   // MMA-warp cycle breakdown of gemm_wide.cu
+  return n < 0 ? gemm_expand_read_timeline(host, -n) : gemm_tc_read_timeline(host, n);
+}
 
 int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* out_dev, double* stats_dev, int64_t M,
                 int P, int Nc, int precision, int impl, int repeat, float* ms_out, void* stream) {
@@ -53,7 +56,13 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
     for (int i = 0; i < nseg; ++i) { segK[i] = segs[i].K; expand = expand && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6 && !segs[i].f16; }
     expand = expand && gemm_expand_supported(nseg, segK, Nc, P) && M % 128 == 0;
   }
-  const int block_n = tc ? (expand ? 128 : gemm_tc_pick_block_n(Nc)) : 0;
+  bool wide = tc && out16 && stats_dev && nseg <= 2 && !expand;
+  if (wide) {
+    int segK[2] = {0, 0};
+    for (int i = 0; i < nseg; ++i) { segK[i] = segs[i].K; wide = wide && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6 && !segs[i].f16; }
+    wide = wide && gemm_wide_supported(nseg, segK, Nc, P) && M % 128 == 0;
+  }
+  const int block_n = tc ? ((expand || wide) ? 128 : gemm_tc_pick_block_n(Nc)) : 0;
   const size_t wbytes = tc ? (size_t)Nc * Kpad * 2 : (size_t)Nc * Ktot * (bf ? 2 : 4);
   void* wbuf = nullptr;
   if (cudaMalloc(&wbuf, wbytes) != cudaSuccess) return LCM_ERR_CUDA;
@@ -78,8 +87,9 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   if (expand && cudaMalloc(&xscratch, gemm_expand_scratch_bytes((int)(M / P))) != cudaSuccess) { cudaFree(wbuf); return LCM_ERR_CUDA; }
   Timer t(st, ms_out, repeat);
   for (int r = 0; r < repeat && rc == 0; ++r) {
-    if (expand && repeat > 1 && stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)(M / P) * Nc * 2 * sizeof(double), st);   // the finalisation kernel owns its entries
+    if ((expand || wide) && repeat > 1 && stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)(M / P) * Nc * 2 * sizeof(double), st);   // the finalisation kernel owns its entries
     if (expand) rc = launch_gemm_expand(gp, xscratch, true, sms, st);
+    else if (wide) rc = launch_gemm_wide(gp, sms, st);
     else if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
     else launch_gemm_simt(gp, bf, st);
   }

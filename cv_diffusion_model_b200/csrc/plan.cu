@@ -198,6 +198,7 @@ struct GemmW {
   size_t off = 0;
   int Nc = 0, Ktot = 0, Kpad = 0, block_n = 0;
   bool expand = false;   // served by gemm_expand.cu: block_n = 128
+  bool wide = false;     // served by gemm_wide.cu: block_n = 128
   bool relu6 = false;    // tcgen05 path, relu6 prologue as 6 sat(.): weights scaled by 6
   std::vector<int> seg_off, seg_pad_off;
 };
@@ -226,6 +227,7 @@ struct Builder {
     GemmW g;
     g.Nc = Nc;
     g.expand = p->tc && expand_P > 0 && gemm_expand_supported((int)segK.size(), segK.data(), Nc, expand_P);
+    g.wide = p->tc && expand_P > 0 && !g.expand && gemm_wide_supported((int)segK.size(), segK.data(), Nc, expand_P);
     g.relu6 = p->tc && expand_P > 0;
     for (int k : segK) {
       g.seg_off.push_back(g.Ktot);
@@ -233,7 +235,7 @@ struct Builder {
       g.Ktot += k;
       g.Kpad += (k + 63) / 64 * 64;
     }
-    if (p->tc) { g.block_n = g.expand ? 128 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
+    if (p->tc) { g.block_n = (g.expand || g.wide) ? 128 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
     else g.off = p->walloc((size_t)Nc * g.Ktot * p->esz);
     return g;
   }
@@ -277,7 +279,7 @@ struct Builder {
     std::vector<SegSpec> sg = segs;
     // Gram / column-sum scratch of the expand kernel: a slice of the region zeroed at the start of the forward
     const size_t xs = (pl->tc && w.expand) ? p->zalloc(gemm_expand_scratch_bytes(N)) : 0;
-    push(name, pl->tc ? (w.expand ? "gemm_expand" : "gemm_tc") : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
+    push(name, pl->tc ? (w.expand ? "gemm_expand" : (w.wide ? "gemm_wide" : "gemm_tc")) : "gemm_simt", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
       GemmParams gp{};
       gp.nseg = (int)sg.size();
       for (int i = 0; i < gp.nseg; ++i) {
@@ -299,6 +301,7 @@ struct Builder {
       gp.Nc = w.Nc;
       gp.out_f16 = out->f16 ? 1 : 0;
       if (pl->tc && w.expand) { if (launch_gemm_expand(gp, c.z + xs, false, pl->num_sms, st)) *c.launch_err = 1; }
+      else if (pl->tc && w.wide) { if (launch_gemm_wide(gp, pl->num_sms, st)) *c.launch_err = 1; }
       else if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
     });

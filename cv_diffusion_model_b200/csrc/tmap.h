@@ -13,4 +13,7 @@ enum TmapDtype : int { TMAP_BF16 = 0, TMAP_F16 = 1 };
 bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const cuuint64_t* gdim,
                  const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128);
 
+// cached map of a [M][K] 16-bit matrix with row stride ld: box = 64 elements x 128 rows, 128-byte swizzle (gemm_expand.cu)
+bool tmap_rows128(const void* ptr, long long M, int K, int ld, int dtype, CUtensorMap* out);
+
 }  // namespace lcm

@@ -228,7 +228,19 @@ EXPAND_CASES = [  # (images, P, [K...], Nc): bf16 segments, relu6 prologue, fp16
 ]
 
 
-@pytest.mark.parametrize("images,P,Ks,Nc", EXPAND_CASES)
+WIDE_CASES = [  # the same operation on gemm_wide.cu (K a multiple of 64, 128..448; activation tile stationary)
+    (2, 256, [128], 512),
+    (3, 128, [256], 1024),
+    (5, 128 * 9, [128, 64], 768),     # concat expand of decoder level 2
+    (2, 1024, [256, 128], 1536),      # concat expand of decoder level 1
+    (70, 128, [192], 256),            # more images than a CTA has tiles, three chunks
+    (3, 4096, [256], 1024),
+    (2, 640, [448], 128),
+    (200, 128 * 3, [128], 2048),      # more tiles than CTAs: several tiles and images per CTA, 16 n-blocks
+]
+
+
+@pytest.mark.parametrize("images,P,Ks,Nc", EXPAND_CASES + WIDE_CASES)
 def test_gemm_expand_kernel(images, P, Ks, Nc):
     """Expand GEMM specialisation: TMA store + tensor-core column statistics, x read once for all n-blocks."""
     from cv_diffusion_model_b200 import ops
