@@ -280,7 +280,9 @@ __global__ void __launch_bounds__(128) final_conv_h2_kernel(const bf16* __restri
   for (int p = 0; p < 4; ++p) {
     const int gx = x0 + tx + 16 * p;
     if (gx >= W) continue;
-    for (int co = 0; co < Co; ++co) {
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {   // constant trip count: a runtime bound would index acc[] dynamically and put it in local memory
+      if (co >= Co) break;
       const size_t o = (((size_t)n * Co + co) * H + gy) * W + gx;
       const float e = acc[p][co] + bias[co];
       if (eps) eps[o] = e;

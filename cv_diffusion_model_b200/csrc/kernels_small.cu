@@ -178,29 +178,41 @@ __device__ __forceinline__ void se_fc_rows(const float* __restrict__ W, const fl
     int lpr = 32;
     while (lpr > 1 && (lpr >> 1) >= units) lpr >>= 1;
     const int rpp = 32 / lpr, sub = lane / lpr, sl = lane - sub * lpr;
-    for (int rb = r0 + warp * rpp; rb < r1; rb += nw * rpp) {
-      const int r = rb + sub;
-      float acc[SE_IMG];
+    // RB row groups per pass: the weight loads of RB rows are in flight together (a warp walking one row at a time
+    // has one or two loads outstanding and the layer becomes a chain of L2 latencies)
+    constexpr int RB = 4;
+    for (int rb = r0 + warp * rpp * RB; rb < r1; rb += nw * rpp * RB) {
+      float acc[RB][SE_IMG];
 #pragma unroll
-      for (int i = 0; i < SE_IMG; ++i) acc[i] = 0.f;
-      if (r < r1) {
-        const float4* wr = reinterpret_cast<const float4*>(W + (size_t)r * K);
-#pragma unroll 4
-        for (int u = sl; u < units; u += lpr) {
-          const float4 w = __ldg(wr + u);
+      for (int q = 0; q < RB; ++q)
 #pragma unroll
-          for (int i = 0; i < SE_IMG; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(xs + i * K + u * 4);
-            acc[i] = fmaf(w.x, x.x, acc[i]); acc[i] = fmaf(w.y, x.y, acc[i]);
-            acc[i] = fmaf(w.z, x.z, acc[i]); acc[i] = fmaf(w.w, x.w, acc[i]);
+        for (int i = 0; i < SE_IMG; ++i) acc[q][i] = 0.f;
+      for (int u = sl; u < units; u += lpr) {
+        float4 w[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          const int r = rb + q * rpp + sub;
+          w[q] = r < r1 ? __ldg(reinterpret_cast<const float4*>(W + (size_t)r * K) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < SE_IMG; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + i * K + u * 4);
+#pragma unroll
+          for (int q = 0; q < RB; ++q) {
+            acc[q][i] = fmaf(w[q].x, x.x, acc[q][i]); acc[q][i] = fmaf(w[q].y, x.y, acc[q][i]);
+            acc[q][i] = fmaf(w[q].z, x.z, acc[q][i]); acc[q][i] = fmaf(w[q].w, x.w, acc[q][i]);
           }
         }
       }
-      for (int o = lpr >> 1; o > 0; o >>= 1) {
 #pragma unroll
-        for (int i = 0; i < SE_IMG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      for (int q = 0; q < RB; ++q) {
+        for (int o = lpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int i = 0; i < SE_IMG; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], o);
+        }
+        const int r = rb + q * rpp + sub;
+        if (r < r1 && sl == 0) emit(r, acc[q]);
       }
-      if (r < r1 && sl == 0) emit(r, acc);
     }
   } else {
     for (int r = r0 + warp; r < r1; r += nw) {
