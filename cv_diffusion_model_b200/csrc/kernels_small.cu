@@ -3,6 +3,8 @@
 // that the heavy kernels' prologues are a single per-(image, channel) affine.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace lcm {
@@ -124,18 +126,29 @@ __global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const doub
   const int n = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  const double inv_count = 1.0 / count;   // one fp64 division per thread
+  // one warp per group (fixed summation order: lanes stride over the group's channels, then a shuffle tree)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int g = warp; g < groups; g += (int)(blockDim.x >> 5)) {
     double sum = 0.0, sq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double* p = (c < C0) ? s0 + ((size_t)n * C0 + c) * 2 : s1 + ((size_t)n * C1 + (c - C0)) * 2;
-      sum += p[0];
-      sq += p[1];
+#pragma unroll 1
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      const double2 v = *reinterpret_cast<const double2*>((c < C0) ? s0 + ((size_t)n * C0 + c) * 2 : s1 + ((size_t)n * C1 + (c - C0)) * 2);
+      sum += v.x;
+      sq += v.y;
     }
-    double mean = sum / count;
-    double var = sq / count - mean * mean;
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    // sums in fp64 (cancellation in E[x^2] - mean^2), the rest in fp32: fp64 division and sqrt are long software
+    // routines, and this kernel runs cold 47 times per forward — its cost is its code footprint
+    const double mean = sum * inv_count;
+    double var = sq * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    s_mean[g] = (float)mean;
-    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+    if (lane == 0) {
+      s_mean[g] = (float)mean;
+      s_rstd[g] = rsqrtf((float)var + 1e-5f);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -163,30 +176,34 @@ void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, 
 //   hid[n][j]  = relu6(b1[j] + sum_c w1[j][c] * mean[n][c])          (mean = pooled sum * inv_count)
 //   gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * hid[n][j])         -> prologue coefficient (gate, 0)
 // The gate sits on the serial chain depthwise -> gate -> project of every block, so what it costs is latency, not
-// bandwidth (two dependent launches used to cost ~32 us per block inside the graph, 0.7 ms per forward).
-// A thread-block CLUSTER of 8 CTAs owns 8 images: each CTA stages the 8 pooled vectors, computes 1/8 of the hidden
-// rows, the slices are exchanged through distributed shared memory, then each CTA computes 1/8 of the gate rows.
+// bandwidth.  Measured inside the graph (skip / no-op experiments, profiles/r01_micro_kernels.txt): two dependent
+// launches cost ~32 us per block; one launch with a fully unrolled 74 KB body still ~20 us although it executes only
+// ~6000 warp instructions per CTA — between two uses GBs of activations pass through L2 and the instruction caches,
+// so a cold kernel pays for its code FOOTPRINT.  Hence: one launch, and a deliberately compact body (one shared,
+// non-inlined row routine, modest unrolling).
+// A thread-block CLUSTER of 8 CTAs owns 4 images: each CTA stages the pooled vectors, computes 1/8 of the hidden rows,
+// the slices are exchanged through distributed shared memory, then each CTA computes 1/8 of the gate rows.
 // A weight row is split over just enough lanes (float4 per lane), several rows per warp when rows are short.
-constexpr int SE_IMG = 8, SE_CL = 8, SE_THREADS = 512;
+constexpr int SE_IMG = 4, SE_CL = 8, SE_THREADS = 512;
 
-template <class Emit>
-__device__ __forceinline__ void se_fc_rows(const float* __restrict__ W, const float* __restrict__ xs, int K, int r0, int r1,
-                                           Emit emit) {
+// out_mode 0: relu6 -> dst_s[i * dst_ld + (r - r0)] (shared);  1: sigmoid -> dst_g[(n0 + i) * dst_ld + r] = (gate, 0)
+__device__ __noinline__ void se_fc_rows(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ xs,
+                                        int K, int r0, int r1, int out_mode, float* dst_s, float2* dst_g, int dst_ld, int nimg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = SE_THREADS / 32;
-  if ((K & 3) == 0) {
-    const int units = K >> 2;
-    int lpr = 32;
-    while (lpr > 1 && (lpr >> 1) >= units) lpr >>= 1;
-    const int rpp = 32 / lpr, sub = lane / lpr, sl = lane - sub * lpr;
-    // RB row groups per pass: the weight loads of RB rows are in flight together (a warp walking one row at a time
-    // has one or two loads outstanding and the layer becomes a chain of L2 latencies)
-    constexpr int RB = 4;
-    for (int rb = r0 + warp * rpp * RB; rb < r1; rb += nw * rpp * RB) {
-      float acc[RB][SE_IMG];
+  const bool vec = (K & 3) == 0;
+  const int units = vec ? K >> 2 : K;          // float4 units (or scalars when K is not a multiple of 4)
+  int lpr = 32;
+  while (lpr > 1 && (lpr >> 1) >= units) lpr >>= 1;
+  const int rpp = 32 / lpr, sub = lane / lpr, sl = lane - sub * lpr;
+  constexpr int RB = 2;   // row groups per pass: their weight loads are in flight together
+  for (int rb = r0 + warp * rpp * RB; rb < r1; rb += nw * rpp * RB) {
+    float acc[RB][SE_IMG];
 #pragma unroll
-      for (int q = 0; q < RB; ++q)
+    for (int q = 0; q < RB; ++q)
 #pragma unroll
-        for (int i = 0; i < SE_IMG; ++i) acc[q][i] = 0.f;
+      for (int i = 0; i < SE_IMG; ++i) acc[q][i] = 0.f;
+    if (vec) {
+#pragma unroll 2
       for (int u = sl; u < units; u += lpr) {
         float4 w[RB];
 #pragma unroll
@@ -204,31 +221,34 @@ __device__ __forceinline__ void se_fc_rows(const float* __restrict__ W, const fl
           }
         }
       }
+    } else {
+#pragma unroll 1
+      for (int u = sl; u < units; u += lpr) {
 #pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        for (int o = lpr >> 1; o > 0; o >>= 1) {
+        for (int q = 0; q < RB; ++q) {
+          const int r = rb + q * rpp + sub;
+          const float w = r < r1 ? __ldg(W + (size_t)r * K + u) : 0.f;
 #pragma unroll
-          for (int i = 0; i < SE_IMG; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], o);
+          for (int i = 0; i < SE_IMG; ++i) acc[q][i] = fmaf(w, xs[i * K + u], acc[q][i]);
         }
-        const int r = rb + q * rpp + sub;
-        if (r < r1 && sl == 0) emit(r, acc[q]);
       }
     }
-  } else {
-    for (int r = r0 + warp; r < r1; r += nw) {
-      float acc[SE_IMG];
 #pragma unroll
-      for (int i = 0; i < SE_IMG; ++i) acc[i] = 0.f;
-      for (int k = lane; k < K; k += 32) {
-        const float w = __ldg(W + (size_t)r * K + k);
+    for (int q = 0; q < RB; ++q) {
+      for (int o = lpr >> 1; o > 0; o >>= 1) {
 #pragma unroll
-        for (int i = 0; i < SE_IMG; ++i) acc[i] = fmaf(w, xs[i * K + k], acc[i]);
+        for (int i = 0; i < SE_IMG; ++i) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], o);
       }
-      for (int o = 16; o > 0; o >>= 1) {
+      const int r = rb + q * rpp + sub;
+      if (r < r1 && sl == 0) {
+        const float b = bias[r];
 #pragma unroll
-        for (int i = 0; i < SE_IMG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        for (int i = 0; i < SE_IMG; ++i) {
+          const float v = acc[q][i] + b;
+          if (out_mode == 0) dst_s[i * dst_ld + (r - r0)] = fminf(fmaxf(v, 0.f), 6.f);
+          else if (i < nimg) dst_g[(size_t)i * dst_ld + r] = make_float2(1.f / (1.f + expf(-v)), 0.f);
+        }
       }
-      if (lane == 0) emit(r, acc);
     }
   }
 }
@@ -247,8 +267,9 @@ __device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
 
 __global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(SE_THREADS)
 se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __restrict__ w1, const float* __restrict__ b1,
-               const float* __restrict__ w2, const float* __restrict__ b2, float2* __restrict__ coef, int N, int C, int SQ) {
+               const float* __restrict__ w2, const float* __restrict__ b2, float2* __restrict__ coef, int N, int C, int SQ, int dbg) {
   extern __shared__ __align__(16) float se_sm[];
+  if (dbg == 1) { pdl_wait(); pdl_trigger(); return; }   // LCM_SE_DEBUG: launch-only timing experiment
   const int sqr = (SQ + SE_CL - 1) / SE_CL;         // hidden rows per CTA
   float* xs = se_sm;                                // [SE_IMG][C] pooled means
   float* hid = xs + SE_IMG * C;                     // [SE_IMG][SQ] all hidden rows (after the exchange)
@@ -258,44 +279,39 @@ se_gate_kernel(const double* __restrict__ pool, float inv_count, const float* __
   const int h0 = (int)rank * sqr, h1 = min(SQ, h0 + sqr);
   const int cr = (C + SE_CL - 1) / SE_CL;
   const int c0 = (int)rank * cr, c1 = min(C, c0 + cr);
-  // the FC weights do not depend on the previous kernel: pull this CTA's rows towards L2 while the depthwise conv
-  // that feeds the pool is still draining (activations of GBs pass through L2 between two uses of these weights)
+  // the FC weights do not depend on the previous kernel: pull this CTA's rows towards L2 before the dependency wait
   {
     const char* a = reinterpret_cast<const char*>(w1 + (size_t)h0 * C);
     const long long na = (long long)max(h1 - h0, 0) * C * 4;
+#pragma unroll 1
     for (long long o = (long long)threadIdx.x * 128; o < na; o += SE_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
     const char* b = reinterpret_cast<const char*>(w2 + (size_t)c0 * SQ);
     const long long nb = (long long)max(c1 - c0, 0) * SQ * 4;
+#pragma unroll 1
     for (long long o = (long long)threadIdx.x * 128; o < nb; o += SE_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
   }
   pdl_wait();
   pdl_trigger();
-#pragma unroll 4
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < SE_IMG * C; idx += SE_THREADS)
     xs[idx] = idx < nimg * C ? (float)pool[(size_t)n0 * C + idx] * inv_count : 0.f;
   __syncthreads();
-  se_fc_rows(w1, xs, C, h0, h1, [&](int r, const float* acc) {
-    const float b = b1[r];
-#pragma unroll
-    for (int i = 0; i < SE_IMG; ++i) mine[i * sqr + (r - h0)] = fminf(fmaxf(acc[i] + b, 0.f), 6.f);
-  });
+  se_fc_rows(w1, b1, xs, C, h0, h1, 0, mine, nullptr, sqr, nimg);
   cluster_sync_all();
+#pragma unroll 1
   for (int idx = threadIdx.x; idx < SE_IMG * SQ; idx += SE_THREADS) {
     const int i = idx / SQ, j = idx - i * SQ;
     const int src = j / sqr;
     hid[idx] = ld_dsmem(mine + i * sqr + (j - src * sqr), (uint32_t)src);
   }
   cluster_sync_all();   // every peer has finished reading this CTA's slice (and hid is complete CTA-wide)
-  se_fc_rows(w2, hid, SQ, c0, c1, [&](int r, const float* acc) {
-    const float b = b2[r];
-#pragma unroll
-    for (int i = 0; i < SE_IMG; ++i)
-      if (i < nimg) coef[(size_t)(n0 + i) * C + r] = make_float2(1.f / (1.f + expf(-(acc[i] + b))), 0.f);
-  });
+  se_fc_rows(w2, b2, hid, SQ, c0, c1, 1, nullptr, coef + (size_t)n0 * C, C, nimg);
 }
 
 int launch_se_gate(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2,
                    const float* b2, float2* coef, int N, int C, int SQ, cudaStream_t st) {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("LCM_SE_DEBUG"); dbg = e ? atoi(e) : 0; }
   const int sqr = (SQ + SE_CL - 1) / SE_CL;
   const size_t sm = ((size_t)SE_IMG * C + (size_t)SE_IMG * SQ + (size_t)SE_IMG * sqr) * sizeof(float);
   if (sm > 200 * 1024) return 1;
@@ -304,8 +320,8 @@ int launch_se_gate(const double* pool, float inv_count, const float* w1, const f
     if (cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 1;
     attr = sm;
   }
-  const int clusters = (N + SE_IMG - 1) / SE_IMG;
-  launch_pdl(se_gate_kernel, dim3(clusters * SE_CL), dim3(SE_THREADS), sm, st, pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ);
+  const int groups = (N + SE_IMG - 1) / SE_IMG;
+  launch_pdl(se_gate_kernel, dim3(groups * SE_CL), dim3(SE_THREADS), sm, st, pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ, dbg);
   return 0;
 }
 
