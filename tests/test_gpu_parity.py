@@ -235,3 +235,21 @@ def test_production_size_reproducible_and_parity():
     eps = pipe.unet(torch.cat([lat0, low], dim=1).cuda(), t0.cuda()).cpu()     # first step's noise prediction
     assert rel_rms(eps, trace[0][0]) <= 0.03
     assert psnr(res.intermediate[-1].cpu(), trace[-1][1], 2.0) >= 30.0
+
+
+@pytest.mark.parametrize("variant,size", [("base", 256), ("large", 128)])
+def test_wider_variants_forward_parity(variant, size):
+    """Base (48-channel stem: K = 192 / 384 expands on the activation-stationary kernel, K = 96 on the resident-weight
+    one) and Large (64-channel stem: K = 512 expands and everything above on the general kernel) at sizes where every
+    level has whole 128-pixel tiles; one forward against the oracle, bf16 tolerances of this file, run twice bitwise."""
+    m = seeded_unet(variant, 512, patched=(variant == "base"), affine=True, seed=11)   # 48 channels need gcd groups
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(1, 6, size, size, generator=g)
+    t = torch.tensor([617])
+    with torch.no_grad():
+        want = unet_oracle.unet_forward(m.state_dict(), m.config, x, t, strict_groupnorm=(variant != "base"))
+    y = _run_unet(m, x, t, "bf16", False)
+    y2 = _run_unet(m, x, t, "bf16", False)
+    assert torch.equal(y, y2)
+    assert rel_rms(y, want) <= 0.03
+    assert (y - want).abs().max().item() <= 0.15 * want.abs().max().item()
