@@ -37,3 +37,22 @@ gemm_case("project0 8 images", 8, 65536, [128, 32], 32, [4, 0], [1, 0], 0)
 gemm_case("project_e1 f16", 64, 16384, [256, 64], 64, [4, 0], [1, 0], 0)
 gemm_case("project_d3 f16", 32, 65536, [384, 64, 32], 32, [4, 0, 0], [1, 0, 0], 0)
 gemm_case("project0 ungated", 64, 65536, [128, 32], 32, [0, 0], [1, 0], 0)
+# activation-stationary expand kernel (gemm_wide.cu) and resident-weight expand kernel at production shapes
+gemm_case("expand_d1 wide", 64, 4096, [256, 128], 1536, [2, 2], [0, 0], 1)
+gemm_case("expand_d2 wide", 64, 16384, [128, 64], 768, [2, 2], [0, 0], 1)
+gemm_case("expand_m wide", 64, 1024, [256], 1024, [2], [0], 1)
+gemm_case("expand_l2 wide", 64, 4096, [128], 512, [2], [0], 1)
+gemm_case("expand0 resident", 64, 65536, [32], 128, [2], [0], 1)
+
+
+def conv_case(name, N, H, W, Ci, Co, mode):
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (9 * Ci) ** 0.5).bfloat16().float()
+    b = torch.randn(Co, device="cuda", generator=g) * 0.1
+    r = [ops.conv3x3(x, w, b, mode, impl=1) for _ in range(3)]
+    print(f"{name}: out", all(same(r[0][0], q[0]) for q in r), "stats", all(same(r[0][1], q[1]) for q in r))
+
+
+conv_case("up-conv halo 256x256 64ch", 16, 256, 256, 64, 32, 0)
+conv_case("up-conv halo 128x128 128ch", 16, 128, 128, 128, 64, 0)
+conv_case("down-conv 256x256 32ch", 16, 256, 256, 32, 32, 1)
