@@ -66,6 +66,8 @@ struct alignas(64) Tc2Params {
   int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
   int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
+  int bpair;             // streamed weights shared by a 2-CTA cluster: each CTA fetches half of every weight chunk and
+                         // multicasts it to both (halves the L2 -> shared-memory weight traffic, the bound of the 32x32 / 64x64 levels)
   int conv_halo, achunks; // halo mode: ONE [64 ch][130 px][3 rows] load per tile and 64-channel chunk serves all 9 taps
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(raw_bar(s), 1);
       mbar_init(xf_bar(s), conv ? 128 : kXfThreads);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.bpair ? 2 : 1);   // pair mode: this CTA's and the peer's MMAs release a stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -157,13 +159,25 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // pair mode: the peer multicasts into this CTA's stages and arrives on its barriers, so they must be initialised
+  if (p.bpair) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   pdl_wait();      // everything above is CTA-local; from here on the previous kernel's output is read
   pdl_trigger();
 
   const int m_tiles = (int)p.m_tiles;
   const long long total_tiles = p.m_tiles * p.n_tiles;
-  const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-  const int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
+  long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+  int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
+  const int tstep = p.bpair ? 2 : 1;
+  const uint32_t pair_rank = blockIdx.x & 1u;   // = %cluster_ctarank for a (2,1,1) cluster
+  if (p.bpair) {
+    // the two CTAs of a cluster take tiles 2u and 2u + 1 of the same pair-unit u: same n tile (m_tiles is even), same
+    // chunk sequence, equal tile counts — they advance in lockstep through the shared weight stream
+    const long long units = total_tiles >> 1, npairs = gridDim.x >> 1, pr = blockIdx.x >> 1;
+    const long long u0 = units * pr / npairs, u1 = units * (pr + 1) / npairs;
+    t_begin = 2 * u0 + pair_rank;
+    my_tiles = (int)(u1 - u0);
+  }
   const uint32_t b_chunk_bytes = (uint32_t)p.block_n * 128u;
   const int M = (int)p.M;
 
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     const int group = ptid >> 7, gt = ptid & 127;
     int cur_img = -1, gate_img = -1, gate_nt = -1;
     uint32_t gate_phase = 0;
-    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    TileIter ti; ti.init(t_begin, m_tiles, p.P, tstep);
     Ring ring{0, 0u, p.stages};
     int par = 0;
     for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     // registers; one elected lane issues the copies.
     {
       int cur_nt = -1, cur_img = -1;
-      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      TileIter ti; ti.init(t_begin, m_tiles, p.P, tstep);
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
       int last_stage = -1; uint32_t last_phase = 0;   // ring slot / phase of the last activation chunk issued
@@ -420,8 +434,20 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 tma_load_2d(a_smem, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
               }
             }
-            if (!p.resident)
-              bulk_g2s(a_smem + kStageA2, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, raw_bar(stage));
+            if (!p.resident) {
+              if (p.bpair) {
+                // this CTA's half of the chunk, to the same stage offset (and barrier) of both CTAs of the pair
+                const uint32_t half = b_chunk_bytes >> 1;
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                        a_smem + kStageA2 + pair_rank * half),
+                    "l"(reinterpret_cast<const uint8_t*>(wt + (size_t)ci * p.block_n * 64) + pair_rank * half), "r"(half), "r"(raw_bar(stage)),
+                    "h"((uint16_t)3)
+                    : "memory");
+              } else {
+                bulk_g2s(a_smem + kStageA2, wt + (size_t)ci * p.block_n * 64, b_chunk_bytes, raw_bar(stage));
+              }
+            }
           }
           __syncwarp();
           last_stage = stage; last_phase = ring.phase;
@@ -436,7 +462,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       const uint32_t idesc_b = idesc_h | (1u << 7) | (1u << 10);
       int cur_nt = -1, cur_img = -1;
       uint32_t bres_phase = 0;
-      TileIter ti; ti.init(t_begin, m_tiles, p.P);
+      TileIter ti; ti.init(t_begin, m_tiles, p.P, tstep);
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -498,7 +524,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
             if (gated)
               for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
-            umma_commit(empty_bar(stage));
+            if (p.bpair)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                               empty_bar(stage)), "h"((uint16_t)3)
+                           : "memory");
+            else
+              umma_commit(empty_bar(stage));
             if (ci == p.nchunks - 1) umma_commit(tfull_bar(acc));
           }
           __syncwarp();
@@ -511,7 +542,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   } else if (warp < 4) {
     // ================================ E1: TMEM -> bf16 staging ==========================================
     int cur_nt = -1;
-    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    TileIter ti; ti.init(t_begin, m_tiles, p.P, tstep);
     int acc = 0; uint32_t aphase = 0;
     int sb = 0; uint32_t sphase = 0;
     for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
@@ -598,7 +629,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
     };
-    TileIter ti; ti.init(t_begin, m_tiles, p.P);
+    TileIter ti; ti.init(t_begin, m_tiles, p.P, tstep);
     int sb = 0; uint32_t sphase = 0;
     for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
       const int n_tile = ti.n_tile, m0 = ti.m0, n0 = n_tile * p.block_n;
@@ -646,6 +677,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  // pair mode: the peer may still be multicasting into this CTA's shared memory / arriving on its barriers
+  if (p.bpair) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- host side: tensor maps ----------------------------------------------------------------------------
@@ -848,7 +881,15 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   const uint32_t smem_bytes = off + 1024;
   if (smem_bytes > kSmemLimit2) return -1;
   const long long tiles = p.m_tiles * p.n_tiles;
-  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  // weights streamed (not resident) by a plain GEMM: CTA pairs can share the weight stream (LCM_PAIR=1).  OFF by default:
+  // measured on the model it is a wash (32x32-level projects 0.102 -> 0.094 ms, but only 72 pairs = 144 CTAs fit and
+  // the K = 768 expand / 64x64 concat project get slower; 912 vs 920 images/s same-box) — those GEMMs are bound by the
+  // depth of the TMA -> prologue -> MMA pipeline (2-3 stages of 48 KB), not by L2 bandwidth.  Kept as the tested
+  // building block (multicast halves, cluster-wide empty barriers) for a cta_group::2 version.
+  static int no_pair = -1;
+  if (no_pair < 0) { const char* e = getenv("LCM_PAIR"); no_pair = (e && atoi(e)) ? 0 : 1; }
+  p.bpair = (!no_pair && p.conv_mode < 0 && !p.conv_tma && !p.resident && p.m_tiles % 2 == 0 && tiles >= 2 && !(p.debug & 1)) ? 1 : 0;
   typedef void (*KernelFn)(const Tc2Params);
   KernelFn fn;
   if (p.debug) fn = p.conv_mode >= 0 ? (p.fast ? gemm_tc2_kernel<true, true, true> : gemm_tc2_kernel<true, false, true>)
@@ -861,6 +902,29 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
     if (!attr_done[(void*)fn]) {
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit2) != cudaSuccess) return -2;
       attr_done[(void*)fn] = true;
+    }
+  }
+  if (p.bpair) {
+    static std::unordered_map<void*, int> max_pairs;   // per instantiation (shared memory is the same opt-in size class)
+    int mp;
+    {
+      std::lock_guard<std::mutex> lk(g_map_mu);
+      auto it = max_pairs.find((void*)fn);
+      if (it == max_pairs.end()) {
+        int n = 0;
+        if (launch_pdl_cluster(fn, dim3(num_sms & ~1), dim3(kThreads2), kSmemLimit2, st, 2, &n, p) != cudaSuccess || n < 1) n = 0;
+        it = max_pairs.emplace((void*)fn, n).first;
+      }
+      mp = it->second;
+    }
+    if (mp < 1) { p.bpair = 0; }
+    else {
+      long long pairs = tiles / 2;
+      if (pairs > mp) pairs = mp;
+      if (pairs > num_sms / 2) pairs = num_sms / 2;
+      grid = (int)(2 * pairs);
+      launch_pdl_cluster(fn, dim3(grid), dim3(kThreads2), smem_bytes, st, 2, nullptr, p);
+      return 0;
     }
   }
   launch_pdl(fn, dim3(grid), dim3(kThreads2), smem_bytes, st, p);

@@ -196,7 +196,9 @@ __device__ __forceinline__ int div_upr(int u, int upr) {
 // dependent cycles and every role is a single warp (or thread) on the critical path of the pipeline.
 struct TileIter {
   int n_tile, m_tile, m0, img, rem;   // m0 = m_tile*128 ; img = m0 / P ; rem = m0 % P
-  __device__ __forceinline__ void init(long long t, int m_tiles, int P) {
+  int step;                           // tiles per next(): 2 when a CTA pair walks the tile list in lockstep
+  __device__ __forceinline__ void init(long long t, int m_tiles, int P, int step_ = 1) {
+    step = step_;
     n_tile = (int)(t / m_tiles);
     m_tile = (int)(t - (long long)n_tile * m_tiles);
     m0 = m_tile * 128;
@@ -204,9 +206,13 @@ struct TileIter {
     rem = m0 - img * P;
   }
   __device__ __forceinline__ void next(int m_tiles, int P) {
-    if (++m_tile == m_tiles) { m_tile = 0; ++n_tile; m0 = 0; img = 0; rem = 0; return; }
-    m0 += 128;
-    rem += 128;
+    m_tile += step;
+    if (m_tile >= m_tiles) {   // step == 2 requires an even m_tiles: the pair stays inside one n row
+      m_tile -= m_tiles; ++n_tile; m0 = m_tile * 128; img = m0 / P; rem = m0 - img * P;
+      return;
+    }
+    m0 += 128 * step;
+    rem += 128 * step;
     while (rem >= P) { rem -= P; ++img; }
   }
 };

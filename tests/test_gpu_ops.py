@@ -176,6 +176,10 @@ GEMM_F16_CASES = [  # (images, P, [K...], [segment is fp16], Nc, modes, out_f16)
     (2, 64, [128, 32], [True, False], 64, [4, 0], False),    # tile spans images -> A-side gating of the fp16 operand
     (2, 128, [1024, 256], [True, False], 256, [4, 0], False),
     (2, 100, [192, 48], [True, False], 48, [4, 0], False),   # ragged M
+    # streamed weights, even tile count: with LCM_PAIR=1 CTA pairs share the weight stream (multicast halves), gemm_tc2.cu `bpair`
+    (64, 1024, [1024, 256], [True, False], 256, [4, 0], False),   # 32x32-level project at production size (512 tiles)
+    (5, 768, [768, 192], [True, False], 128, [4, 0], False),      # 30 tiles: pairs with unequal unit counts
+    (3, 256, [1024, 256], [True, False], 512, [4, 0], False),     # two n tiles
 ]
 
 
@@ -237,6 +241,7 @@ WIDE_CASES = [  # the same operation on gemm_wide.cu (K a multiple of 64, 128..4
     (3, 4096, [256], 1024),
     (2, 640, [448], 128),
     (200, 128 * 3, [128], 2048),      # more tiles than CTAs: several tiles and images per CTA, 16 n-blocks
+    (4, 1024, [512, 256], 3072),      # K = 768 (decoder level 0 concat): general kernel (CTA pairs sharing the weight stream with LCM_PAIR=1)
 ]
 
 
