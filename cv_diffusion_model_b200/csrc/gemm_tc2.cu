@@ -47,7 +47,7 @@ constexpr uint32_t kStageA2 = 16384;
 constexpr uint32_t kHaloBytes = 130u * 3u * 128u, kHaloStage = 51200;   // [3 rows][130 px][64 ch] bf16, stage rounded to 1 KB
 constexpr int kMaxChunks2 = 160;
 constexpr uint32_t kSmemLimit2 = 232448;
-constexpr uint32_t kMisc2 = 4096 + 16384;
+constexpr uint32_t kMisc2 = 4096 + 8192;    // barriers + per-column accumulators | statistics flush scratch [2048] fp32
 
 struct alignas(64) Tc2Params {
   CUtensorMap tmap[LCM_MAX_SEGS];
@@ -66,6 +66,8 @@ struct alignas(64) Tc2Params {
   int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
   int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
+  int coef_compact;      // fp16 SE-gated segments keep only their packed half2 gate pairs in shared memory (4 B per two
+                         // channels instead of 16): with streamed weights every KB decides the number of pipeline stages
   int bpair;             // streamed weights shared by a 2-CTA cluster: each CTA fetches half of every weight chunk and
                          // multicasts it to both (halves the L2 -> shared-memory weight traffic, the bound of the 32x32 / 64x64 levels)
   int conv_halo, achunks; // halo mode: ONE [64 ch][130 px][3 rows] load per tile and 64-channel chunk serves all 9 taps
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   float* s_sum = reinterpret_cast<float*>(misc + 512);
   float* s_sq = s_sum + 256;
   float* s_bias = s_sq + 256;
-  float* s_scr = reinterpret_cast<float*>(misc + 4096);   // { psum[2048], psq[2048] }: statistics flush scratch
+  float* s_scr = reinterpret_cast<float*>(misc + 4096);   // [2048]: statistics flush scratch (sums, then squares)
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_off);
 
   auto ld_s = [&](uint32_t saddr) { return *reinterpret_cast<const uint4*>(smem + (saddr - sbase)); };
@@ -203,8 +205,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
             for (int k = 2 * ptid; k < p.seg[s].K; k += 2 * kXfThreads) {
               const float2 c0v = src[k], c1v = src[k + 1];
               const __half2 gp = __floats2half2_rn(c0v.x, c1v.x);
-              s_coef[p.coef_base[s] + k] = make_float2(c0v.x, __uint_as_float(*reinterpret_cast<const uint32_t*>(&gp)));
-              s_coef[p.coef_base[s] + k + 1] = make_float2(c1v.x, 0.f);
+              if (p.coef_compact) {
+                reinterpret_cast<uint32_t*>(s_coef + p.coef_base[s])[k >> 1] = *reinterpret_cast<const uint32_t*>(&gp);
+              } else {
+                s_coef[p.coef_base[s] + k] = make_float2(c0v.x, __uint_as_float(*reinterpret_cast<const uint32_t*>(&gp)));
+                s_coef[p.coef_base[s] + k + 1] = make_float2(c1v.x, 0.f);
+              }
             }
           } else {
             const float sc = p.seg[s].mode == XF_AFFINE_RELU6 ? (1.f / 6.f) : 1.f;   // relu6 as 6 sat(.): see apply_xform
@@ -290,9 +296,15 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 4; ++i) v[i] = ld_s(a_smem + (uint32_t)(ptid + i * 256) * 16u);
               if (kFast && sg.f16 && mode == XF_SCALE) {
-                const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
-                const __half2 g0 = h2bits(__float_as_uint(c4[0].y)), g1 = h2bits(__float_as_uint(c4[1].y));
-                const __half2 g2 = h2bits(__float_as_uint(c4[2].y)), g3 = h2bits(__float_as_uint(c4[3].y));
+                __half2 g0, g1, g2, g3;
+                if (p.coef_compact) {
+                  const uint4 gp4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(s_coef + p.coef_base[sidx]) + ((c0 + cu * 8) >> 1));
+                  g0 = h2bits(gp4.x); g1 = h2bits(gp4.y); g2 = h2bits(gp4.z); g3 = h2bits(gp4.w);
+                } else {
+                  const float4* c4 = reinterpret_cast<const float4*>(s_coef + p.coef_base[sidx] + c0 + cu * 8);
+                  g0 = h2bits(__float_as_uint(c4[0].y)); g1 = h2bits(__float_as_uint(c4[1].y));
+                  g2 = h2bits(__float_as_uint(c4[2].y)); g3 = h2bits(__float_as_uint(c4[3].y));
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const __half2* hv = reinterpret_cast<const __half2*>(&v[i]);
@@ -607,20 +619,21 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     float cs[8], cq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-    float* psum = s_scr;
-    float* psq = s_scr + 2048;
-    auto flush = [&]() {   // uniform across the 256 E2 threads
-      if (active) {
-        float4* ps = reinterpret_cast<float4*>(psum + rg * p.block_n + cu * 8);
-        float4* pq = reinterpret_cast<float4*>(psq + rg * p.block_n + cu * 8);
-        ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
-        pq[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); pq[1] = make_float4(cq[4], cq[5], cq[6], cq[7]);
-      }
+    auto flush = [&]() {   // uniform across the 256 E2 threads; sums, then squares through the same 8 KB scratch
+      float a = 0.f, b = 0.f;
+      float4* ps = reinterpret_cast<float4*>(s_scr + rg * p.block_n + cu * 8);
+      if (active) { ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]); }
       bar_sync(2, kE2Threads);
       if (et < p.block_n) {
-        float a = 0.f, b = 0.f;
 #pragma unroll 4
-        for (int g = 0; g < RG; ++g) { a += psum[g * p.block_n + et]; b += psq[g * p.block_n + et]; }
+        for (int g = 0; g < RG; ++g) a += s_scr[g * p.block_n + et];
+      }
+      bar_sync(2, kE2Threads);
+      if (active) { ps[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); ps[1] = make_float4(cq[4], cq[5], cq[6], cq[7]); }
+      bar_sync(2, kE2Threads);
+      if (et < p.block_n) {
+#pragma unroll 4
+        for (int g = 0; g < RG; ++g) b += s_scr[g * p.block_n + et];
         double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + et) * 2;
         atomicAdd(d, (double)a);
         atomicAdd(d + 1, (double)b);
@@ -839,8 +852,8 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
   const uint32_t stg_bytes = (128u * stg_stride + 1023u) & ~1023u;
-  const uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
-  const uint32_t base_fixed = coef_bytes + kMisc2 + 1024;
+  uint32_t coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
+  uint32_t base_fixed = coef_bytes + kMisc2 + 1024;
   int ngate = 0;
   for (int ci = 0; ci < nch; ++ci) {
     p.lo_slot[ci] = 0xff;
@@ -853,6 +866,29 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   if (has_gate && p.resident && p.fast && !no_wgate) {
     const uint32_t bres2 = (uint32_t)(nch + ngate) * b_chunk;   // + low-order images of the gated chunks
     if (bres2 <= 131072 && base_fixed + stg_bytes + bres2 + 3 * kStageA2 <= kSmemLimit2) { p.wgate = 1; bres = bres2; }
+  }
+  if (!p.resident && p.fast && p.conv_mode < 0 && !p.conv_tma) {
+    // streamed weights: an fp16 SE-gated segment needs only its packed gate pairs (K * 2 bytes) in shared memory
+    int nc2 = 0, base2[LCM_MAX_SEGS];
+    bool any = false;
+    for (int s2 = 0; s2 < g.nseg; ++s2) {
+      base2[s2] = -1;
+      if (g.seg[s2].mode == XF_NONE) continue;
+      base2[s2] = nc2;
+      const bool gate16 = g.seg[s2].f16 && g.seg[s2].mode == XF_SCALE && g.seg[s2].K % 8 == 0;
+      any |= gate16;
+      nc2 += ((gate16 ? g.seg[s2].K / 4 : g.seg[s2].K) + 1) & ~1;   // float2 units, 16-byte aligned bases
+    }
+    bool all16 = true;   // the flag is per launch: every gated fp16 segment must qualify
+    for (int s2 = 0; s2 < g.nseg; ++s2)
+      if (g.seg[s2].f16 && g.seg[s2].mode == XF_SCALE && g.seg[s2].K % 8) all16 = false;
+    if (any && all16) {
+      for (int s2 = 0; s2 < g.nseg; ++s2) p.coef_base[s2] = base2[s2];
+      p.coef_compact = 1;
+      p.ncoef = ncoef = nc2;
+      coef_bytes = ((uint32_t)ncoef * 8u + 1023u) & ~1023u;
+      base_fixed = coef_bytes + kMisc2 + 1024;
+    }
   }
   p.all_raw = p.conv_tma ? 1 : 0;
   if (p.conv_mode < 0 && !p.conv_tma) {

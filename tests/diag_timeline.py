@@ -18,6 +18,8 @@ CASES = {
     "expand_l2": (64, 4096, [128], 512, [2], [0], 1),
     "expand_d2f": (64, 16384, [128, 64], 768, [2, 2], [0, 0], 1),
     "project_m": (64, 1024, [1024, 256], 256, [4, 0], [1, 0], 0),
+    "project_m128": (64, 1024, [1024, 256], 128, [4, 0], [1, 0], 0),
+    "project_m_raw": (64, 1024, [1024, 256], 256, [0, 0], [1, 0], 0),
 }
 images, P, Ks, Nc, modes, h16, o16 = CASES[sys.argv[1] if len(sys.argv) > 1 else "expand0"]
 g = torch.Generator(device="cuda").manual_seed(7)
