@@ -386,8 +386,10 @@ bool plan_layout_w(int nseg, const int* segK, int Nc, WideLayout* L) {
   const uint32_t fixed = kWPatchBytes + kWPartBytes + stat + coef + 1024 /* misc */ + 1024 /* align */;
   const int units = (int)((kWSmemLimit - fixed) / kWChunk);   // 16 KB units shared by the two rings
   if (units < nch + 3) return false;
-  // activation ring: the tile plus up to two tiles of look-ahead, as long as the weight ring keeps 4 stages
-  int extra = units - nch - 4;
+  // activation ring: the tile plus up to two tiles of look-ahead, as long as the weight ring keeps 5 stages (sweep 3..8: flat from 4 on, 3 is 15 % slower at K = 384)
+  static int min_b = -1;   // LCM_W_BSTAGES: weight-ring stages reserved before the activation ring gets look-ahead slots
+  if (min_b < 0) { const char* e = getenv("LCM_W_BSTAGES"); min_b = e ? atoi(e) : 5; if (min_b < 3) min_b = 3; }
+  int extra = units - nch - min_b;
   if (extra < 0) extra = 0;
   if (extra > 2 * nch) extra = 2 * nch;
   int aslots = nch + extra;
