@@ -900,7 +900,9 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   p.stage_bytes = p.conv_halo ? kHaloStage : kStageA2 + (p.resident ? 0u : b_chunk);
   if (p.conv_halo && !p.resident) return -1;
   const uint32_t used1 = base_fixed + stg_bytes + (p.resident ? bres : 0u);
-  p.nbuf = (used1 + stg_bytes + 4 * p.stage_bytes <= kSmemLimit2) ? 2 : 1;
+  static int nbuf_min_stages = -1;   // a second epilogue staging tile only if this many pipeline stages still fit
+  if (nbuf_min_stages < 0) { const char* e = getenv("LCM_TC_NBUF_STAGES"); nbuf_min_stages = e ? atoi(e) : 6; }   // sweep 4..8 on the model: 6 is best (-0.16 ms per forward against 4)
+  p.nbuf = (used1 + stg_bytes + (uint32_t)nbuf_min_stages * p.stage_bytes <= kSmemLimit2) ? 2 : 1;
   const uint32_t used = used1 + (p.nbuf == 2 ? stg_bytes : 0u);
   if (used >= kSmemLimit2) return -1;
   int stages = (int)((kSmemLimit2 - used) / p.stage_bytes);
