@@ -65,6 +65,7 @@ struct alignas(64) Tc2Params {
   int out_f16;           // store the output (and take its statistics) as fp16
   int wgate;             // SE gate folded into the smem-resident weights per image (XF_SCALE segments stay raw)
   int all_raw;           // no chunk needs the XF stage: the MMA warp consumes TMA tiles directly
+  int conv_stride;       // conv_tma: 1, or 2 for the stride-2 convs (tensor map with element strides 2 along W and H)
   int conv_tma, box_w;   // stride-1 3x3 conv fed by 4-D TMA tiles (zero fill = padding); box_w = pixels per tile row
   int coef_compact;      // fp16 SE-gated segments keep only their packed half2 gate pairs in shared memory (4 B per two
                          // channels instead of 16): with streamed weights every KB decides the number of pipeline stages
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         }
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
         int ty0 = 0, tx0 = 0;               // conv_tma: first pixel of this tile inside its image
-        if (p.conv_tma) { ty0 = ti.rem / p.Win; tx0 = ti.rem - ty0 * p.Win; }
+        if (p.conv_tma) { ty0 = ti.rem / p.Wout; tx0 = ti.rem - ty0 * p.Wout; }   // first OUTPUT pixel of the tile
         for (int ci = 0; ci < p.achunks; ++ci, ring.advance()) {
           const int stage = ring.stage;
           const uint32_t cd = p.chunk[ci];
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 tma_load_4d(a_smem, &p.tmap[0], ci * 64, tx0 - 1, ty0 - 1, ti.img, raw_bar(stage));
               } else if (p.conv_tma) {
                 const int tap = cd & 0x7f, ky = tap / 3, kx = tap - ky * 3;
-                tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), tx0 + kx - 1, ty0 + ky - 1, ti.img, raw_bar(stage));
+                tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), p.conv_stride * tx0 + kx - 1, p.conv_stride * ty0 + ky - 1, ti.img, raw_bar(stage));
               } else {
                 tma_load_2d(a_smem, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
               }
@@ -742,20 +743,25 @@ bool activation_map(const void* ptr, long long M, int K, int ld, bool f16, CUten
 }
 
 // NHWC image tensor [N][H][W][C] bf16: box = 64 channels x box_w pixels x box_h rows (box_w * box_h = 128), zero fill
-bool image_map(const void* ptr, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out) {
+// box = box_w x box_h pixels of 64 channels; stride 2: every second pixel / row of a (2 box_w) x (2 box_h) window
+// (element strides: the box is given in traversal space and ceil(box / stride) elements are loaded)
+bool image_map(const void* ptr, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out, int stride = 1) {
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  return encode_tmap(out, TMAP_BF16, 4, ptr, gdim, gstride, box, true);
+  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  return encode_tmap(out, TMAP_BF16, 4, ptr, gdim, gstride, box, true, estr);
 }
 
 }  // namespace
 
 bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const cuuint64_t* gdim,
-                 const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128) {
+                 const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128, const cuuint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank && i < 5; ++i) estr[i] = elem_strides[i];
   return enc(out, dtype == TMAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
              const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -813,13 +819,20 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
     {
       static int no_tma = -1;
       if (no_tma < 0) { const char* e = getenv("LCM_CONV_GATHER"); no_tma = (e && atoi(e)) ? 1 : 0; }
-      const int W = cg.Win, H = cg.Hin;
-      const bool boxable = (W >= 128 ? W % 128 == 0 : 128 % W == 0) && ((long long)H * W) % 128 == 0;
-      if (cg.mode == CONV_S1 && boxable && !no_tma) {
+      // tiles are boxes of OUTPUT pixels; the stride-2 convs read every second input pixel / row through a tensor map
+      // with element strides (they used to gather their taps with ordinary loads: 1.3 TB/s)
+      const int W = cg.Wout, H = cg.Hout;
+      const int cstride = cg.mode == CONV_S2 ? 2 : 1;
+      const bool boxable = (W >= 128 ? W % 128 == 0 : 128 % W == 0) && ((long long)H * W) % 128 == 0 &&
+                           cg.Win == W * cstride && cg.Hin == H * cstride;
+      static int no_s2 = -1;
+      if (no_s2 < 0) { const char* e = getenv("LCM_CONV_S2_GATHER"); no_s2 = (e && atoi(e)) ? 1 : 0; }
+      if ((cg.mode == CONV_S1 || (cg.mode == CONV_S2 && !no_s2)) && boxable && !no_tma) {
         const int bw = W >= 128 ? 128 : W, bh = 128 / bw;
         const long long imgs = g.M / ((long long)H * W);
-        if (!image_map(g.seg[0].A, (int)imgs, H, W, cg.Ci, bw, bh, &p.tmap[0])) return -3;
+        if (!image_map(g.seg[0].A, (int)imgs, cg.Hin, cg.Win, cg.Ci, bw, bh, &p.tmap[0], cstride)) return -3;
         p.conv_tma = 1;
+        p.conv_stride = cstride;
         p.box_w = bw;
         p.conv_mode = -1;   // runs the TMA-fed (non-gather) kernel variant
         // halo mode: tile = 128 pixels of one image row, weights of all 9 taps resident next to >= 2 halo stages
@@ -828,7 +841,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
         const int nchh = (cg.Ci + 63) / 64;
         const uint32_t wres = 9u * nchh * (uint32_t)block_n * 128u;
         const uint32_t stg1 = (128u * ((uint32_t)block_n * 2u + 16u) + 1023u) & ~1023u;
-        if (!no_halo && bw == 128 && wres <= 131072 && kMisc2 + 2048 + stg1 + wres + 2 * kHaloStage <= kSmemLimit2) {
+        if (!no_halo && cstride == 1 && bw == 128 && wres <= 131072 && kMisc2 + 2048 + stg1 + wres + 2 * kHaloStage <= kSmemLimit2) {
           if (!image_map(g.seg[0].A, (int)imgs, H, W, cg.Ci, 130, 3, &p.tmap[0])) return -3;
           p.conv_halo = 1;
         }
