@@ -47,7 +47,7 @@ constexpr uint32_t kStageA2 = 16384;
 constexpr uint32_t kHaloBytes = 130u * 3u * 128u, kHaloStage = 51200;   // [3 rows][130 px][64 ch] bf16, stage rounded to 1 KB
 constexpr int kMaxChunks2 = 160;
 constexpr uint32_t kSmemLimit2 = 232448;
-constexpr uint32_t kMisc2 = 4096 + 8192;    // barriers + per-column accumulators | statistics flush scratch [2048] fp32
+constexpr uint32_t kMisc2 = 4096 + 4096;    // barriers + per-column accumulators | statistics flush scratch [1024] fp32
 
 struct alignas(64) Tc2Params {
   CUtensorMap tmap[LCM_MAX_SEGS];
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   float* s_sum = reinterpret_cast<float*>(misc + 512);
   float* s_sq = s_sum + 256;
   float* s_bias = s_sq + 256;
-  float* s_scr = reinterpret_cast<float*>(misc + 4096);   // [2048]: statistics flush scratch (sums, then squares)
+  float* s_scr = reinterpret_cast<float*>(misc + 4096);   // [1024]: statistics flush scratch
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_off);
 
   auto ld_s = [&](uint32_t saddr) { return *reinterpret_cast<const uint4*>(smem + (saddr - sbase)); };
@@ -620,26 +620,36 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
     float cs[8], cq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-    auto flush = [&]() {   // uniform across the 256 E2 threads; sums, then squares through the same 8 KB scratch
-      float a = 0.f, b = 0.f;
-      float4* ps = reinterpret_cast<float4*>(s_scr + rg * p.block_n + cu * 8);
-      if (active) { ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]); }
-      bar_sync(2, kE2Threads);
-      if (et < p.block_n) {
+    auto flush = [&]() {   // uniform across the 256 E2 threads
+      // four passes through one 4 KB scratch (sums / squares x lower / upper half of the columns): with streamed weights
+      // every KB of shared memory decides the number of pipeline stages, and a flush happens once per image
+      const int hb = p.block_n >> 1;              // columns per pass
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};       // { sum lo, sum hi, sq lo, sq hi } of columns et and et + hb
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int half = pass & 1;
+        const int col = cu * 8 - half * hb;
+        if (active && col >= 0 && col < hb) {
+          float4* ps = reinterpret_cast<float4*>(s_scr + rg * hb + col);
+          if (pass < 2) { ps[0] = make_float4(cs[0], cs[1], cs[2], cs[3]); ps[1] = make_float4(cs[4], cs[5], cs[6], cs[7]); }
+          else { ps[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); ps[1] = make_float4(cq[4], cq[5], cq[6], cq[7]); }
+        }
+        bar_sync(2, kE2Threads);
+        if (et < hb) {
+          float a = 0.f;
 #pragma unroll 4
-        for (int g = 0; g < RG; ++g) a += s_scr[g * p.block_n + et];
+          for (int g = 0; g < RG; ++g) a += s_scr[g * hb + et];
+          acc4[pass] = a;
+        }
+        bar_sync(2, kE2Threads);
       }
-      bar_sync(2, kE2Threads);
-      if (active) { ps[0] = make_float4(cq[0], cq[1], cq[2], cq[3]); ps[1] = make_float4(cq[4], cq[5], cq[6], cq[7]); }
-      bar_sync(2, kE2Threads);
-      if (et < p.block_n) {
-#pragma unroll 4
-        for (int g = 0; g < RG; ++g) b += s_scr[g * p.block_n + et];
+      if (et < hb) {
         double* d = p.stats + ((size_t)cur_img * p.Nc + (size_t)cur_nt * p.block_n + et) * 2;
-        atomicAdd(d, (double)a);
-        atomicAdd(d + 1, (double)b);
+        atomicAdd(d, (double)acc4[0]);
+        atomicAdd(d + 1, (double)acc4[2]);
+        atomicAdd(d + 2 * hb, (double)acc4[1]);
+        atomicAdd(d + 2 * hb + 1, (double)acc4[3]);
       }
-      bar_sync(2, kE2Threads);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
     };
