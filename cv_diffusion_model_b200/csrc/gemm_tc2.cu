@@ -885,10 +885,12 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   static int no_wgate = -1;
   if (no_wgate < 0) { const char* e = getenv("LCM_NO_WGATE"); no_wgate = (e && atoi(e)) ? 1 : 0; }
   uint32_t bres = (uint32_t)nch * b_chunk;
-  p.resident = (bres <= 131072 && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
+  static uint32_t res_limit = 0;   // largest weight image kept resident (LCM_TC_RES_LIMIT, bytes)
+  if (!res_limit) { const char* e = getenv("LCM_TC_RES_LIMIT"); res_limit = e ? (uint32_t)atoi(e) : 131072u; }
+  p.resident = (bres <= res_limit && base_fixed + stg_bytes + bres + 3 * kStageA2 <= kSmemLimit2) ? 1 : 0;
   if (has_gate && p.resident && p.fast && !no_wgate) {
     const uint32_t bres2 = (uint32_t)(nch + ngate) * b_chunk;   // + low-order images of the gated chunks
-    if (bres2 <= 131072 && base_fixed + stg_bytes + bres2 + 3 * kStageA2 <= kSmemLimit2) { p.wgate = 1; bres = bres2; }
+    if (bres2 <= res_limit && base_fixed + stg_bytes + bres2 + 3 * kStageA2 <= kSmemLimit2) { p.wgate = 1; bres = bres2; }
   }
   if (!p.resident && p.fast && p.conv_mode < 0 && !p.conv_tma) {
     // streamed weights: an fp16 SE-gated segment needs only its packed gate pairs (K * 2 bytes) in shared memory

@@ -120,11 +120,22 @@ __global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const doub
                                int groups, double count, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                                float2* __restrict__ coef) {
-  pdl_wait();
-  pdl_trigger();
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.x;
   const int C = C0 + C1;
+  // gamma / beta / FiLM do not depend on the producer of the statistics: start pulling them in before the dependency
+  // wait, so that their (cold) latency overlaps the statistics loads instead of following them
+#pragma unroll 1
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(gamma + c));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(beta + c));
+    if (film) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(film + (size_t)n * film_ld + c));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(film + (size_t)n * film_ld + C + c));
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
   const int cpg = C / groups;
   const double inv_count = 1.0 / count;   // one fp64 division per thread
   // one warp per group (fixed summation order: lanes stride over the group's channels, then a shuffle tree)
