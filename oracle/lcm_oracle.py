@@ -67,7 +67,7 @@ def enhance(sd: Dict[str, torch.Tensor], cfg, low_light: torch.Tensor, latents0:
     latents = latents0
     trace = []
     for i, t in enumerate(sched):
-        tt = torch.full((low_light.shape[0],), t, dtype=torch.long)
+        tt = torch.full((low_light.shape[0],), t, dtype=torch.long, device=low_light.device)
         eps = unet_oracle.unet_forward(sd, cfg, torch.cat([latents, low_light], dim=1), tt, strict_groupnorm)
         nz = noises[i] if i < len(sched) - 1 else None
         latents, _ = step(eps, t, latents, sched, abar, nz)
