@@ -85,6 +85,9 @@ void launch_affine_residual(const void* u, const float2* coef, const void* x, vo
 // ---- a11: LCMScheduler.step / add_noise stand-alone ---------------------------------------------------
 void launch_lcm_step(const float* eps, const float* sample, const float* noise, float* prev, float* x0,
                      long long numel, int prediction, float sb_t, float sa_t, float sa_p, float sb_p, cudaStream_t st);
+// image formats either side of the path (scripts/inference.py:111-116, 121-127)
+void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st);
+void launch_image_post_u8(const float* nchw, uint8_t* hwc, int N, int H, int W, cudaStream_t st);
 void launch_lcm_mix(const float* a, const float* b, const long long* t, const float* abar, float* out, int batch,
                     long long per_sample, int velocity, cudaStream_t st);
 

@@ -381,6 +381,44 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Image formats either side of the path (scripts/inference.py:111-116, 121-127): byte work, HBM-bound.
+// One thread per pixel: 3 interleaved bytes <-> one element of each of the three planes (plane accesses coalesced,
+// the 3-byte pixel accesses are consecutive across the warp: 96 contiguous bytes).
+__global__ void image_pre_u8_kernel(const uint8_t* __restrict__ hwc, float* __restrict__ nchw, long long hw, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, p = i - n * hw;
+    const uint8_t* src = hwc + i * 3;
+    float* dst = nchw + n * 3 * hw + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c * hw] = __fsub_rn(__fdiv_rn((float)src[c], 127.5f), 1.0f);   // numpy: x.astype(f32) / 127.5 - 1.0
+  }
+}
+__global__ void image_post_u8_kernel(const float* __restrict__ nchw, uint8_t* __restrict__ hwc, long long hw, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, p = i - n * hw;
+    const float* src = nchw + n * 3 * hw + p;
+    uint8_t* dst = hwc + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fmul_rn(__fadd_rn(src[c * hw], 1.0f), 127.5f);   // numpy: (y + 1.0) * 127.5
+      dst[c] = (uint8_t)(int)fminf(fmaxf(v, 0.f), 255.f);                 // np.clip(., 0, 255).astype(np.uint8): truncation
+    }
+  }
+}
+void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st) {
+  const long long hw = (long long)H * W, total = hw * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  image_pre_u8_kernel<<<blocks, 256, 0, st>>>(hwc, nchw, hw, total);
+}
+void launch_image_post_u8(const float* nchw, uint8_t* hwc, int N, int H, int W, cudaStream_t st) {
+  const long long hw = (long long)H * W, total = hw * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  image_post_u8_kernel<<<blocks, 256, 0, st>>>(nchw, hwc, hw, total);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight packing: fp32 state_dict tensors -> the layouts the kernels read.
 // destination element type of a logical-matrix job: PackJob::bf16 = 0 fp32, 1 bf16, 2 fp16
 __device__ __forceinline__ void put_any(const PackJob& j, int n, int k, float v) {

@@ -860,6 +860,19 @@ int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_d
   return 0;
 }
 
+int lcm_image_preprocess_u8(const uint8_t* hwc_dev, float* nchw_dev, int batch, int height, int width, void* stream) {
+  if (!hwc_dev || !nchw_dev || batch < 1 || height < 1 || width < 1) return fail(LCM_ERR_INVALID, "null argument or empty image");
+  launch_image_pre_u8(hwc_dev, nchw_dev, batch, height, width, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch, int height, int width, void* stream) {
+  if (!hwc_dev || !nchw_dev || batch < 1 || height < 1 || width < 1) return fail(LCM_ERR_INVALID, "null argument or empty image");
+  launch_image_post_u8(nchw_dev, hwc_dev, batch, height, width, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int lcm_plan_num_taps(const lcm_plan* plan) { return plan ? (int)plan->tap_order.size() : 0; }
 int lcm_plan_tap_info(const lcm_plan* plan, int index, const char** name, int* channels, int* height, int* width) {
   if (!plan || index < 0 || index >= (int)plan->tap_order.size()) return fail(LCM_ERR_INVALID, "bad tap index");

@@ -95,3 +95,27 @@ def dwconv(x: torch.Tensor, coef: torch.Tensor, weight: torch.Tensor, impl: int 
         native.check(native.lib().lcm_op_dwconv(_p(x), _p(coef), _p(wt), _p(out), _p(pool), n, h, w_, c, _prec(x), impl,
                                                 repeat, C.byref(ms) if timing else None, _stream_ptr()))
     return (out, pool, ms.value) if timing else (out, pool)
+
+
+def image_preprocess_u8(images: torch.Tensor) -> torch.Tensor:
+    """uint8 RGB ``[N,H,W,3]`` on the device -> fp32 ``[N,3,H,W]`` in [-1, 1]: ``x / 127.5 - 1``
+    (the reference's ``preprocess_image`` after its resize, scripts/inference.py:111-116; bit-identical)."""
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3 or not images.is_cuda:
+        raise ValueError("expected a CUDA uint8 tensor [N, H, W, 3]")
+    images = images.contiguous()
+    n, h, w, _ = images.shape
+    out = torch.empty(n, 3, h, w, dtype=torch.float32, device=images.device)
+    native.check(native.lib().lcm_image_preprocess_u8(_p(images), _p(out), n, h, w, _stream_ptr()))
+    return out
+
+
+def image_postprocess_u8(images: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[N,3,H,W]`` on the device -> uint8 RGB ``[N,H,W,3]``: ``clip((y + 1) * 127.5, 0, 255)`` truncated
+    (the reference's ``postprocess_image`` before its resize, scripts/inference.py:121-127; bit-identical)."""
+    if images.dtype != torch.float32 or images.dim() != 4 or images.shape[1] != 3 or not images.is_cuda:
+        raise ValueError("expected a CUDA fp32 tensor [N, 3, H, W]")
+    images = images.contiguous()
+    n, _, h, w = images.shape
+    out = torch.empty(n, h, w, 3, dtype=torch.uint8, device=images.device)
+    native.check(native.lib().lcm_image_postprocess_u8(_p(images), _p(out), n, h, w, _stream_ptr()))
+    return out

@@ -78,6 +78,16 @@ class LowLightDiffusion(nn.Module):
             return LowLightDiffusionOutput(enhanced=out, intermediate=[tr[i] for i in range(steps)])
         return res
 
+    @torch.no_grad()
+    def enhance_uint8(self, images: torch.Tensor, num_inference_steps: Optional[int] = None,
+                      generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """uint8 RGB ``[N,H,W,3]`` in, uint8 RGB ``[N,H,W,3]`` out, everything on the device: the normalisation
+        and layout steps of the reference's ``preprocess_image`` / ``postprocess_image`` (scripts/inference.py:111-127)
+        around :meth:`enhance`.  Resizing stays with the caller.  A quarter of the PCIe bytes of the fp32 NCHW surface."""
+        from . import ops
+        x = ops.image_preprocess_u8(images)
+        return ops.image_postprocess_u8(self.enhance(x, num_inference_steps=num_inference_steps, generator=generator))
+
     def forward(self, low_light: torch.Tensor, normal_light: Optional[torch.Tensor] = None,
                 timesteps: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                 return_dict: bool = True):

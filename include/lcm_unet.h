@@ -114,6 +114,14 @@ int lcm_scheduler_step(const float* model_out_dev, const float* sample_dev, cons
 int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_dev, const float* abar_dev,
                       float* out_dev, int batch, int64_t per_sample, int velocity, void* stream);
 
+/* ---- image formats either side of the path -----------------------------------
+ * preprocess (scripts/inference.py:111-116): uint8 RGB HWC [N][H][W][3] -> fp32 NCHW, x / 127.5 - 1 (fp32 division, then
+ * fp32 subtraction: bit-identical to the reference's numpy expression).
+ * postprocess (scripts/inference.py:121-127): fp32 NCHW -> uint8 RGB HWC, (y + 1) * 127.5, clip to [0, 255], truncate.
+ * Resizing (cv2.resize) stays with the caller. */
+int lcm_image_preprocess_u8(const uint8_t* hwc_dev, float* nchw_dev, int batch, int height, int width, void* stream);
+int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch, int height, int width, void* stream);
+
 /* ---- debugging / unit parity --------------------------------------------------------------------
  * Copy a named intermediate of the most recent forward (e.g. "encoder_blocks.0.0.expand",
  * "mid_attn.out", see lcm_plan_tap_info) into fp32 NCHW.  Only valid when the plan was created with

@@ -272,3 +272,29 @@ def test_gemm_expand_kernel(images, P, Ks, Nc):
     e0 = ((stats - sref)[..., 0].abs() / (sref[..., 1].sqrt() * P ** 0.5 + 1e-6)).max().item()   # |dSum| / (rms * P)
     e1 = ((stats - sref)[..., 1].abs() / sref[..., 1]).max().item()
     assert e0 < 1e-3 and e1 < 2e-3, (e0, e1)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 32, 32), (1, 5, 7), (3, 33, 129), (64, 256, 256)])
+def test_image_io_u8_bit_exact(N, H, W):
+    """uint8 HWC <-> fp32 NCHW either side of the path (scripts/inference.py:111-127): bit-exact against the oracle,
+    on the committed reference golden vectors and on seeded inputs up to the bench batch (64 x 256 x 256)."""
+    import numpy as np
+    from cv_diffusion_model_b200 import ops
+    from oracle import image_io_oracle
+    if (N, H, W) == (2, 32, 32):
+        kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_io_kat.npz"))
+        rgb, y = kat["rgb"], kat["y"]
+        assert np.array_equal(ops.image_preprocess_u8(torch.from_numpy(rgb).cuda()).cpu().numpy(), kat["pre"])
+        assert np.array_equal(ops.image_postprocess_u8(torch.from_numpy(y).cuda()).cpu().numpy(), kat["post"])
+    rng = np.random.default_rng(N * 1000 + H)
+    rgb = rng.integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)
+    y = rng.uniform(-1.2, 1.2, size=(N, 3, H, W)).astype(np.float32)
+    y.reshape(-1)[:4] = [-1.0, 1.0, np.float32(2.0 / 255 - 1), -1.0000001]
+    pre = ops.image_preprocess_u8(torch.from_numpy(rgb).cuda())
+    assert pre.dtype == torch.float32 and tuple(pre.shape) == (N, 3, H, W)
+    assert np.array_equal(pre.cpu().numpy(), image_io_oracle.preprocess_u8(rgb))
+    post = ops.image_postprocess_u8(torch.from_numpy(y).cuda())
+    assert post.dtype == torch.uint8 and tuple(post.shape) == (N, H, W, 3)
+    assert np.array_equal(post.cpu().numpy(), image_io_oracle.postprocess_u8(y))
+    with pytest.raises(ValueError):
+        ops.image_preprocess_u8(torch.zeros(1, 3, 4, 4, dtype=torch.uint8, device="cuda"))

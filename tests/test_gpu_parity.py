@@ -253,3 +253,21 @@ def test_wider_variants_forward_parity(variant, size):
     assert torch.equal(y, y2)
     assert rel_rms(y, want) <= 0.03
     assert (y - want).abs().max().item() <= 0.15 * want.abs().max().item()
+
+
+def test_enhance_uint8_surface():
+    """uint8 HWC in / out around enhance: equals preprocess -> enhance -> postprocess of the oracle formats (bit-exact
+    given the same enhance result), values stay bytes."""
+    import numpy as np
+    from cv_diffusion_model_b200 import LowLightDiffusion
+    from oracle import image_io_oracle
+    torch.manual_seed(0)
+    pipe = LowLightDiffusion(unet_variant="small", image_size=64, num_inference_steps=4, precision="bf16").cuda().eval()
+    rgb = torch.randint(0, 60, (2, 64, 64, 3), dtype=torch.uint8)            # a dark image
+    torch.manual_seed(3)
+    out = pipe.enhance_uint8(rgb.cuda())
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (2, 64, 64, 3)
+    torch.manual_seed(3)                                                      # same RNG protocol -> same latents / noises
+    x = torch.from_numpy(image_io_oracle.preprocess_u8(rgb.numpy())).cuda()
+    y = pipe.enhance(x).cpu().numpy()
+    assert np.array_equal(out.cpu().numpy(), image_io_oracle.postprocess_u8(y))

@@ -132,3 +132,22 @@ def test_enhance_oracle_matches_reference_golden(golden, weight_digests, tag, si
     out, trace = lcm_oracle.enhance(sd, m.config, low, lat0, noises, steps, return_all=True)
     assert (out - torch.from_numpy(golden[f"enh_{tag}_out"])).abs().max().item() <= 1e-5
     assert (trace[-1][1] - torch.from_numpy(golden[f"enh_{tag}_preclamp"])).abs().max().item() <= 1e-4
+
+
+def test_image_io_oracle_matches_reference_golden():
+    """oracle/image_io_oracle.py against the outputs of the unmodified reference's preprocess_image / postprocess_image
+    (tests/golden/make_golden_image_io.py), bit-exact."""
+    import os
+    import numpy as np
+    from oracle import image_io_oracle
+    kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_io_kat.npz"))
+    pre = image_io_oracle.preprocess_u8(kat["rgb"])
+    assert pre.dtype == np.float32 and np.array_equal(pre, kat["pre"])
+    post = image_io_oracle.postprocess_u8(kat["y"])
+    assert post.dtype == np.uint8 and np.array_equal(post, kat["post"])
+    # the byte grid: every value maps into [-1, 1] and comes back as itself or one below (truncation after two roundings)
+    u = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    x = image_io_oracle.preprocess_u8(u)
+    assert x.min() == -1.0 and x.max() == 1.0
+    back = image_io_oracle.postprocess_u8(x).astype(np.int32)
+    assert ((u.astype(np.int32) - back) >= 0).all() and ((u.astype(np.int32) - back) <= 1).all()
