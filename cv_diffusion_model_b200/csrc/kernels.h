@@ -88,6 +88,7 @@ void launch_lcm_step(const float* eps, const float* sample, const float* noise, 
 // image formats either side of the path (scripts/inference.py:111-116, 121-127)
 void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st);
 void launch_image_post_u8(const float* nchw, uint8_t* hwc, int N, int H, int W, cudaStream_t st);
+void launch_image_resize_u8(const uint8_t* src, int N, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st);
 void launch_lcm_mix(const float* a, const float* b, const long long* t, const float* abar, float* out, int batch,
                     long long per_sample, int velocity, cudaStream_t st);
 

@@ -405,6 +405,50 @@ __global__ void image_post_u8_kernel(const float* __restrict__ nchw, uint8_t* __
     }
   }
 }
+// cv2.resize INTER_LINEAR, CV_8UC3 (OpenCV resize.cpp: HResizeLinear<uchar,int,short,2048> + VResizeLinear with
+// FixedPtCast<int,uchar,22>): coefficient tables rebuilt per thread with the same float / double operations.
+__device__ __forceinline__ void resize_tap(int d, double scale, int src, bool is_x, int& s, int& w0, int& w1) {
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  s = (int)floorf(f);
+  f -= (float)s;
+  if (is_x) {                       // x: out-of-range taps are folded into the border pixel with weight 1
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  w0 = __float2int_rn((1.f - f) * 2048.f);   // saturate_cast<short>(cvRound(.)): round half to even, |.| <= 2048
+  w1 = __float2int_rn(f * 2048.f);
+}
+__global__ void image_resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                                       double scale_x, double scale_y, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % dw);
+    const long long q = i / dw;
+    const int dy = (int)(q % dh), n = (int)(q / dh);
+    int sx, ax0, ax1, sy, by0, by1;
+    resize_tap(dx, scale_x, sw, true, sx, ax0, ax1);
+    resize_tap(dy, scale_y, sh, false, sy, by0, by1);
+    const int x1 = min(sx + 1, sw - 1);
+    const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);   // y: rows clamped, weights kept
+    const uint8_t* r0 = src + ((long long)n * sh + y0) * sw * 3;
+    const uint8_t* r1 = src + ((long long)n * sh + y1) * sw * 3;
+    uint8_t* o = dst + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = (int)r0[sx * 3 + c] * ax0 + (int)r0[x1 * 3 + c] * ax1;
+      const int h1 = (int)r1[sx * 3 + c] * ax0 + (int)r1[x1 * 3 + c] * ax1;
+      const int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
+}
+void launch_image_resize_u8(const uint8_t* src, int N, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st) {
+  const long long total = (long long)N * dh * dw;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  // OpenCV: inv_scale = dsize / ssize (double), scale = 1. / inv_scale
+  const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);
+  image_resize_u8_kernel<<<blocks, 256, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, total);
+}
 void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st) {
   const long long hw = (long long)H * W, total = hw * N;
   int blocks = (int)((total + 255) / 256);

@@ -873,6 +873,15 @@ int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch,
   return 0;
 }
 
+int lcm_image_resize_u8(const uint8_t* src_hwc_dev, int batch, int src_h, int src_w, uint8_t* dst_hwc_dev, int dst_h, int dst_w,
+                        void* stream) {
+  if (!src_hwc_dev || !dst_hwc_dev || batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1)
+    return fail(LCM_ERR_INVALID, "null argument or empty image");
+  launch_image_resize_u8(src_hwc_dev, batch, src_h, src_w, dst_hwc_dev, dst_h, dst_w, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int lcm_plan_num_taps(const lcm_plan* plan) { return plan ? (int)plan->tap_order.size() : 0; }
 int lcm_plan_tap_info(const lcm_plan* plan, int index, const char** name, int* channels, int* height, int* width) {
   if (!plan || index < 0 || index >= (int)plan->tap_order.size()) return fail(LCM_ERR_INVALID, "bad tap index");

@@ -57,6 +57,7 @@ SIGNATURES = {
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "lcm_image_preprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lcm_image_postprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "lcm_image_resize_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lcm_scheduler_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                     C.c_int, C.c_void_p]),
     "lcm_plan_num_taps": (C.c_int, [C.c_void_p]),

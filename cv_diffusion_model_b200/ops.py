@@ -119,3 +119,15 @@ def image_postprocess_u8(images: torch.Tensor) -> torch.Tensor:
     out = torch.empty(n, h, w, 3, dtype=torch.uint8, device=images.device)
     native.check(native.lib().lcm_image_postprocess_u8(_p(images), _p(out), n, h, w, _stream_ptr()))
     return out
+
+
+def image_resize_u8(images: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """``cv2.resize(img, (width, height))`` (default INTER_LINEAR) on uint8 RGB ``[N,H,W,3]`` device tensors,
+    bit-identical to OpenCV's fixed-point bilinear (scripts/inference.py:109,130)."""
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3 or not images.is_cuda:
+        raise ValueError("expected a CUDA uint8 tensor [N, H, W, 3]")
+    images = images.contiguous()
+    n, h, w, _ = images.shape
+    out = torch.empty(n, int(height), int(width), 3, dtype=torch.uint8, device=images.device)
+    native.check(native.lib().lcm_image_resize_u8(_p(images), n, h, w, _p(out), int(height), int(width), _stream_ptr()))
+    return out

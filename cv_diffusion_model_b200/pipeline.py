@@ -80,13 +80,18 @@ class LowLightDiffusion(nn.Module):
 
     @torch.no_grad()
     def enhance_uint8(self, images: torch.Tensor, num_inference_steps: Optional[int] = None,
-                      generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """uint8 RGB ``[N,H,W,3]`` in, uint8 RGB ``[N,H,W,3]`` out, everything on the device: the normalisation
-        and layout steps of the reference's ``preprocess_image`` / ``postprocess_image`` (scripts/inference.py:111-127)
-        around :meth:`enhance`.  Resizing stays with the caller.  A quarter of the PCIe bytes of the fp32 NCHW surface."""
+                      generator: Optional[torch.Generator] = None, target_size: Optional[int] = None) -> torch.Tensor:
+        """uint8 RGB ``[N,H,W,3]`` in, uint8 RGB ``[N,H,W,3]`` out, everything on the device: the reference's
+        ``preprocess_image`` / ``postprocess_image`` (scripts/inference.py:99-134) around :meth:`enhance` —
+        ``cv2.resize`` to ``target_size`` x ``target_size`` (if given), ``x / 127.5 - 1``, HWC -> NCHW, enhance,
+        ``clip((y + 1) * 127.5)`` -> uint8, NCHW -> HWC, ``cv2.resize`` back to the original size.  All three steps are
+        bit-identical to the reference's numpy / OpenCV arithmetic.  A quarter of the PCIe bytes of the fp32 surface."""
         from . import ops
-        x = ops.image_preprocess_u8(images)
-        return ops.image_postprocess_u8(self.enhance(x, num_inference_steps=num_inference_steps, generator=generator))
+        h, w = int(images.shape[1]), int(images.shape[2])
+        x = images if target_size is None else ops.image_resize_u8(images, target_size, target_size)
+        y = ops.image_postprocess_u8(self.enhance(ops.image_preprocess_u8(x), num_inference_steps=num_inference_steps,
+                                                  generator=generator))
+        return y if target_size is None else ops.image_resize_u8(y, h, w)
 
     def forward(self, low_light: torch.Tensor, normal_light: Optional[torch.Tensor] = None,
                 timesteps: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,

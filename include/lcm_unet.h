@@ -121,6 +121,11 @@ int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_d
  * Resizing (cv2.resize) stays with the caller. */
 int lcm_image_preprocess_u8(const uint8_t* hwc_dev, float* nchw_dev, int batch, int height, int width, void* stream);
 int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch, int height, int width, void* stream);
+/* cv2.resize(img, (dst_w, dst_h)) with the default INTER_LINEAR on 8-bit 3-channel images (scripts/inference.py:109,130):
+ * OpenCV's fixed-point bilinear (11-bit coefficients, x taps clamped with the weight reset, y taps clamped by row index),
+ * bit-identical to OpenCV 4.x including the exact-2x shrink (where OpenCV switches to area averaging: same values). */
+int lcm_image_resize_u8(const uint8_t* src_hwc_dev, int batch, int src_h, int src_w, uint8_t* dst_hwc_dev, int dst_h,
+                        int dst_w, void* stream);
 
 /* ---- debugging / unit parity --------------------------------------------------------------------
  * Copy a named intermediate of the most recent forward (e.g. "encoder_blocks.0.0.expand",

@@ -48,5 +48,19 @@ post = np.stack([ref.postprocess_image(y[i:i + 1], (S, S)) for i in range(y.shap
 assert post.dtype == np.uint8 and post.shape == (2, S, S, 3)
 assert np.array_equal(image_io_oracle.postprocess_u8(y), post), "oracle postprocess differs from the reference"
 
-np.savez_compressed(os.path.join(HERE, "image_io_kat.npz"), rgb=rgb, pre=pre, y=y, post=post)
+# cv2.resize exactly as the reference calls it (inference.py:109 and :130): default interpolation, dsize = (width, height)
+resize = {}
+for k, (sh, sw, dh, dw) in enumerate([(24, 32, 64, 64), (50, 70, 32, 32), (64, 64, 32, 32), (33, 17, 40, 56), (7, 5, 64, 48),
+                                      (48, 48, 48, 48), (96, 64, 32, 32)]):
+    src = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
+    dst = cv2.resize(src, (dw, dh))
+    assert np.array_equal(image_io_oracle.resize_bilinear_u8(src[None], dh, dw)[0], dst), ("oracle resize differs from cv2", sh, sw, dh, dw)
+    resize[f"rs{k}_src"], resize[f"rs{k}_dst"] = src, dst
+# a photo-sized check that is not stored
+big = rng.integers(0, 256, size=(1080, 1920, 3), dtype=np.uint8)
+assert np.array_equal(image_io_oracle.resize_bilinear_u8(big[None], 256, 256)[0], cv2.resize(big, (256, 256)))
+small = rng.integers(0, 256, size=(256, 256, 3), dtype=np.uint8)
+assert np.array_equal(image_io_oracle.resize_bilinear_u8(small[None], 1080, 1920)[0], cv2.resize(small, (1920, 1080)))
+
+np.savez_compressed(os.path.join(HERE, "image_io_kat.npz"), rgb=rgb, pre=pre, y=y, post=post, cv2_version=cv2.__version__, **resize)
 print("image_io_kat.npz written:", rgb.shape, pre.shape, y.shape, post.shape)

@@ -271,3 +271,12 @@ def test_enhance_uint8_surface():
     x = torch.from_numpy(image_io_oracle.preprocess_u8(rgb.numpy())).cuda()
     y = pipe.enhance(x).cpu().numpy()
     assert np.array_equal(out.cpu().numpy(), image_io_oracle.postprocess_u8(y))
+    # with the reference's resize to the model size and back (scripts/inference.py:109,130)
+    big = torch.randint(0, 60, (1, 90, 120, 3), dtype=torch.uint8)
+    torch.manual_seed(4)
+    out2 = pipe.enhance_uint8(big.cuda(), target_size=64)
+    assert out2.dtype == torch.uint8 and tuple(out2.shape) == (1, 90, 120, 3)
+    torch.manual_seed(4)
+    x2 = image_io_oracle.preprocess_u8(image_io_oracle.resize_bilinear_u8(big.numpy(), 64, 64))
+    y2 = image_io_oracle.postprocess_u8(pipe.enhance(torch.from_numpy(x2).cuda()).cpu().numpy())
+    assert np.array_equal(out2.cpu().numpy(), image_io_oracle.resize_bilinear_u8(y2, 90, 120))

@@ -145,6 +145,13 @@ def test_image_io_oracle_matches_reference_golden():
     assert pre.dtype == np.float32 and np.array_equal(pre, kat["pre"])
     post = image_io_oracle.postprocess_u8(kat["y"])
     assert post.dtype == np.uint8 and np.array_equal(post, kat["post"])
+    # cv2.resize (default INTER_LINEAR) as the reference calls it, outputs stored by the generator
+    k = 0
+    while f"rs{k}_src" in kat:
+        src, dst = kat[f"rs{k}_src"], kat[f"rs{k}_dst"]
+        assert np.array_equal(image_io_oracle.resize_bilinear_u8(src[None], dst.shape[0], dst.shape[1])[0], dst), k
+        k += 1
+    assert k >= 7
     # the byte grid: every value maps into [-1, 1] and comes back as itself or one below (truncation after two roundings)
     u = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
     x = image_io_oracle.preprocess_u8(u)
