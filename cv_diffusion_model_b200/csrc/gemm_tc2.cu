@@ -113,16 +113,16 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 
   uint8_t* misc = smem + p.misc_off;
   const uint32_t bar0 = sbase + p.misc_off;
-  auto raw_bar = [&](int s) { return bar0 + 8u * s; };
-  auto xf_bar = [&](int s) { return bar0 + 8u * (8 + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (24 + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (26 + a); };
-  auto sfull_bar = [&](int b) { return bar0 + 8u * (28 + b); };
-  auto sempty_bar = [&](int b) { return bar0 + 8u * (30 + b); };
-  const uint32_t bres_bar = bar0 + 8u * 32;
-  const uint32_t bsc_bar = bar0 + 8u * 33;    // weights rescaled by the SE gate of the current image
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 320);
+  auto raw_bar = [&](int s) { return bar0 + 8u * s; };                 // up to kMaxStages2 = 16 pipeline stages
+  auto xf_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (32 + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (48 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (50 + a); };
+  auto sfull_bar = [&](int b) { return bar0 + 8u * (52 + b); };
+  auto sempty_bar = [&](int b) { return bar0 + 8u * (54 + b); };
+  const uint32_t bres_bar = bar0 + 8u * 56;
+  const uint32_t bsc_bar = bar0 + 8u * 57;    // weights rescaled by the SE gate of the current image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 480);
   float* s_sum = reinterpret_cast<float*>(misc + 512);
   float* s_sq = s_sum + 256;
   float* s_bias = s_sq + 256;
@@ -931,7 +931,9 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   const uint32_t used = used1 + (p.nbuf == 2 ? stg_bytes : 0u);
   if (used >= kSmemLimit2) return -1;
   int stages = (int)((kSmemLimit2 - used) / p.stage_bytes);
-  if (stages > 8) stages = 8;
+  static int max_stages = -1;   // LCM_TC_MAX_STAGES (<= 16); sweep 8..16 on the model: no difference, the small-K GEMMs are not bound by bytes in flight
+  if (max_stages < 0) { const char* e = getenv("LCM_TC_MAX_STAGES"); max_stages = e ? atoi(e) : 8; if (max_stages > 16) max_stages = 16; if (max_stages < 2) max_stages = 2; }
+  if (stages > max_stages) stages = max_stages;
   if (stages < 2) return -1;
   p.stages = stages;
   uint32_t off = (uint32_t)stages * p.stage_bytes;
