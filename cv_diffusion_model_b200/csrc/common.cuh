@@ -21,6 +21,14 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 bool pdl_enabled();   // plan.cu
 
+// Function attributes and occupancy are per DEVICE: a process that builds plans on several GPUs must opt every kernel in
+// on each of them.  ensure_dyn_smem remembers (current device, function) -> bytes opted in so far and raises the limit
+// when needed; device_cache_slot returns a zero-initialised int slot per (current device, key) for occupancy caches.
+// Both are thread-safe (plan.cu).
+int ensure_dyn_smem(const void* fn, size_t bytes);   // 0 = ok
+int* device_cache_slot(const void* key, int sub = 0);
+template <class F> inline int ensure_dyn_smem_fn(F fn, size_t bytes) { return ensure_dyn_smem((const void*)fn, bytes); }
+
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};

@@ -320,13 +320,11 @@ bool launch_final_conv_h2(const void* in, const float2* coef, const float* w, co
     case 16: launch_pdl(final_conv_h2_kernel<16>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     case 32: launch_pdl(final_conv_h2_kernel<32>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     case 48: {
-      static bool done = false;
-      if (!done) { cudaFuncSetAttribute(final_conv_h2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+      if (ensure_dyn_smem_fn(final_conv_h2_kernel<48>, smem)) return false;
       launch_pdl(final_conv_h2_kernel<48>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     }
     default: {
-      static bool done = false;
-      if (!done) { cudaFuncSetAttribute(final_conv_h2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+      if (ensure_dyn_smem_fn(final_conv_h2_kernel<64>, smem)) return false;
       launch_pdl(final_conv_h2_kernel<64>, grid, dim3(128), smem, st, (const bf16*)in, coef, w, bias, eps, step, H, W, Co); break;
     }
   }

@@ -303,15 +303,17 @@ int launch_strips(DwParams& p, int num_sms, cudaStream_t st) {
   if (ring < 3) return -1;
   p.ring = ring;
   const size_t smem = fixed + (size_t)ring * p.row_bytes;
-  static int ctas_per_sm = 0;   // per instantiation; smem depends on STRIPS only
+  int ctas_per_sm;   // per (device, instantiation); smem depends on STRIPS only
   {
+    if (ensure_dyn_smem((const void*)fn, 100 * 1024)) return -2;
+    int* slot = device_cache_slot((const void*)fn);
     std::lock_guard<std::mutex> lk(g_dw_mu);
-    if (!ctas_per_sm) {
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) return -2;
+    if (!*slot) {
       int n = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem) != cudaSuccess || n < 1) return -2;
-      ctas_per_sm = n;
+      *slot = n;
     }
+    ctas_per_sm = *slot;
   }
   const int max_ctas = num_sms * ctas_per_sm;
   // row segments: as long as possible while every CTA still gets >= 4 items (tail balance), never below 8 rows

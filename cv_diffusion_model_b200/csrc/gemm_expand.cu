@@ -596,16 +596,9 @@ int launch_gemm_expand(const GemmParams& g, void* scratch, bool zero_scratch, in
     cbase += g.seg[s].K;
   }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_X_TIMELINE"); dbg = (e && atoi(e)) ? 1 : 0; } p.debug = dbg; }
-  static bool attr_done = false;
-  {
-    std::lock_guard<std::mutex> lk(g_x_mu);
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(gemm_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitX) != cudaSuccess) return -2;
-      if (cudaFuncSetAttribute(expand_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 128 + 128 * 32 + 512) * 4) != cudaSuccess) return -2;
-      if (cudaFuncSetAttribute(expand_stats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 64 + 64 * 32 + 512) * 4) != cudaSuccess) return -2;
-      attr_done = true;
-    }
-  }
+  if (ensure_dyn_smem_fn(gemm_expand_kernel, kSmemLimitX) ||
+      ensure_dyn_smem_fn(expand_stats_kernel<128>, (128 * 128 + 128 + 128 * 32 + 512) * 4) ||
+      ensure_dyn_smem_fn(expand_stats_kernel<64>, (64 * 64 + 64 + 64 * 32 + 512) * 4)) return -2;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   if (zero_scratch) {
     if (cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(images), st) != cudaSuccess) return -2;

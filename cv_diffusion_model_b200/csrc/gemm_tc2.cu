@@ -961,26 +961,18 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
                                      : (p.fast ? gemm_tc2_kernel<false, true, true> : gemm_tc2_kernel<false, false, true>);
   else fn = p.conv_mode >= 0 ? (p.fast ? gemm_tc2_kernel<true, true, false> : gemm_tc2_kernel<true, false, false>)
                              : (p.fast ? gemm_tc2_kernel<false, true, false> : gemm_tc2_kernel<false, false, false>);
-  static std::unordered_map<void*, bool> attr_done;
-  {
-    std::lock_guard<std::mutex> lk(g_map_mu);
-    if (!attr_done[(void*)fn]) {
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit2) != cudaSuccess) return -2;
-      attr_done[(void*)fn] = true;
-    }
-  }
+  if (ensure_dyn_smem((const void*)fn, kSmemLimit2)) return -2;
   if (p.bpair) {
-    static std::unordered_map<void*, int> max_pairs;   // per instantiation (shared memory is the same opt-in size class)
-    int mp;
+    int mp;   // per (device, instantiation): 0 = not measured yet, -1 = no pair fits
     {
+      int* slot = device_cache_slot((const void*)fn, 1);
       std::lock_guard<std::mutex> lk(g_map_mu);
-      auto it = max_pairs.find((void*)fn);
-      if (it == max_pairs.end()) {
+      if (*slot == 0) {
         int n = 0;
-        if (launch_pdl_cluster(fn, dim3(num_sms & ~1), dim3(kThreads2), kSmemLimit2, st, 2, &n, p) != cudaSuccess || n < 1) n = 0;
-        it = max_pairs.emplace((void*)fn, n).first;
+        if (launch_pdl_cluster(fn, dim3(num_sms & ~1), dim3(kThreads2), kSmemLimit2, st, 2, &n, p) != cudaSuccess || n < 1) n = -1;
+        *slot = n;
       }
-      mp = it->second;
+      mp = *slot;
     }
     if (mp < 1) { p.bpair = 0; }
     else {

@@ -449,15 +449,7 @@ int launch_gemm_wide(const GemmParams& g, int num_sms, cudaStream_t st) {
     cbase += g.seg[s].K;
   }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_W_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  static std::mutex mu;
-  static bool attr_done = false;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemLimit) != cudaSuccess) return -2;
-      attr_done = true;
-    }
-  }
+  if (ensure_dyn_smem_fn(gemm_wide_kernel, kWSmemLimit)) return -2;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   launch_pdl(gemm_wide_kernel, dim3(grid), dim3(kThreadsW), (size_t)L.total, st, p);
   return 0;

@@ -326,11 +326,7 @@ int launch_se_gate(const double* pool, float inv_count, const float* w1, const f
   const int sqr = (SQ + SE_CL - 1) / SE_CL;
   const size_t sm = ((size_t)SE_IMG * C + (size_t)SE_IMG * SQ + (size_t)SE_IMG * sqr) * sizeof(float);
   if (sm > 200 * 1024) return 1;
-  static size_t attr = 48 * 1024;   // dynamic shared memory opted in so far
-  if (sm > attr) {
-    if (cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 1;
-    attr = sm;
-  }
+  if (ensure_dyn_smem_fn(se_gate_kernel, sm)) return 1;
   const int groups = (N + SE_IMG - 1) / SE_IMG;
   launch_pdl(se_gate_kernel, dim3(groups * SE_CL), dim3(SE_THREADS), sm, st, pool, inv_count, w1, b1, w2, b2, coef, N, C, SQ, dbg);
   return 0;

@@ -16,6 +16,8 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -28,6 +30,31 @@ namespace lcm {
 bool pdl_enabled() {
   static const bool on = !getenv("LCM_NO_PDL");
   return on;
+}
+
+namespace {
+std::mutex g_dev_mu;
+std::map<std::tuple<int, const void*, int>, int> g_dev_slots;      // (device, key, sub) -> cached int
+std::map<std::pair<int, const void*>, size_t> g_dev_smem;          // (device, function) -> dynamic smem opted in
+}  // namespace
+
+int ensure_dyn_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  size_t& have = g_dev_smem[std::make_pair(dev, fn)];
+  if (have >= bytes) return 0;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -2;
+  have = bytes;
+  return 0;
+}
+
+int* device_cache_slot(const void* key, int sub) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  return &g_dev_slots[std::make_tuple(dev, key, sub)];   // std::map nodes are address-stable
 }
 }  // namespace lcm
 
@@ -48,6 +75,16 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (x);                                                                   \
     if (e_ != cudaSuccess) return fail(LCM_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
   } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
@@ -308,9 +345,11 @@ struct Builder {
   }
 
   // ---- InvertedResidualBlock (efficient_unet.py:203-236) -------------------------------------
-  TensorP block(const std::string& name, const View& x, int Co) {
+  // se_ratio: the reference passes config.se_ratio to the encoder/decoder blocks only; mid_block1/2 are built with the
+  // constructor default 0.25 (efficient_unet.py:467-478 vs :440,502)
+  TensorP block(const std::string& name, const View& x, int Co, float se_ratio) {
     const int Ci = x.C(), Ch = Ci * p->cfg.expansion_ratio;
-    int SQ = (int)(Ch * p->cfg.se_ratio);
+    int SQ = (int)(Ch * se_ratio);
     if (SQ < 1) SQ = 1;
     const int h = x.part[0]->H, w = x.part[0]->W;
     const double P = (double)h * w, es = (double)p->esz;
@@ -548,7 +587,7 @@ int build_plan(lcm_plan* p) {
     int idx = 0;
     TensorP cur;
     for (int i = 0; i < nblocks; ++i) {
-      cur = b.block(prefix + "." + std::to_string(idx++), x, Co);
+      cur = b.block(prefix + "." + std::to_string(idx++), x, Co, c.se_ratio);
       if (has_attn(res)) cur = b.attention(prefix + "." + std::to_string(idx++), cur);
       x = View::of(cur);
     }
@@ -569,9 +608,9 @@ int build_plan(lcm_plan* p) {
     }
   }
   // middle (:573-575)
-  h = b.block("mid_block1", View::of(h), widths.back());
+  h = b.block("mid_block1", View::of(h), widths.back(), 0.25f);
   h = b.attention("mid_attn", h);
-  h = b.block("mid_block2", View::of(h), widths.back());
+  h = b.block("mid_block2", View::of(h), widths.back(), 0.25f);
   // decoder (:580-597)
   for (int li = 0; li < c.num_levels; ++li) {
     const int Co = widths[c.num_levels - 1 - li];
@@ -726,7 +765,8 @@ int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LCM_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);   // the caller's current device is restored on every return path
+  if (!guard.ok) return fail(LCM_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(LCM_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);

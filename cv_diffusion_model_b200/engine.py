@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -46,18 +47,28 @@ class Engine:
         cfg = native.config_struct(unet.config, unet.groupnorm)
         flags = (native.FLAG_SIMT_GEMM if simt_gemm else 0) | (native.FLAG_TAPS if taps else 0)
         handle = C.c_void_p()
-        native.check(self.lib.lcm_plan_create(C.byref(cfg), batch, height, width, _PREC[precision], flags, dev_index,
-                                              C.byref(handle)))
+        with torch.cuda.device(self.device):
+            native.check(self.lib.lcm_plan_create(C.byref(cfg), batch, height, width, _PREC[precision], flags, dev_index,
+                                                  C.byref(handle)))
         self.handle = handle
         self.workspace = torch.empty(self.lib.lcm_plan_workspace_bytes(handle), dtype=torch.uint8, device=self.device)
         self._weight_version = None
-        self._graphs: Dict[tuple, dict] = {}
+        self._params = None
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._use_graph = not os.environ.get("LCM_NO_GRAPH")
         self.upload_weights()
 
     # ---- weights --------------------------------------------------------------------------------
-    def _version(self) -> Tuple[int, ...]:
-        return tuple(p._version for p in self.unet.parameters())
+    def _version(self) -> Tuple[int, int]:
+        # (explicit epoch, sum of autograd version counters).  The epoch is bumped by load_state_dict / the native
+        # optimizer / EfficientUNet.mark_weights_changed(); the version sum catches in-place updates by foreign code
+        # (torch optimizers).  The parameter list is cached: walking the module tree costs more than the 321 reads.
+        if self._params is None:
+            self._params = list(self.unet.parameters())
+        v = 0
+        for p in self._params:
+            v += p._version
+        return (getattr(self.unet, "_weights_epoch", 0), v)
 
     def upload_weights(self) -> None:
         sd = self.unet.state_dict()
@@ -136,6 +147,10 @@ class Engine:
         ent = self._graphs.get(key) if self._use_graph and not torch.cuda.is_current_stream_capturing() else None
         if self._use_graph and ent is None and not torch.cuda.is_current_stream_capturing():
             ent = self._graphs[key] = {"calls": 0, "graph": None}
+            while len(self._graphs) > MAX_GRAPHS_PER_ENGINE:     # bounded: each graph pins 3-5 static buffers
+                self._graphs.popitem(last=False)
+        if ent is not None:
+            self._graphs.move_to_end(key)
         if ent is not None and ent["graph"] is None and ent["calls"] >= 2:
             ent["cond"], ent["lat"] = torch.empty_like(cond), torch.empty_like(latents)
             ent["noises"] = torch.empty_like(noises) if steps > 1 else None
@@ -227,15 +242,29 @@ class Engine:
             pass
 
 
+# A plan owns its packed-weight arena and a full activation workspace (7.5 GB for Small@256 B=64, 22-30 GB for the
+# Base@512 / Large@1024 configurations), a graph 3-5 static I/O buffers: both caches are bounded LRUs.  Callers that serve
+# variable batch sizes should pad to a few fixed sizes (every new (B, H, W) builds a plan; the third call with the same
+# schedule captures a graph).
+MAX_ENGINES_PER_UNET = int(os.environ.get("LCM_MAX_ENGINES", "4"))
+MAX_GRAPHS_PER_ENGINE = int(os.environ.get("LCM_MAX_GRAPHS", "4"))
+
+
 def get_engine(unet, batch: int, height: int, width: int, device, precision: Optional[str] = None, **kw) -> Engine:
     precision = precision or unet.precision
     dev = torch.device(device)
     key = (batch, height, width, precision, dev.index if dev.index is not None else torch.cuda.current_device(),
            tuple(sorted(kw.items())))
-    eng = unet._engines.get(key)
+    cache = unet._engines
+    eng = cache.get(key)
     if eng is None:
+        while len(cache) >= max(1, MAX_ENGINES_PER_UNET):      # evict the least recently used plan + workspace
+            _, old = cache.popitem(last=False)
+            old.close()
         eng = Engine(unet, batch, height, width, precision, device=dev, **kw)
-        unet._engines[key] = eng
+        cache[key] = eng
+    else:
+        cache.move_to_end(key)
     return eng
 
 
@@ -272,7 +301,15 @@ def lcm_mix(a: torch.Tensor, b: torch.Tensor, timesteps: torch.Tensor, alphas_cu
     _require_cuda(a, "samples")
     _require_cuda(b, "noise")
     a, b = a.contiguous(), b.contiguous()
+    if timesteps.is_floating_point() or timesteps.dtype == torch.bool:
+        # the reference indexes `alphas_cumprod[timesteps]`: float indices raise there as well
+        raise IndexError("timesteps must be an integer tensor (tensors used as indices must be long, int or byte)")
+    if timesteps.numel() != a.shape[0]:
+        raise ValueError("timesteps must have one entry per sample")
     t = timesteps.to(device=a.device, dtype=torch.long).contiguous()
+    n_train = alphas_cumprod.numel()
+    if t.is_cuda:   # same failure mode as the reference's device-side index check, without a host sync
+        torch._assert_async(((t >= 0) & (t < n_train)).all())
     abar = alphas_cumprod.to(device=a.device, dtype=torch.float32).contiguous()
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):

@@ -14,6 +14,7 @@ golden vectors made from the reference be replayed on a box that does not have i
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import List, Tuple
 
 import torch
@@ -49,7 +50,7 @@ def _gn(c, strict):
     return nn.GroupNorm(group_count(c, strict), c)
 
 
-def _inverted_residual(ci: int, co: int, cfg: EfficientUNetConfig, strict: bool) -> _Named:
+def _inverted_residual(ci: int, co: int, cfg: EfficientUNetConfig, strict: bool, se_ratio=None) -> _Named:
     """Weights of one MobileNetV3-style block (reference :147-201).  Creation order
     norm1, norm2, expand, depthwise, se.fc1, se.fc2, project, time_mlp.1, [skip]."""
     ch = int(ci * cfg.expansion_ratio)
@@ -59,7 +60,7 @@ def _inverted_residual(ci: int, co: int, cfg: EfficientUNetConfig, strict: bool)
     blk.add_module("expand", _conv(ci, ch, 1, bias=False))
     blk.add_module("depthwise", _conv(ch, ch, 3, bias=False, groups=ch))
     if cfg.use_se:
-        sq = max(1, int(ch * cfg.se_ratio))
+        sq = max(1, int(ch * (cfg.se_ratio if se_ratio is None else se_ratio)))
         blk.add_module("se", _Named(fc1=_conv(ch, sq, 1, bias=True), fc2=_conv(sq, ch, 1, bias=True)))
     blk.add_module("project", _conv(ch, co, 1, bias=False))
     blk.add_module("time_mlp", _Named.indexed([(1, nn.Linear(cfg.time_embed_dim, 2 * ch))]))
@@ -130,9 +131,11 @@ class EfficientUNet(nn.Module):
                 res //= 2
 
         mid = widths[-1]
-        self.mid_block1 = _inverted_residual(mid, mid, cfg, strict)
+        # the reference builds the two mid blocks with the constructor default se_ratio=0.25, not config.se_ratio
+        # (efficient_unet.py:467-478)
+        self.mid_block1 = _inverted_residual(mid, mid, cfg, strict, se_ratio=0.25)
         self.mid_attn = _linear_attention(mid, cfg.num_attention_heads, strict)
-        self.mid_block2 = _inverted_residual(mid, mid, cfg, strict)
+        self.mid_block2 = _inverted_residual(mid, mid, cfg, strict, se_ratio=0.25)
 
         self.decoder_blocks = nn.ModuleList()
         self.upsamplers = nn.ModuleList()
@@ -153,7 +156,8 @@ class EfficientUNet(nn.Module):
         self.final_conv = _conv(widths[0], cfg.out_channels, 3, bias=True)
 
         self.precision = "bf16"
-        self._engines = {}
+        self._engines = OrderedDict()      # LRU of native plans, see engine.get_engine
+        self._weights_epoch = 0
 
     # ---- reference surface --------------------------------------------------
     def forward(self, x: torch.Tensor, timestep: torch.Tensor, return_features: bool = False):
@@ -171,6 +175,12 @@ class EfficientUNet(nn.Module):
         return {"num_params": n, "fp32_mb": n * 4 / mb, "fp16_mb": n * 2 / mb, "int8_mb": n / mb}
 
     # ---- native plumbing ----------------------------------------------------
+    def mark_weights_changed(self) -> None:
+        """Tell the native plans that parameters were modified in a way autograd's version counters do not see
+        (``param.data.copy_``, e.g. the reference's EMA ``apply_shadow`` / ``restore``, trainer.py:106-118); the next
+        call re-packs the weights.  Cheaper than :meth:`invalidate_engines` (plans and workspaces are kept)."""
+        self._weights_epoch += 1
+
     def invalidate_engines(self) -> None:
         """Drop native plans (call after mutating weights in place, e.g. EMA swap)."""
         for e in self._engines.values():

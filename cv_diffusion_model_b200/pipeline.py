@@ -27,7 +27,7 @@ class LowLightDiffusionOutput:
 class LowLightDiffusion(nn.Module):
     def __init__(self, unet: Optional[EfficientUNet] = None, scheduler: Optional[LCMScheduler] = None,
                  unet_variant: str = "small", image_size: int = 256, num_inference_steps: int = 4,
-                 condition_mode: str = "concat", groupnorm: str = "strict", precision: str = "bf16"):
+                 condition_mode: str = "concat", groupnorm: str = "strict", precision: Optional[str] = None):
         super().__init__()
         if condition_mode != "concat":
             raise ValueError('only condition_mode="concat" is supported by the B200 path '
@@ -37,7 +37,8 @@ class LowLightDiffusion(nn.Module):
         self.condition_mode = condition_mode
         self.unet = unet if unet is not None else create_efficient_unet(
             variant=unet_variant, image_size=image_size, groupnorm=groupnorm, in_channels=6)
-        self.unet.precision = precision
+        if precision is not None:          # an explicitly passed unet keeps its own precision unless told otherwise
+            self.unet.precision = precision
         self.scheduler = scheduler if scheduler is not None else LCMScheduler(
             num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
             num_inference_steps=num_inference_steps, rescale_betas_zero_snr=True)
@@ -66,9 +67,19 @@ class LowLightDiffusion(nn.Module):
             latents = torch.randn(b, 3, s, s, device=device, generator=generator)
         else:
             latents = latents.to(device=device, dtype=torch.float32).clone()
-        if noises is None and steps > 1:
-            noises = torch.stack([torch.randn_like(latents) for _ in range(steps - 1)])
         coefs = [self.scheduler.step_coefficients(t) for t in ts]
+        # "last" follows the reference's rule prev_t == 0 (lcm_scheduler.py:228), not the loop index: with
+        # num_train_timesteps // original_inference_steps == 1 the schedule ends in t = 0 and the step before it already
+        # returns x0 without drawing noise.  Such a step runs as x_prev = 1 * x0 + 0 * (zero noise).
+        early_last = [c[4] for c in coefs[:-1]]
+        if noises is None and steps > 1:
+            noises = torch.stack([torch.zeros_like(latents) if last else torch.randn_like(latents) for last in early_last])
+        if any(early_last):
+            coefs = [(c[0], c[1], 1.0, 0.0, True) if c[4] else c for c in coefs]
+            noises = noises.clone()
+            for i, last in enumerate(early_last):
+                if last:
+                    noises[i].zero_()
         eng = get_engine(self.unet, b, s, s, device)
         low = low_light.to(torch.float32).contiguous()
         res = eng.enhance(low, latents.contiguous(), noises, ts, coefs, trace=return_intermediate)

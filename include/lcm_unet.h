@@ -118,7 +118,7 @@ int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_d
  * preprocess (scripts/inference.py:111-116): uint8 RGB HWC [N][H][W][3] -> fp32 NCHW, x / 127.5 - 1 (fp32 division, then
  * fp32 subtraction: bit-identical to the reference's numpy expression).
  * postprocess (scripts/inference.py:121-127): fp32 NCHW -> uint8 RGB HWC, (y + 1) * 127.5, clip to [0, 255], truncate.
- * Resizing (cv2.resize) stays with the caller. */
+ * Resizing (cv2.resize, scripts/inference.py:109,130) is lcm_image_resize_u8 below. */
 int lcm_image_preprocess_u8(const uint8_t* hwc_dev, float* nchw_dev, int batch, int height, int width, void* stream);
 int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch, int height, int width, void* stream);
 /* cv2.resize(img, (dst_w, dst_h)) with the default INTER_LINEAR on 8-bit 3-channel images (scripts/inference.py:109,130):
