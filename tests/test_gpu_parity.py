@@ -129,7 +129,8 @@ def test_enhance_vs_reference_golden(golden, weight_digests, tag, size, b, steps
     bf16 note: with random-init weights the sampler is chaotic (x0 = (x_t - ..)/sqrt(abar_t) amplifies eps
     errors 5-12x per step).  The reference's OWN torch-autocast-bf16 run scores 33.3 dB on the 64x64 4-step
     case and -0.1 dB on the 32x32 8-step case (calibrated in the build container), so the free-running bf16
-    gate is applied to the 4-step case only; the 8-step case is checked step by step below."""
+    gate (33 dB) is applied to the 4-step case only; the ill-conditioned 32x32 8-step case is checked step by step
+    below and a well-conditioned 8-step loop in test_enhance_8step_free_running_well_conditioned."""
     pipe, low, lat0, noises = _golden_pipe(golden, weight_digests, tag, size, steps, precision)
     if precision == "bf16" and steps == 8:
         pytest.skip("free-running bf16 parity is not meaningful at 8 steps (see docstring); teacher-forced test below")
@@ -144,8 +145,10 @@ def test_enhance_vs_reference_golden(golden, weight_digests, tag, size, b, steps
         assert (pre - want_pre).abs().max().item() <= 5e-3
         assert (res.enhanced.cpu() - want).abs().max().item() <= 5e-3
     else:
-        assert psnr(pre, want_pre, 2.0) >= 30.0
-        assert psnr(res.enhanced.cpu(), want, 2.0) >= 30.0
+        # measured 34.5 dB (bitwise reproducible); the reference under torch's own bf16 autocast: 33.3 dB
+        # (profiles/r02_loop_parity_bf16_vs_autocast.txt)
+        assert psnr(pre, want_pre, 2.0) >= 33.0
+        assert psnr(res.enhanced.cpu(), want, 2.0) >= 33.0
 
 
 @pytest.mark.parametrize("tag,size,b,steps", [("small64", 64, 2, 4), ("small32_8step", 32, 1, 8)])
@@ -235,7 +238,7 @@ def test_production_size_reproducible_and_parity():
     t0 = torch.full((2,), int(pipe.scheduler._host_timesteps[0]), dtype=torch.long)
     eps = pipe.unet(torch.cat([lat0, low], dim=1).cuda(), t0.cuda()).cpu()     # first step's noise prediction
     assert rel_rms(eps, trace[0][0]) <= 0.03
-    assert psnr(res.intermediate[-1].cpu(), trace[-1][1], 2.0) >= 30.0
+    assert psnr(res.intermediate[-1].cpu(), trace[-1][1], 2.0) >= 33.0
 
 
 @pytest.mark.parametrize("variant,size", [("base", 256), ("large", 128)])
