@@ -94,6 +94,9 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 
 // ---- weight packing ---------------------------------------------------------------------------------
 enum PackKind : int {
+  PACK_MAT_T = 6,    // src [Cc][src_ld] -> logical W(r, off + c) = src[c][src_col0 + r]   (transposed copy: dgrad weights)
+  PACK_CONV3_T = 7,  // src [Co][Ci][3][3] -> logical W(ci, off + (8 - tap)*tap_stride + co): the transposed conv as a
+                     // conv over dY with flipped taps and swapped channel roles (R = Ci rows, Cc = Co)
   PACK_COPY = 0,     // dst_f32[i] = src[i]
   PACK_MAT = 1,      // src [R][Cc] -> logical W(r, off + c)
   PACK_CONV3 = 2,    // src [Co][Ci][3][3] -> logical W(co, off + tap*Ci + ci)
@@ -151,5 +154,59 @@ int gemm_wide_read_profile(long long* host8);   // LCM_W_DEBUG & 16
 int gemm_expand_read_timeline(long long* host, int n);   // debug: LCM_X_TIMELINE=1
 int gemm_tc_pick_block_n(int Nc);
 int gemm_tc_read_timeline(long long* host, int n);   // debug: per-tile clock stamps of block 0 (LCM_TC_DEBUG & 64)
+
+// =====================================================================================================
+// Training step (BASELINE config 5): backward of every op above + loss + optimizer (train_kernels.cu).
+// Element types are run-time codes: one backward op touches the residual stream (bf16), hidden tensors (fp16) and
+// gradients (bf16) on the tensor-core plan, fp32 everywhere on the fp32 plan.
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// g <- g * [0 < a x + b < 6] (mode 1, in place) and T1 += sum_p g, T2 += sum_p g x per (image, channel) (mode 0: no write)
+void launch_bwd_mask_reduce(void* g, int dtg, int ldg, int goff, const void* x, int dtx, int ldx, int xoff, const float2* coef,
+                            int coef_ld, double* t12, int t_ld, int N, int P, int Cs, int mode, cudaStream_t st);
+// dst (=|+=) A g + B x + C (+ r) with (A, B, C) = coef4[n][coff + c]
+void launch_bwd_affine3(const void* g, int dtg, int ldg, int goff, const void* x, int dtx, int ldx, int xoff,
+                        const float4* coef4, int coef_ld, int coff, const void* r, int dtr, int ldr, int roff, void* dst,
+                        int dtd, int ldd, int doff, int accumulate, int N, int P, int Cs, cudaStream_t st);
+void launch_bwd_add(const void* src, int dts, int lds, int soff, void* dst, int dtd, int ldd, int doff, int accumulate,
+                    long long rows, int Cs, cudaStream_t st);
+// GroupNorm (+FiLM) backward finalise: (T1, T2) + forward statistics -> (A, B, C), d gamma, d beta, d FiLM rows
+void launch_gn_bwd_coef(const double* t12, const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
+                        const float* gamma, const float* beta, const float* film, float* dfilm, int film_ld, float4* coef4,
+                        float* dgamma, float* dbeta, int N, cudaStream_t st);
+int launch_se_bwd_vec(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2, const float2* gate,
+                      const double* t12, float2* coef_se, float* v_pm, float* v_z, float* v_ds2, float* v_dz1, int N, int C,
+                      int SQ, cudaStream_t st);
+void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* dW, float* dbias, int N, int R, int Cc,
+                      cudaStream_t st);
+void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
+                       void* du, double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st);
+void launch_wgrad_1x1(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
+                      int num_sms, cudaStream_t st);
+void launch_wgrad_conv3(const void* in, int dti, const void* dY, int dty, float* dW, float* dbias, int N, int Hin, int Win, int Ci,
+                        int Co, int mode, int num_sms, cudaStream_t st);
+void launch_upsample2x_any(const void* in, void* out, int dt, int N, int H, int W, int C, cudaStream_t st);
+void launch_upsample2x_bwd(const void* dout, void* din, int dt, int N, int H, int W, int C, int accumulate, cudaStream_t st);
+void launch_attn_bwd(const void* qkv, int dtq, const double* state, const void* dO, int dtg, void* dqkv, double* dstate, int N, int P,
+                     int heads, cudaStream_t st);
+void launch_film_bwd_input(const float* dfilm, const float* W, float* dst, int N, int rows, int ted, cudaStream_t st);
+void launch_time_mlp_bwd(const long long* t_dev, long long t_scalar, int N, int base, int ted, const float* w1, const float* b1,
+                         const float* w3, const float* b3, const float* dst, float* dw1, float* db1, float* dw3, float* db3,
+                         cudaStream_t st);
+void launch_loss(const float* eps, const float* target, long long numel, int type, double* out, cudaStream_t st);
+int launch_final_conv_bwd(const void* h, int dth, const float2* coef, const float* w, const float* eps, const float* target,
+                          int loss_type, float gscale, const float* gscale_dev, void* dpre, int dtg, double* t12, float* dW,
+                          float* dbias, int N, int H, int W, int Ci, int Co, int num_sms, cudaStream_t st);
+int launch_init_conv_wgrad(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const void* dY, int dtg,
+                           float* dW, float* dbias, int N, int H, int W, int Co, int num_sms, cudaStream_t st);
+void launch_sumsq(const float* g, long long n, double* out, cudaStream_t st);
+void launch_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long long n, float lr, float beta1, float beta2,
+                      float eps, float wd, int step, float ema_decay, const double* sumsq, float grad_div, float max_norm,
+                      cudaStream_t st);
+// transposed dense 3x3 conv on the CUDA cores (input gradient): dX [N][Hin][Win][Ci] from dY [N][Hout][Wout][Co];
+// Wt row-major [Ci][9*Co] packed with PACK_CONV3_T.  mode CONV_S1 or CONV_S2 (forward stride).
+void launch_conv3x3_dgrad_simt(const void* dY, const void* Wt, void* dX, int N, int Hin, int Win, int Ci, int Co, int mode,
+                               int bf16act, cudaStream_t st);
 
 }  // namespace lcm

@@ -81,6 +81,30 @@ struct LoaderConv3 {
   }
 };
 
+// Transposed conv (input gradient) as an implicit GEMM over dY: row m = input pixel (n, yi, xi), k = tap' * Co + co with
+// FLIPPED taps (weights packed by PACK_CONV3_T): yy = yi + ky' - 1 is the position in stride-1 output coordinates; for the
+// stride-2 forward only even yy < 2 Hout hit an output pixel (yo = yy / 2).
+template <typename T>
+struct LoaderConv3T {
+  const T* dy;
+  int Hin, Win, Hout, Wout, Co, mode;
+  __device__ __forceinline__ void load4(long long m, int k, float (&v)[4]) const {
+    const int tap = k / Co, co = k - tap * Co;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int x = (int)(m % Win);
+    const long long q = m / Win;
+    const int y = (int)(q % Hin);
+    const long long n = q / Hin;
+    int yy = y + ky - 1, xx = x + kx - 1;
+    bool ok = yy >= 0 && xx >= 0;
+    if (mode == CONV_S2) { ok = ok && !(yy & 1) && !(xx & 1); yy >>= 1; xx >>= 1; }
+    if (!ok || yy >= Hout || xx >= Wout) { v[0] = v[1] = v[2] = v[3] = 0.f; return; }
+    const T* p = dy + ((n * Hout + yy) * (long long)Wout + xx) * Co + co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = to_f<T>(p[j]);
+  }
+};
+
 // 64x64 output tile, BK = 16, 256 threads, 4x4 outputs per thread.  W row-major [Nc][Ktot].
 template <typename T, typename Loader>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(Loader ld, const T* __restrict__ W, T* __restrict__ out,
@@ -192,6 +216,22 @@ void launch_conv3x3_simt(const void* in, const void* Wt, const float* bias, void
     LoaderConv3<float> ld{(const float*)in, Hin, Win, Hout, Wout, Ci, mode};
     gemm_simt_kernel<float, LoaderConv3<float>><<<grid, 256, 0, st>>>(ld, (const float*)Wt, (float*)out, bias, stats,
                                                                     M, Hout * Wout, Co, 9 * Ci);
+  }
+}
+
+void launch_conv3x3_dgrad_simt(const void* dY, const void* Wt, void* dX, int N, int Hin, int Win, int Ci, int Co, int mode,
+                               int bf16act, cudaStream_t st) {
+  const int Hout = mode == CONV_S2 ? Hin / 2 : Hin, Wout = mode == CONV_S2 ? Win / 2 : Win;
+  const long long M = (long long)N * Hin * Win;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((Ci + 63) / 64));
+  if (bf16act) {
+    LoaderConv3T<bf16> ld{(const bf16*)dY, Hin, Win, Hout, Wout, Co, mode};
+    gemm_simt_kernel<bf16, LoaderConv3T<bf16>><<<grid, 256, 0, st>>>(ld, (const bf16*)Wt, (bf16*)dX, nullptr, nullptr, M,
+                                                                   Hin * Win, Ci, 9 * Co);
+  } else {
+    LoaderConv3T<float> ld{(const float*)dY, Hin, Win, Hout, Wout, Co, mode};
+    gemm_simt_kernel<float, LoaderConv3T<float>><<<grid, 256, 0, st>>>(ld, (const float*)Wt, (float*)dX, nullptr, nullptr, M,
+                                                                     Hin * Win, Ci, 9 * Co);
   }
 }
 

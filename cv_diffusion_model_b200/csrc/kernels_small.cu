@@ -482,6 +482,20 @@ __global__ void pack_kernel(PackJob j, const float* __restrict__ src, long long 
         put_any(j, r, j.off + c, v);
         break;
       }
+      case PACK_MAT_T: {   // logical (r, c) = src[c][src_col0 + r]
+        int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
+        const float v = src[(size_t)c * j.src_ld + j.src_col0 + r];
+        put_any(j, r, j.off + c, v);
+        break;
+      }
+      case PACK_CONV3_T: {  // src [Co][Ci][3][3]; R = Ci rows, Cc = Co
+        int tap = (int)(i % 9);
+        long long q = i / 9;
+        int ci = (int)(q % j.R), co = (int)(q / j.R);
+        int k = j.off + (8 - tap) * j.tap_stride + co;
+        put_any(j, ci, k, src[i]);
+        break;
+      }
       case PACK_IDENTITY: {
         int r = (int)(i / j.Cc), c = (int)(i % j.Cc);
         float v = (r == c) ? 1.f : 0.f;
@@ -516,8 +530,9 @@ void launch_pack(const PackJob& job, const float* src, cudaStream_t st) {
   long long total = 0;
   switch (job.kind) {
     case PACK_COPY: total = (long long)job.R * job.Cc; break;
-    case PACK_MAT: case PACK_IDENTITY: total = (long long)job.R * job.Cc; break;
+    case PACK_MAT: case PACK_IDENTITY: case PACK_MAT_T: total = (long long)job.R * job.Cc; break;
     case PACK_CONV3: case PACK_CONV3_KN: total = (long long)job.R * job.Ci * 9; break;
+    case PACK_CONV3_T: total = (long long)job.R * job.Cc * 9; break;
     case PACK_DW: total = (long long)job.R * 9; break;
   }
   if (total == 0) return;

@@ -96,11 +96,17 @@ struct Tensor {
   bool f16 = false;      // stored as fp16 (hidden tensors of a block on the tcgen05 path), else the plan's type
   size_t stats_off = 0;  // byte offset of double[N][C][2] in region Z
   int refs = 0;
+  // training plans: gradient buffer in region G (allocated by the first backward op that writes it)
+  bool g_alloc = false, g_written = false;
+  size_t g_off = 0, g_bytes = 0;
+  std::string tap;
 };
 typedef std::shared_ptr<Tensor> TensorP;
 
 struct RunCtx {
   char* z; char* f; char* a;   // region bases
+  char* zb; char* fb; char* g; float* wg;   // training: zeroed backward scratch, backward coefficient tables, gradients, flat weight gradients
+  const float* target; int loss_type; float gscale; const float* gscale_dev;   // training: loss definition
   const float* xa; int ca; long long sa;
   const float* xb; int cb; long long sb;
   const long long* t_dev; long long t_scalar;
@@ -190,6 +196,22 @@ struct lcm_plan {
   size_t film_f_off = 0, silu_f_off = 0;
 
   std::vector<Op> ops;
+  // ---- training (LCM_FLAG_TRAIN) -------------------------------------------------------------------
+  bool train = false;
+  int dt_act = 0, dt_hid = 0, dt_grad = 0;     // DType of the residual stream / a block's hidden tensors / gradients
+  size_t gsz = 4;                              // gradient element size
+  PoolAlloc gpool;                             // region G
+  size_t zb_bytes = 0, fb_bytes = 0;
+  size_t wg_elems = 0;                         // flat fp32 weight-gradient buffer (state_dict layouts, weight_order order)
+  std::map<std::string, size_t> wgrad_off;     // element offset of every weight's gradient
+  std::map<std::string, int> wgrad_last_op;    // index of the last backward op that writes it (bucketed all-reduce)
+  std::vector<Op> bwd_ops;
+  size_t dfilm_fb_off = 0, dst_zb_off = 0;     // d FiLM table [N][film_rows] (FB), d silu(t_emb) [N][ted] (ZB)
+  size_t zero_bias_off = 0;
+  size_t zb_off_ws = 0, fb_off_ws = 0, g_off_ws = 0, wg_off_ws = 0;   // region offsets inside the workspace
+  std::map<std::string, TensorP> gtap_map;
+  size_t zballoc(size_t bytes) { size_t o = zb_bytes; zb_bytes += align_up(bytes, 256); return o; }
+  size_t fballoc(size_t bytes) { size_t o = fb_bytes; fb_bytes += align_up(bytes, 256); return o; }
   std::map<std::string, TensorP> tap_map;
   std::vector<std::string> tap_order;
   double total_bytes = 0, total_flops = 0;
@@ -209,6 +231,7 @@ struct lcm_plan {
     t->bytes = (size_t)N * h * w * C * esz;
     t->off = pool.alloc(t->bytes);
     t->refs = 1;
+    t->tap = tap;
     if (stats) t->stats_off = zalloc((size_t)N * C * 2 * sizeof(double));
     if (taps && !tap.empty()) { tap_map[tap] = t; tap_order.push_back(tap); }
     return t;
@@ -216,7 +239,12 @@ struct lcm_plan {
   void release(const TensorP& t) { if (--t->refs == 0) pool.release(t->off, t->bytes); }
 
   void add_weight(const std::string& name, int64_t numel, const PackJob& job) {
-    if (weights.find(name) == weights.end()) { weight_order.push_back(name); weights[name].numel = numel; }
+    if (weights.find(name) == weights.end()) {
+      weight_order.push_back(name);
+      weights[name].numel = numel;
+      wgrad_off[name] = wg_elems;
+      wg_elems += (size_t)(numel + 3) / 4 * 4;    // 16-byte aligned slices
+    }
     weights[name].jobs.push_back(job);
   }
   size_t add_copy(const std::string& name, int64_t numel) {   // verbatim fp32 copy; returns weight-arena offset
@@ -253,6 +281,90 @@ struct Builder {
   struct FilmBlock { std::string wname; int row0, rows; };
   std::vector<FilmBlock> film_blocks;
   explicit Builder(lcm_plan* plan) : p(plan), N(plan->N) {}
+
+  // ---- training tape -------------------------------------------------------------------------------
+  // Every forward builder registers a closure that, run in REVERSE registration order once the forward plan is
+  // complete, emits the backward ops of its forward op and allocates / releases gradient buffers in region G with the
+  // same first-fit pool as the activations (lifetimes follow the backward execution order).
+  std::vector<std::function<void()>> tape;
+  void on_backward(std::function<void()> fn) { if (p->train) tape.push_back(std::move(fn)); }
+
+  void pushb(const std::string& name, const char* kernel, const std::vector<std::string>& writes, RunFn fn) {
+    Op o; o.name = name; o.kernel = kernel; o.run = std::move(fn);
+    for (const std::string& w : writes) p->wgrad_last_op[w] = (int)p->bwd_ops.size();
+    p->bwd_ops.push_back(std::move(o));
+  }
+  size_t galloc(size_t bytes) { return p->gpool.alloc(bytes); }
+  void gfree(size_t off, size_t bytes) { p->gpool.release(off, bytes); }
+  // gradient of a forward tensor: the first writer stores, later writers accumulate
+  struct GradW { size_t off; int accumulate; };
+  GradW grad_w(const TensorP& t) {
+    if (!t->g_alloc) {
+      t->g_bytes = (size_t)N * t->H * t->W * t->C * p->gsz;
+      t->g_off = galloc(t->g_bytes);
+      t->g_alloc = true;
+      if (p->taps && !t->tap.empty()) p->gtap_map[t->tap] = t;
+    }
+    GradW g{t->g_off, t->g_written ? 1 : 0};
+    t->g_written = true;
+    return g;
+  }
+  size_t grad_r(const TensorP& t) { return t->g_off; }   // valid when has_grad(t)
+  bool has_grad(const TensorP& t) const { return t->g_alloc && t->g_written; }
+  void grad_done(const TensorP& t) { if (t->g_alloc) gfree(t->g_off, t->g_bytes); }
+  size_t wg(const std::string& name) const { return p->wgrad_off.at(name); }
+
+  // dgrad weights of a 1x1 conv: W'[k_in][n_out] = W[n_out][k_in]  (logical [Nc = rows of W'][K = cols])
+  struct DgradW { size_t off; int Nc, K, Kpad, block_n; };
+  DgradW make_dgrad_w(const std::string& wname, int64_t numel, int rows_out /*Nc'*/, int K /*cols'*/, int src_ld, int src_col0) {
+    DgradW d{};
+    d.Nc = rows_out; d.K = K; d.Kpad = (K + 63) / 64 * 64;
+    PackJob j{};
+    j.kind = PACK_MAT_T;
+    j.R = rows_out; j.Cc = K; j.src_ld = src_ld; j.src_col0 = src_col0;
+    if (p->tc) {
+      d.block_n = gemm_tc_pick_block_n(rows_out);
+      d.off = p->walloc((size_t)rows_out * d.Kpad * sizeof(bf16));
+      j.layout = WL_UMMA; j.bf16 = 1; j.ld = d.Kpad; j.block_n = d.block_n;
+    } else {
+      d.off = p->walloc((size_t)rows_out * K * p->esz);
+      j.layout = WL_ROWMAJOR; j.bf16 = p->bf16 ? 1 : 0; j.ld = K;
+    }
+    j.dst = (void*)d.off;
+    p->add_weight(wname, numel, j);
+    return d;
+  }
+  // out[M][Nc'] = dY[M][K] . W'^T  (input gradient of a 1x1 conv); all buffers in region G
+  void dgrad_gemm(const std::string& name, size_t dy_off, const DgradW& w, size_t out_off, int P) {
+    lcm_plan* pl = p; const int n = N;
+    pushb(name, pl->tc ? "gemm_tc" : "gemm_simt", {}, [=](const RunCtx& c, cudaStream_t st) {
+      GemmParams gp{};
+      gp.nseg = 1;
+      gp.seg[0].A = c.g + dy_off; gp.seg[0].K = w.K; gp.seg[0].ld = w.K; gp.seg[0].mode = XF_NONE;
+      gp.Ktot = w.K; gp.W = pl->wbase + w.off; gp.out = c.g + out_off; gp.stats = nullptr;
+      gp.P = P; gp.M = (long long)n * P; gp.Nc = w.Nc;
+      if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
+      else launch_gemm_simt(gp, pl->bf16, st);
+    });
+  }
+  // GroupNorm backward finalise for a view x (one or two tensors): (T1, T2) in ZB -> coef4 in FB, d gamma / d beta
+  struct GnInfo { size_t coef, g_off, b_off; int G; double count; std::string wname; };
+  size_t gn_backward(const std::string& name, const View& x, const GnInfo& gi, size_t t12, int film_row0) {
+    const int C = x.C();
+    const size_t coef4 = p->fballoc((size_t)N * C * sizeof(float4));
+    const size_t s0 = x.part[0]->stats_off; const int C0 = x.part[0]->C;
+    const size_t s1 = x.n > 1 ? x.part[1]->stats_off : 0; const int C1 = x.n > 1 ? x.part[1]->C : 0;
+    lcm_plan* pl = p; const int n = N;
+    const size_t dg = wg(gi.wname + ".weight"), db = wg(gi.wname + ".bias");
+    pushb(name, "gn_bwd_coef", {gi.wname + ".weight", gi.wname + ".bias"}, [=](const RunCtx& c, cudaStream_t st) {
+      const float* film = film_row0 >= 0 ? (const float*)(c.f + pl->film_f_off) + film_row0 : nullptr;
+      float* dfilm = film_row0 >= 0 ? (float*)(c.fb + pl->dfilm_fb_off) + film_row0 : nullptr;
+      launch_gn_bwd_coef((const double*)(c.zb + t12), (const double*)(c.z + s0), C0, C1 ? (const double*)(c.z + s1) : nullptr, C1,
+                         gi.G, gi.count, pl->wf(gi.g_off), pl->wf(gi.b_off), film, dfilm, pl->film_rows,
+                         (float4*)(c.fb + coef4), c.wg + dg, c.wg + db, n, st);
+    });
+    return coef4;
+  }
 
   void push(const std::string& name, const char* kernel, double bytes, double flops, RunFn fn) {
     Op o; o.name = name; o.kernel = kernel; o.bytes = bytes; o.flops = flops; o.run = std::move(fn);
@@ -292,7 +404,7 @@ struct Builder {
   }
 
   // GroupNorm finalise -> coef buffer [N][C] in region F
-  size_t gn_coef(const std::string& name, const View& x, const std::string& wname, int film_row0) {
+  GnInfo gn_coef(const std::string& name, const View& x, const std::string& wname, int film_row0) {
     const int C = x.C(), G = p->groups(C);
     const size_t coef = p->falloc((size_t)N * C * sizeof(float2));
     const size_t g_off = p->add_copy(wname + ".weight", C), b_off = p->add_copy(wname + ".bias", C);
@@ -305,7 +417,7 @@ struct Builder {
       launch_gn_coef((const double*)(c.z + s0), C0, C1 ? (const double*)(c.z + s1) : nullptr, C1, G, count,
                      pl->wf(g_off), pl->wf(b_off), film, pl->film_rows, (float2*)(c.f + coef), n, st);
     });
-    return coef;
+    return GnInfo{coef, g_off, b_off, G, count, wname};
   }
 
   struct SegSpec { TensorP t; size_t coef; int coef_ld, coef_off, mode; };
@@ -358,7 +470,8 @@ struct Builder {
     film_blocks.push_back({name + ".time_mlp.1", row0, 2 * Ch});
 
     // norm1 -> ReLU6 -> expand (:207-209)
-    const size_t coef1 = gn_coef(name + ".norm1", x, name + ".norm1", -1);
+    const GnInfo gn1 = gn_coef(name + ".norm1", x, name + ".norm1", -1);
+    const size_t coef1 = gn1.coef;
     // tcgen05 path: both hidden tensors are fp16 (dwconv_stream.cu explains why)
     const bool hid16 = p->tc;
     TensorP h1 = p->new_tensor(Ch, h, w, true, name + ".expand", hid16);
@@ -377,7 +490,8 @@ struct Builder {
       if (we.expand) p->ops.back().launches = 2;   // GEMM + statistics finalisation
     }
     // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
-    const size_t coef2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
+    const GnInfo gn2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
+    const size_t coef2 = gn2.coef;
     TensorP h2 = p->new_tensor(Ch, h, w, false, name + ".depthwise", hid16);
     const size_t pool = p->zalloc((size_t)N * Ch * sizeof(double));
     const size_t dw_off = p->walloc((size_t)9 * Ch * sizeof(float));
@@ -429,9 +543,181 @@ struct Builder {
       const double flops = 2.0 * N * P * Ch * Co + (Ci != Co ? 2.0 * N * P * Ci * Co : 0.0);
       gemm(name + ".project", segs, wp, out, true, bytes, flops);
     }
+    if (p->train) block_backward(name, x, h1, h2, out, gn1, gn2, gate, pool, dw_off, w1, b1, w2, SQ, row0, Co);
     p->release(h2);
     for (int i = 0; i < x.n; ++i) p->release(x.part[i]);
     return out;
+  }
+
+  // ---- backward of one InvertedResidualBlock (reverse of efficient_unet.py:203-236) -----------------------
+  //   dq  = dY Wp                      d(gate * h2)                 [project dgrad]
+  //   dWp = dY^T (gate h2), dWskip = dY^T x                         [wgrad]
+  //   dgate = sum_p dq h2 -> SE FC backward -> (gate, dpool / P)    [mask_reduce, se_bwd_vec, outer_sum x2]
+  //   du  = dwconv^T(gate dq + dpool / P) [0 < u < 6], dWdw, T1/T2  [dwconv_bwd]
+  //   (A, B, C) of norm2 + FiLM, d gamma2 / d beta2 / d FiLM        [gn_bwd_coef]
+  //   dh1 = A du + B h1 + C                                         [affine3, in place]
+  //   dr  = dh1 We ; dWe = dh1^T relu6(a1 x + b1)                   [expand dgrad, wgrad]
+  //   dpre = dr [0 < a1 x + b1 < 6], T1/T2                          [mask_reduce mode 1, in place]
+  //   (A, B, C) of norm1                                            [gn_bwd_coef]
+  //   dx (+)= A dpre + B x + C + (dY | dY Wskip)                    [affine3 per input part]
+  void block_backward(const std::string& name, const View& x, const TensorP& h1, const TensorP& h2, const TensorP& out,
+                      const GnInfo& gn1, const GnInfo& gn2, size_t gate, size_t pool, size_t dw_off, size_t w1, size_t b1,
+                      size_t w2, int SQ, int row0, int Co) {
+    const int Ci = x.C(), Ch = h1->C;
+    const int h = h1->H, w = h1->W, P = h * w;
+    const int n = N;
+    lcm_plan* pl = p;
+    // transposed weight copies for the input-gradient GEMMs (packed with the forward weights on every upload)
+    const DgradW wpT = make_dgrad_w(name + ".project.weight", (int64_t)Co * Ch, Ch, Co, Ch, 0);     // [Ch][Co]
+    const DgradW weT = make_dgrad_w(name + ".expand.weight", (int64_t)Ch * Ci, Ci, Ch, Ci, 0);      // [Ci][Ch]
+    DgradW wsT{};
+    const bool has_skip = Ci != Co;
+    if (has_skip) wsT = make_dgrad_w(name + ".skip.weight", (int64_t)Co * Ci, Ci, Co, Ci, 0);       // [Ci][Co]
+    View xv = x;
+    on_backward([=]() {
+      const size_t gsz = pl->gsz;
+      const size_t M = (size_t)n * P;
+      const int dta = pl->dt_act, dth = pl->dt_hid, dtg = pl->dt_grad;
+      const size_t dY = grad_r(out);
+      // 1. project dgrad
+      const size_t dq = galloc(M * Ch * gsz);
+      dgrad_gemm(name + ".project.dgrad", dY, wpT, dq, P);
+      // 2. project (+ skip) wgrad
+      {
+        std::vector<std::string> writes{name + ".project.weight"};
+        if (has_skip) writes.push_back(name + ".skip.weight");
+        const size_t gp_w = wg(name + ".project.weight"), gs_w = has_skip ? wg(name + ".skip.weight") : 0;
+        pushb(name + ".project.wgrad", "wgrad_simt", writes, [=](const RunCtx& c, cudaStream_t st) {
+          GemmParams gp{};
+          int seg_dt[LCM_MAX_SEGS] = {0, 0, 0, 0};
+          float* dst[LCM_MAX_SEGS] = {nullptr, nullptr, nullptr, nullptr};
+          int dst_ld[LCM_MAX_SEGS] = {0, 0, 0, 0};
+          gp.nseg = 1 + xv.n;
+          gp.seg[0].A = c.a + h2->off; gp.seg[0].K = Ch; gp.seg[0].ld = Ch; gp.seg[0].mode = XF_SCALE;
+          gp.seg[0].coef = (const float2*)(c.f + gate); gp.seg[0].coef_ld = Ch; gp.seg[0].coef_off = 0;
+          seg_dt[0] = dth; dst[0] = c.wg + gp_w; dst_ld[0] = Ch;
+          int col = 0;
+          for (int i = 0; i < xv.n; ++i) {
+            gp.seg[1 + i].A = c.a + xv.part[i]->off; gp.seg[1 + i].K = xv.part[i]->C; gp.seg[1 + i].ld = xv.part[i]->C;
+            gp.seg[1 + i].mode = XF_NONE;
+            seg_dt[1 + i] = dta;
+            dst[1 + i] = has_skip ? c.wg + gs_w + col : nullptr;   // identity residual: no weight
+            dst_ld[1 + i] = Ci;
+            col += xv.part[i]->C;
+          }
+          gp.Ktot = Ch + Ci; gp.P = P; gp.M = (long long)n * P; gp.Nc = Co;
+          launch_wgrad_1x1(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st);
+        });
+      }
+      // 3. residual path: identity (r = dY) or skip conv (r = dY Wskip)
+      size_t dxres = 0;
+      if (has_skip) {
+        dxres = galloc(M * Ci * gsz);
+        dgrad_gemm(name + ".skip.dgrad", dY, wsT, dxres, P);
+      }
+      // 4. SE backward
+      const size_t t12se = pl->zballoc((size_t)n * Ch * 2 * sizeof(double));
+      pushb(name + ".se.dgate", "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
+        launch_bwd_mask_reduce(c.g + dq, dtg, Ch, 0, c.a + h2->off, dth, Ch, 0, nullptr, 0, (double*)(c.zb + t12se), Ch, n, P, Ch, 0, st);
+      });
+      const size_t coef_se = pl->fballoc((size_t)n * Ch * sizeof(float2));
+      const size_t v_pm = pl->fballoc((size_t)n * Ch * 4), v_ds2 = pl->fballoc((size_t)n * Ch * 4);
+      const size_t v_z = pl->fballoc((size_t)n * SQ * 4), v_dz1 = pl->fballoc((size_t)n * SQ * 4);
+      pushb(name + ".se.bwd", "se_bwd_vec", {}, [=](const RunCtx& c, cudaStream_t st) {
+        if (launch_se_bwd_vec((const double*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2),
+                              (const float2*)(c.f + gate), (const double*)(c.zb + t12se), (float2*)(c.fb + coef_se),
+                              (float*)(c.fb + v_pm), (float*)(c.fb + v_z), (float*)(c.fb + v_ds2), (float*)(c.fb + v_dz1), n, Ch, SQ, st))
+          *c.launch_err = 1;
+      });
+      {
+        const size_t g_w1 = wg(name + ".se.fc1.weight"), g_b1 = wg(name + ".se.fc1.bias");
+        const size_t g_w2 = wg(name + ".se.fc2.weight"), g_b2 = wg(name + ".se.fc2.bias");
+        pushb(name + ".se.wgrad", "outer_sum",
+              {name + ".se.fc1.weight", name + ".se.fc1.bias", name + ".se.fc2.weight", name + ".se.fc2.bias"},
+              [=](const RunCtx& c, cudaStream_t st) {
+                launch_outer_sum((const float*)(c.fb + v_ds2), Ch, (const float*)(c.fb + v_z), SQ, c.wg + g_w2, c.wg + g_b2, n, Ch, SQ, st);
+                launch_outer_sum((const float*)(c.fb + v_dz1), SQ, (const float*)(c.fb + v_pm), Ch, c.wg + g_w1, c.wg + g_b1, n, SQ, Ch, st);
+              });
+        p->bwd_ops.back().launches = 2;
+      }
+      // 5. depthwise backward (+ SE scale prologue, ReLU6 backward, norm2 reductions)
+      const size_t du = galloc(M * Ch * gsz);
+      const size_t t12h = pl->zballoc((size_t)n * Ch * 2 * sizeof(double));
+      {
+        const size_t g_dw = wg(name + ".depthwise.weight");
+        pushb(name + ".depthwise.bwd", "dwconv_bwd", {name + ".depthwise.weight"}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_dwconv_bwd(c.g + dq, dtg, (const float2*)(c.fb + coef_se), c.a + h1->off, dth, (const float2*)(c.f + gn2.coef),
+                            pl->wf(dw_off), c.g + du, (double*)(c.zb + t12h), c.wg + g_dw, n, h, w, Ch, pl->num_sms, st);
+        });
+      }
+      gfree(dq, M * Ch * gsz);
+      // 6.-7. norm2 + FiLM backward, dh1 in place
+      const size_t coef4h = gn_backward(name + ".norm2.bwd", View::of(h1), gn2, t12h, row0);
+      pushb(name + ".norm2.apply", "bwd_affine3", {}, [=](const RunCtx& c, cudaStream_t st) {
+        launch_bwd_affine3(c.g + du, dtg, Ch, 0, c.a + h1->off, dth, Ch, 0, (const float4*)(c.fb + coef4h), Ch, 0, nullptr, 0, 0, 0,
+                           c.g + du, dtg, Ch, 0, 0, n, P, Ch, st);
+      });
+      // 8. expand dgrad
+      const size_t dr = galloc(M * Ci * gsz);
+      dgrad_gemm(name + ".expand.dgrad", du, weT, dr, P);
+      // 9. expand wgrad
+      {
+        const size_t g_we = wg(name + ".expand.weight");
+        pushb(name + ".expand.wgrad", "wgrad_simt", {name + ".expand.weight"}, [=](const RunCtx& c, cudaStream_t st) {
+          GemmParams gp{};
+          int seg_dt[LCM_MAX_SEGS] = {0, 0, 0, 0};
+          float* dst[LCM_MAX_SEGS] = {nullptr, nullptr, nullptr, nullptr};
+          int dst_ld[LCM_MAX_SEGS] = {0, 0, 0, 0};
+          gp.nseg = xv.n;
+          int col = 0;
+          for (int i = 0; i < xv.n; ++i) {
+            gp.seg[i].A = c.a + xv.part[i]->off; gp.seg[i].K = xv.part[i]->C; gp.seg[i].ld = xv.part[i]->C;
+            gp.seg[i].mode = XF_AFFINE_RELU6;
+            gp.seg[i].coef = (const float2*)(c.f + gn1.coef); gp.seg[i].coef_ld = Ci; gp.seg[i].coef_off = col;
+            seg_dt[i] = dta; dst[i] = c.wg + g_we + col; dst_ld[i] = Ci;
+            col += xv.part[i]->C;
+          }
+          gp.Ktot = Ci; gp.P = P; gp.M = (long long)n * P; gp.Nc = Ch;
+          launch_wgrad_1x1(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st);
+        });
+      }
+      gfree(du, M * Ch * gsz);
+      // 10. ReLU6 backward + norm1 reductions, per input part
+      const size_t t12x = pl->zballoc((size_t)n * Ci * 2 * sizeof(double));
+      {
+        int col = 0;
+        for (int i = 0; i < xv.n; ++i) {
+          const TensorP part = xv.part[i];
+          const int c0 = col;
+          pushb(name + ".norm1.mask" + (xv.n > 1 ? std::to_string(i) : ""), "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
+            launch_bwd_mask_reduce(c.g + dr, dtg, Ci, c0, c.a + part->off, dta, part->C, 0, (const float2*)(c.f + gn1.coef), Ci,
+                                   (double*)(c.zb + t12x), Ci, n, P, part->C, 1, st);
+          });
+          col += part->C;
+        }
+      }
+      // 11. norm1 backward coefficients
+      const size_t coef4x = gn_backward(name + ".norm1.bwd", xv, gn1, t12x, -1);
+      // 12. dx (+)= A dpre + B x + C + r
+      {
+        int col = 0;
+        for (int i = 0; i < xv.n; ++i) {
+          const TensorP part = xv.part[i];
+          const int c0 = col;
+          const GradW gx = grad_w(part);
+          const size_t r_off = has_skip ? dxres : dY;
+          const int r_ld = has_skip ? Ci : Co;
+          pushb(name + ".norm1.apply" + (xv.n > 1 ? std::to_string(i) : ""), "bwd_affine3", {}, [=](const RunCtx& c, cudaStream_t st) {
+            launch_bwd_affine3(c.g + dr, dtg, Ci, c0, c.a + part->off, dta, part->C, 0, (const float4*)(c.fb + coef4x), Ci, c0,
+                               c.g + r_off, dtg, r_ld, c0, c.g + gx.off, dtg, part->C, 0, gx.accumulate, n, P, part->C, st);
+          });
+          col += part->C;
+        }
+      }
+      gfree(dr, M * Ci * gsz);
+      if (has_skip) gfree(dxres, M * Ci * gsz);
+      grad_done(out);
+    });
   }
 
   // ---- LinearAttention (efficient_unet.py:273-308) ---------------------------------------------
@@ -439,7 +725,8 @@ struct Builder {
     const int C = x->C, heads = p->cfg.num_attention_heads, inner = heads * 32;
     const int h = x->H, w = x->W, P = h * w;
     const double es = (double)p->esz;
-    const size_t coefn = gn_coef(name + ".norm", View::of(x), name + ".norm", -1);
+    const GnInfo gnn = gn_coef(name + ".norm", View::of(x), name + ".norm", -1);
+    const size_t coefn = gnn.coef;
     TensorP qkv = p->new_tensor(3 * inner, h, w, false, name + ".qkv");
     GemmW wq = make_w(3 * inner, {C});
     p->add_weight(name + ".to_qkv.weight", (int64_t)3 * inner * C, mat_job(wq, 0, PACK_MAT, 3 * inner, C, C, 0));
@@ -463,7 +750,8 @@ struct Builder {
     gemm(name + ".to_out", {{o, 0, 0, 0, XF_NONE}}, wo, u, true, (C + (double)inner) * N * P * es + (double)inner * C * es,
          2.0 * N * P * C * inner);
     p->release(o);
-    const size_t coefo = gn_coef(name + ".to_out.1", View::of(u), name + ".to_out.1", -1);
+    const GnInfo gno = gn_coef(name + ".to_out.1", View::of(u), name + ".to_out.1", -1);
+    const size_t coefo = gno.coef;
     TensorP y = p->new_tensor(C, h, w, true, name + ".out");
     {
       lcm_plan* pl = p; const int n = N;
@@ -472,6 +760,88 @@ struct Builder {
              launch_affine_residual(c.a + u->off, (const float2*)(c.f + coefo), c.a + x->off, c.a + y->off,
                                     (double*)(c.z + y->stats_off), n, P, C, pl->bf16, st);
            });
+    }
+    if (p->train) {
+      // reverse of efficient_unet.py:273-308
+      const DgradW woT = make_dgrad_w(name + ".to_out.0.weight", (int64_t)C * inner, inner, C, inner, 0);        // [inner][C]
+      const DgradW wqT = make_dgrad_w(name + ".to_qkv.weight", (int64_t)3 * inner * C, C, 3 * inner, C, 0);     // [C][3 inner]
+      lcm_plan* pl = p; const int n = N;
+      on_backward([=]() {
+        const size_t gsz = pl->gsz, M = (size_t)n * P;
+        const int dta = pl->dt_act, dtg = pl->dt_grad;
+        const size_t dy = grad_r(y);
+        // residual edge: dx (+)= dy
+        const GradW gx0 = grad_w(x);
+        pushb(name + ".residual.bwd", "bwd_add", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_bwd_add(c.g + dy, dtg, C, 0, c.g + gx0.off, dtg, C, 0, gx0.accumulate, (long long)n * P, C, st);
+        });
+        // GroupNorm after to_out: du = A dy + B u + C
+        const size_t t12u = pl->zballoc((size_t)n * C * 2 * sizeof(double));
+        pushb(name + ".to_out.1.reduce", "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_bwd_mask_reduce(c.g + dy, dtg, C, 0, c.a + u->off, dta, C, 0, nullptr, 0, (double*)(c.zb + t12u), C, n, P, C, 0, st);
+        });
+        const size_t coef4u = gn_backward(name + ".to_out.1.bwd", View::of(u), gno, t12u, -1);
+        const size_t du = galloc(M * C * gsz);
+        pushb(name + ".to_out.1.apply", "bwd_affine3", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_bwd_affine3(c.g + dy, dtg, C, 0, c.a + u->off, dta, C, 0, (const float4*)(c.fb + coef4u), C, 0, nullptr, 0, 0, 0,
+                             c.g + du, dtg, C, 0, 0, n, P, C, st);
+        });
+        // to_out.0: dWo = du^T o ; do = du Wo
+        {
+          const size_t g_wo = wg(name + ".to_out.0.weight");
+          pushb(name + ".to_out.0.wgrad", "wgrad_simt", {name + ".to_out.0.weight"}, [=](const RunCtx& c, cudaStream_t st) {
+            GemmParams gp{};
+            int seg_dt[LCM_MAX_SEGS] = {dta, 0, 0, 0};
+            float* dst[LCM_MAX_SEGS] = {c.wg + g_wo, nullptr, nullptr, nullptr};
+            int dst_ld[LCM_MAX_SEGS] = {inner, 0, 0, 0};
+            gp.nseg = 1; gp.seg[0].A = c.a + o->off; gp.seg[0].K = inner; gp.seg[0].ld = inner; gp.seg[0].mode = XF_NONE;
+            gp.Ktot = inner; gp.P = P; gp.M = (long long)n * P; gp.Nc = C;
+            launch_wgrad_1x1(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st);
+          });
+        }
+        const size_t dO = galloc(M * inner * gsz);
+        dgrad_gemm(name + ".to_out.0.dgrad", du, woT, dO, P);
+        gfree(du, M * C * gsz);
+        // attention core
+        const size_t dstate = pl->zballoc((size_t)n * heads * 32 * 33 * sizeof(double));
+        const size_t dqkv = galloc(M * 3 * inner * gsz);
+        pushb(name + ".attn.bwd", "attn_bwd", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_attn_bwd(c.a + qkv->off, dta, (const double*)(c.z + state), c.g + dO, dtg, c.g + dqkv, (double*)(c.zb + dstate), n, P,
+                          heads, st);
+        });
+        p->bwd_ops.back().launches = 2;
+        gfree(dO, M * inner * gsz);
+        // to_qkv: dWqkv = dqkv^T (a x + b) ; dxn = dqkv Wqkv
+        {
+          const size_t g_wq = wg(name + ".to_qkv.weight");
+          pushb(name + ".to_qkv.wgrad", "wgrad_simt", {name + ".to_qkv.weight"}, [=](const RunCtx& c, cudaStream_t st) {
+            GemmParams gp{};
+            int seg_dt[LCM_MAX_SEGS] = {dta, 0, 0, 0};
+            float* dst[LCM_MAX_SEGS] = {c.wg + g_wq, nullptr, nullptr, nullptr};
+            int dst_ld[LCM_MAX_SEGS] = {C, 0, 0, 0};
+            gp.nseg = 1; gp.seg[0].A = c.a + x->off; gp.seg[0].K = C; gp.seg[0].ld = C; gp.seg[0].mode = XF_AFFINE;
+            gp.seg[0].coef = (const float2*)(c.f + gnn.coef); gp.seg[0].coef_ld = C; gp.seg[0].coef_off = 0;
+            gp.Ktot = C; gp.P = P; gp.M = (long long)n * P; gp.Nc = 3 * inner;
+            launch_wgrad_1x1(gp, seg_dt, c.g + dqkv, dtg, dst, dst_ld, pl->num_sms, st);
+          });
+        }
+        const size_t dxn = galloc(M * C * gsz);
+        dgrad_gemm(name + ".to_qkv.dgrad", dqkv, wqT, dxn, P);
+        gfree(dqkv, M * 3 * inner * gsz);
+        // first GroupNorm: dx += A dxn + B x + C
+        const size_t t12x = pl->zballoc((size_t)n * C * 2 * sizeof(double));
+        pushb(name + ".norm.reduce", "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_bwd_mask_reduce(c.g + dxn, dtg, C, 0, c.a + x->off, dta, C, 0, nullptr, 0, (double*)(c.zb + t12x), C, n, P, C, 0, st);
+        });
+        const size_t coef4x = gn_backward(name + ".norm.bwd", View::of(x), gnn, t12x, -1);
+        const GradW gx1 = grad_w(x);
+        pushb(name + ".norm.apply", "bwd_affine3", {}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_bwd_affine3(c.g + dxn, dtg, C, 0, c.a + x->off, dta, C, 0, (const float4*)(c.fb + coef4x), C, 0, nullptr, 0, 0, 0,
+                             c.g + gx1.off, dtg, C, 0, gx1.accumulate, n, P, C, st);
+        });
+        gfree(dxn, M * C * gsz);
+        grad_done(y);
+      });
     }
     p->release(u);
     p->release(x);
@@ -482,6 +852,8 @@ struct Builder {
   TensorP conv3(const std::string& name, const std::string& wname, const TensorP& x_in, int mode_in) {
     TensorP x = x_in;
     int mode = mode_in;
+    TensorP up_src;   // training: the low-resolution input of an up-convolution
+    if (mode_in == CONV_UP2) up_src = x_in;
     if (p->tc && mode == CONV_UP2) {
       // tensor-core path: materialise the bilinear x2 once (memory-bound), then a stride-1 conv whose operand
       // tiles are TMA boxes; the algorithmic accounting stays with the conv op below.
@@ -534,6 +906,71 @@ struct Builder {
                                  (double*)(c.z + out->stats_off), n, Hin, Win, C, C, mode, pl->bf16, st);
            }
          });
+    if (p->train) {
+      // transposed-conv weights: W'[ci][(8 - tap) * stride + co] (flipped taps, swapped channel roles)
+      PackJob jt{};
+      jt.kind = PACK_CONV3_T; jt.bf16 = p->bf16 ? 1 : 0; jt.R = C; jt.Cc = C; jt.Ci = C;
+      const bool tc_dgrad = p->tc && mode_in == CONV_UP2;   // stride-1 transposed conv = conv over dY: tcgen05 kernel
+      size_t wt_off;
+      int bn_t = 0;
+      if (tc_dgrad) {
+        bn_t = gemm_tc_pick_block_n(C);
+        wt_off = p->walloc((size_t)C * 9 * Cpad * sizeof(bf16));
+        jt.layout = WL_UMMA; jt.ld = 9 * Cpad; jt.tap_stride = Cpad; jt.block_n = bn_t;
+      } else {
+        wt_off = p->walloc((size_t)C * 9 * C * p->esz);
+        jt.layout = WL_ROWMAJOR; jt.ld = 9 * C; jt.tap_stride = C;
+      }
+      jt.dst = (void*)wt_off;
+      p->add_weight(wname + ".weight", (int64_t)C * C * 9, jt);
+      on_backward([=]() {
+        const size_t gsz = pl->gsz;
+        const int dta = pl->dt_act, dtg = pl->dt_grad;
+        const size_t dY = grad_r(out);
+        const size_t g_w = wg(wname + ".weight"), g_b = wg(wname + ".bias");
+        // weight + bias gradient; the fp32 plan recomputes the bilinear blend inside the loader (mode UP2 on the low-res input)
+        pushb(name + ".wgrad", "wgrad_simt", {wname + ".weight", wname + ".bias"}, [=](const RunCtx& c, cudaStream_t st) {
+          launch_wgrad_conv3(c.a + x->off, dta, c.g + dY, dtg, c.wg + g_w, c.wg + g_b, n, Hin, Win, C, C, mode, pl->num_sms, st);
+        });
+        if (mode_in == CONV_S2) {
+          const GradW gx = grad_w(x);
+          const size_t bytes = (size_t)n * Hin * Win * C * gsz;
+          const size_t tmp = gx.accumulate ? galloc(bytes) : 0;
+          pushb(name + ".dgrad", "conv3x3_dgrad_simt", {}, [=](const RunCtx& c, cudaStream_t st) {
+            launch_conv3x3_dgrad_simt(c.g + dY, pl->wbase + wt_off, c.g + (gx.accumulate ? tmp : gx.off), n, Hin, Win, C, C, CONV_S2,
+                                      pl->bf16, st);
+          });
+          if (gx.accumulate) {
+            pushb(name + ".dgrad.add", "bwd_add", {}, [=](const RunCtx& c, cudaStream_t st) {
+              launch_bwd_add(c.g + tmp, dtg, C, 0, c.g + gx.off, dtg, C, 0, 1, (long long)n * Hin * Win, C, st);
+            });
+            gfree(tmp, bytes);
+          }
+        } else {
+          // dUp = transposed stride-1 conv of dY, then the transpose of the bilinear x2
+          const size_t bytes = (size_t)n * Ho * Wo * C * gsz;
+          const size_t dUp = galloc(bytes);
+          pushb(name + ".dgrad", tc_dgrad ? "conv3x3_tc" : "conv3x3_dgrad_simt", {}, [=](const RunCtx& c, cudaStream_t st) {
+            if (tc_dgrad) {
+              GemmParams gp{};
+              gp.nseg = 1; gp.seg[0].A = c.g + dY; gp.seg[0].K = 9 * C; gp.seg[0].ld = C; gp.seg[0].mode = XF_NONE;
+              gp.Ktot = 9 * C; gp.W = pl->wbase + wt_off; gp.out = c.g + dUp; gp.stats = nullptr;
+              gp.P = Ho * Wo; gp.M = (long long)n * Ho * Wo; gp.Nc = C;
+              ConvGeom cg{CONV_S1, Ho, Wo, Ho, Wo, C, nullptr};
+              if (launch_gemm_tc(gp, cg, bn_t, pl->num_sms, st)) *c.launch_err = 1;
+            } else {
+              launch_conv3x3_dgrad_simt(c.g + dY, pl->wbase + wt_off, c.g + dUp, n, Ho, Wo, C, C, CONV_S1, pl->bf16, st);
+            }
+          });
+          const GradW gx = grad_w(up_src);
+          pushb(name + ".bilinear.bwd", "upsample2x_bwd", {}, [=](const RunCtx& c, cudaStream_t st) {
+            launch_upsample2x_bwd(c.g + dUp, c.g + gx.off, dtg, n, up_src->H, up_src->W, C, gx.accumulate, st);
+          });
+          gfree(dUp, bytes);
+        }
+        grad_done(out);
+      });
+    }
     p->release(x);
     return out;
   }
@@ -561,9 +998,24 @@ int build_plan(lcm_plan* p) {
       launch_time_embed(cx.t_dev, cx.t_scalar, N, base, ted, p->wf(w1), p->wf(b1), p->wf(w3), p->wf(b3), nullptr,
                         (float*)(cx.f + p->silu_f_off), st);
     });
+    if (p->train) {
+      p->dst_zb_off = p->zballoc((size_t)N * ted * sizeof(float));
+      Builder* bb = &b;
+      b.on_backward([=]() {
+        const size_t g1 = bb->wg("time_mlp.1.weight"), gb1 = bb->wg("time_mlp.1.bias");
+        const size_t g3 = bb->wg("time_mlp.3.weight"), gb3 = bb->wg("time_mlp.3.bias");
+        bb->pushb("time_mlp.bwd", "time_mlp_bwd", {"time_mlp.1.weight", "time_mlp.1.bias", "time_mlp.3.weight", "time_mlp.3.bias"},
+                  [=](const RunCtx& cx, cudaStream_t st) {
+                    launch_time_mlp_bwd(cx.t_dev, cx.t_scalar, N, base, ted, p->wf(w1), p->wf(b1), p->wf(w3), p->wf(b3),
+                                        (const float*)(cx.zb + p->dst_zb_off), cx.wg + g1, cx.wg + gb1, cx.wg + g3, cx.wg + gb3, st);
+                  });
+      });
+    }
   }
   const size_t film_op_index = p->ops.size();   // filled in once all blocks are enumerated
   b.push("film", "film", 0, 0, nullptr);
+  const size_t film_tape_index = b.tape.size();
+  b.on_backward(nullptr);                       // likewise (needs the complete row table)
 
   // a3: init conv fused with the conditioning concat (:553, low_light_diffusion.py:222)
   TensorP h = p->new_tensor(widths[0], H, W, true, "init_conv");
@@ -581,6 +1033,18 @@ int build_plan(lcm_plan* p) {
              launch_init_conv(cx.xa, cx.ca, cx.sa, cx.xb, cx.cb, cx.sb, p->wf(w_off), p->wf(b_off), cx.a + out->off,
                               (double*)(cx.z + out->stats_off), N, H, W, Co, p->bf16, st);
            });
+    if (p->train) {
+      Builder* bb = &b;
+      b.on_backward([=]() {   // the network input needs no gradient: weight + bias only
+        const size_t dY = bb->grad_r(out);
+        const size_t g_w = bb->wg("init_conv.weight"), g_b = bb->wg("init_conv.bias");
+        bb->pushb("init_conv.wgrad", "init_conv_wgrad", {"init_conv.weight", "init_conv.bias"}, [=](const RunCtx& cx, cudaStream_t st) {
+          if (launch_init_conv_wgrad(cx.xa, cx.ca, cx.sa, cx.xb, cx.cb, cx.sb, cx.g + dY, p->dt_grad, cx.wg + g_w, cx.wg + g_b, N, H, W,
+                                     Co, p->num_sms, st)) *cx.launch_err = 1;
+        });
+        bb->grad_done(out);
+      });
+    }
   }
 
   auto run_level = [&](const std::string& prefix, int nblocks, int res, View x, int Co) -> TensorP {
@@ -626,7 +1090,8 @@ int build_plan(lcm_plan* p) {
   }
   // a8 + a11: final norm + SiLU + conv, LCM step fused (:600-602, lcm_scheduler.py:214-242)
   {
-    const size_t coef = b.gn_coef("final_norm", View::of(h), "final_norm", -1);
+    const Builder::GnInfo gnf = b.gn_coef("final_norm", View::of(h), "final_norm", -1);
+    const size_t coef = gnf.coef;
     const int Ci = widths[0], Co = c.out_channels;
     const size_t w_off = p->walloc((size_t)9 * Ci * Co * sizeof(float));
     PackJob j{}; j.kind = PACK_CONV3_KN; j.dst = (void*)w_off; j.R = Co; j.Ci = Ci;
@@ -640,6 +1105,28 @@ int build_plan(lcm_plan* p) {
              launch_final_conv(cx.a + in->off, (const float2*)(cx.f + coef), p->wf(w_off), p->wf(b_off), cx.eps, cx.step,
                                N, H, W, Ci, Co, p->bf16, st);
            });
+    if (p->train) {
+      Builder* bb = &b;
+      b.on_backward([=]() {
+        // d eps = grad_scale * loss'(eps - target) / numel is formed inside the kernel; dpre = d(final_norm output)
+        const size_t bytes = (size_t)N * H * W * Ci * p->gsz;
+        const size_t dpre = bb->galloc(bytes);
+        const size_t t12 = p->zballoc((size_t)N * Ci * 2 * sizeof(double));
+        const size_t g_w = bb->wg("final_conv.weight"), g_b = bb->wg("final_conv.bias");
+        bb->pushb("final_conv.bwd", "final_conv_bwd", {"final_conv.weight", "final_conv.bias"}, [=](const RunCtx& cx, cudaStream_t st) {
+          if (launch_final_conv_bwd(cx.a + in->off, p->dt_act, (const float2*)(cx.f + coef), p->wf(w_off), cx.eps, cx.target,
+                                    cx.loss_type, cx.gscale, cx.gscale_dev, cx.g + dpre, p->dt_grad, (double*)(cx.zb + t12),
+                                    cx.wg + g_w, cx.wg + g_b, N, H, W, Ci, Co, p->num_sms, st)) *cx.launch_err = 1;
+        });
+        const size_t coef4 = bb->gn_backward("final_norm.bwd", View::of(in), gnf, t12, -1);
+        const Builder::GradW gx = bb->grad_w(in);
+        bb->pushb("final_norm.apply", "bwd_affine3", {}, [=](const RunCtx& cx, cudaStream_t st) {
+          launch_bwd_affine3(cx.g + dpre, p->dt_grad, Ci, 0, cx.a + in->off, p->dt_act, Ci, 0, (const float4*)(cx.fb + coef4), Ci, 0,
+                             nullptr, 0, 0, 0, cx.g + gx.off, p->dt_grad, Ci, 0, gx.accumulate, N, H * W, Ci, st);
+        });
+        bb->gfree(dpre, bytes);
+      });
+    }
   }
   // a4.3: one fused GEMV over all blocks' time_mlp.1 (:189-192,215)
   {
@@ -658,11 +1145,50 @@ int build_plan(lcm_plan* p) {
     f.run = [=](const RunCtx& cx, cudaStream_t st) {
       launch_film((const float*)(cx.f + p->silu_f_off), p->wf(fw), p->wf(fb), (float*)(cx.f + p->film_f_off), N, rows, ted, st);
     };
+    if (p->train) {
+      p->dfilm_fb_off = p->fballoc((size_t)N * rows * sizeof(float));
+      Builder* bb = &b;
+      std::vector<Builder::FilmBlock> blocks = b.film_blocks;
+      b.tape[film_tape_index] = [=]() {
+        // all blocks have written their d scale / d shift rows: weight gradients of every time_mlp.1, then d silu(t_emb)
+        std::vector<std::string> writes;
+        std::vector<std::pair<size_t, size_t>> offs;
+        for (auto& blk : blocks) {
+          writes.push_back(blk.wname + ".weight"); writes.push_back(blk.wname + ".bias");
+          offs.push_back({bb->wg(blk.wname + ".weight"), bb->wg(blk.wname + ".bias")});
+        }
+        bb->pushb("film.wgrad", "outer_sum", writes, [=](const RunCtx& cx, cudaStream_t st) {
+          for (size_t i = 0; i < blocks.size(); ++i)
+            launch_outer_sum((const float*)(cx.fb + p->dfilm_fb_off) + blocks[i].row0, rows, (const float*)(cx.f + p->silu_f_off), ted,
+                             cx.wg + offs[i].first, cx.wg + offs[i].second, N, blocks[i].rows, ted, st);
+        });
+        p->bwd_ops.back().launches = (int)blocks.size();
+        bb->pushb("film.dgrad", "film_bwd_input", {}, [=](const RunCtx& cx, cudaStream_t st) {
+          launch_film_bwd_input((const float*)(cx.fb + p->dfilm_fb_off), p->wf(fw), (float*)(cx.zb + p->dst_zb_off), N, rows, ted, st);
+        });
+      };
+    }
+  }
+  if (p->train) {
+    // replay the tape backwards: emits p->bwd_ops in execution order and sizes regions G / ZB / FB
+    for (auto it = b.tape.rbegin(); it != b.tape.rend(); ++it)
+      if (*it) (*it)();
   }
   return 0;
 }
 
+void finish_layout(lcm_plan* p) {
+  p->ws_bytes = align_up(p->z_bytes, 1024) + align_up(p->f_bytes, 1024) + align_up(p->pool.top, 1024);
+  if (p->train) {
+    p->zb_off_ws = p->ws_bytes; p->ws_bytes += align_up(p->zb_bytes, 1024);
+    p->fb_off_ws = p->ws_bytes; p->ws_bytes += align_up(p->fb_bytes, 1024);
+    p->g_off_ws = p->ws_bytes; p->ws_bytes += align_up(p->gpool.top, 1024);
+    p->wg_off_ws = p->ws_bytes; p->ws_bytes += align_up(p->wg_elems * sizeof(float), 1024);
+  }
+}
+
 int check_ready(const lcm_plan* p) {
+  if (!p->wbase) return fail(LCM_ERR_INVALID, "plan was created with LCM_FLAG_DRY: it describes the layout only");
   for (auto& kv : p->weights)
     if (!kv.second.set) return fail(LCM_ERR_MISSING_WEIGHT, "weight '%s' has not been set", kv.first.c_str());
   return 0;
@@ -673,6 +1199,12 @@ RunCtx make_ctx(const lcm_plan* p, void* workspace) {
   c.z = (char*)workspace;
   c.f = c.z + align_up(p->z_bytes, 1024);
   c.a = c.f + align_up(p->f_bytes, 1024);
+  if (p->train) {
+    c.zb = c.z + p->zb_off_ws;
+    c.fb = c.z + p->fb_off_ws;
+    c.g = c.z + p->g_off_ws;
+    c.wg = (float*)(c.z + p->wg_off_ws);
+  }
   return c;
 }
 
@@ -746,8 +1278,15 @@ int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width
   p->bf16 = precision == LCM_PREC_BF16;
   p->tc = p->bf16 && !(flags & LCM_FLAG_SIMT_GEMM);
   p->taps = (flags & LCM_FLAG_TAPS) != 0;
-  p->pool.reuse = !p->taps;
+  p->train = (flags & LCM_FLAG_TRAIN) != 0;
+  if (p->train && p->bf16 && !p->tc) return fail(LCM_ERR_INVALID, "training plans are fp32 or bf16 (tensor-core); LCM_FLAG_SIMT_GEMM is inference-only");
+  p->pool.reuse = !p->taps && !p->train;     // the backward pass reads every forward tensor
+  p->gpool.reuse = !p->taps;
   p->esz = p->bf16 ? 2 : 4;
+  p->dt_act = p->bf16 ? DT_BF16 : DT_F32;
+  p->dt_hid = p->tc ? DT_F16 : p->dt_act;
+  p->dt_grad = p->dt_act;                    // bf16 gradients keep fp32's exponent range (d loss / d eps is O(1/numel))
+  p->gsz = p->esz;
   // GroupNorm validity: the reference raises ValueError at construction when C % min(32,C) != 0 (F1)
   {
     std::vector<int> widths, cs;
@@ -762,6 +1301,14 @@ int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width
       if ((C * cfg->expansion_ratio) % 32) return fail(LCM_ERR_INVALID, "hidden width %d is not a multiple of 32", C * cfg->expansion_ratio);
     }
   }
+  if (flags & LCM_FLAG_DRY) {
+    // host-side description only (op lists, workspace / gradient layout); no device is touched and nothing can run
+    int rc = build_plan(p.get());
+    if (rc) return rc;
+    finish_layout(p.get());
+    *out = p.release();
+    return 0;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LCM_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
@@ -774,7 +1321,7 @@ int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width
 
   int rc = build_plan(p.get());
   if (rc) return rc;
-  p->ws_bytes = align_up(p->z_bytes, 1024) + align_up(p->f_bytes, 1024) + align_up(p->pool.top, 1024);
+  finish_layout(p.get());
   CUDA_TRY(cudaMalloc((void**)&p->wbase, p->wbytes ? p->wbytes : 256));
   CUDA_TRY(cudaMemset(p->wbase, 0, p->wbytes ? p->wbytes : 256));
   for (PackJob j : p->identity_jobs) {   // residual identities of the project GEMMs
@@ -805,6 +1352,7 @@ int lcm_plan_weight_info(const lcm_plan* plan, int index, const char** name, int
 
 int lcm_plan_set_weight(lcm_plan* plan, const char* name, const float* dev_values, int64_t numel, void* stream) {
   if (!plan || !name || !dev_values) return fail(LCM_ERR_INVALID, "null argument");
+  if (!plan->wbase) return fail(LCM_ERR_INVALID, "plan was created with LCM_FLAG_DRY: it describes the layout only");
   auto it = plan->weights.find(name);
   if (it == plan->weights.end()) return fail(LCM_ERR_UNKNOWN_WEIGHT, "unknown weight '%s'", name);
   if (it->second.numel != numel)
@@ -918,6 +1466,115 @@ int lcm_image_resize_u8(const uint8_t* src_hwc_dev, int batch, int src_h, int sr
   if (!src_hwc_dev || !dst_hwc_dev || batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1)
     return fail(LCM_ERR_INVALID, "null argument or empty image");
   launch_image_resize_u8(src_hwc_dev, batch, src_h, src_w, dst_hwc_dev, dst_h, dst_w, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- training step ----------------------------------------------------------------------------------
+int lcm_train_backward_op_info(const lcm_plan* plan, int index, const char** name, const char** kernel) {
+  if (!plan || !plan->train || index < 0 || index >= (int)plan->bwd_ops.size()) return fail(LCM_ERR_INVALID, "bad op index");
+  if (name) *name = plan->bwd_ops[index].name.c_str();
+  if (kernel) *kernel = plan->bwd_ops[index].kernel.c_str();
+  return 0;
+}
+int lcm_train_num_backward_ops(const lcm_plan* plan) { return plan && plan->train ? (int)plan->bwd_ops.size() : 0; }
+int64_t lcm_train_grad_elems(const lcm_plan* plan) { return plan && plan->train ? (int64_t)plan->wg_elems : 0; }
+size_t lcm_train_grad_offset_bytes(const lcm_plan* plan) { return plan && plan->train ? plan->wg_off_ws : 0; }
+
+int lcm_train_grad_info(const lcm_plan* plan, int index, const char** name, int64_t* offset, int64_t* numel, int* ready_after_op) {
+  if (!plan || !plan->train || index < 0 || index >= (int)plan->weight_order.size()) return fail(LCM_ERR_INVALID, "bad gradient index");
+  const std::string& n = plan->weight_order[index];
+  if (name) *name = n.c_str();
+  if (offset) *offset = (int64_t)plan->wgrad_off.at(n);
+  if (numel) *numel = plan->weights.at(n).numel;
+  if (ready_after_op) {
+    auto it = plan->wgrad_last_op.find(n);
+    *ready_after_op = it == plan->wgrad_last_op.end() ? -1 : it->second;
+  }
+  return 0;
+}
+
+int lcm_train_backward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride, const float* xb_dev, int cb,
+                       int64_t xb_batch_stride, const int64_t* t_dev, const float* eps_dev, const float* target_dev, int loss_type,
+                       float grad_scale, const float* grad_scale_dev, int op_begin, int op_end, void* workspace, void* stream) {
+  if (!plan || !t_dev || !eps_dev || !target_dev || !workspace) return fail(LCM_ERR_INVALID, "null argument");
+  if (!plan->train) return fail(LCM_ERR_INVALID, "plan was created without LCM_FLAG_TRAIN");
+  if (loss_type < 0 || loss_type > 3) return fail(LCM_ERR_INVALID, "Unknown loss type: %d", loss_type);
+  const int nops = (int)plan->bwd_ops.size();
+  if (op_end < 0 || op_end > nops) op_end = nops;
+  if (op_begin < 0 || op_begin > op_end) return fail(LCM_ERR_INVALID, "bad backward op range");
+  int rc = check_ready(plan);
+  if (rc) return rc;
+  RunCtx c = make_ctx(plan, workspace);
+  rc = fill_inputs(plan, c, xa_dev, ca, xa_batch_stride, xb_dev, cb, xb_batch_stride);
+  if (rc) return rc;
+  c.t_dev = (const long long*)t_dev;
+  c.eps = const_cast<float*>(eps_dev);
+  c.target = target_dev; c.loss_type = loss_type; c.gscale = grad_scale; c.gscale_dev = grad_scale_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  int launch_err = 0;
+  c.launch_err = &launch_err;
+  if (op_begin == 0) {
+    CUDA_TRY(cudaMemsetAsync(c.zb, 0, plan->zb_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(c.wg, 0, plan->wg_elems * sizeof(float), st));
+  }
+  for (int i = op_begin; i < op_end; ++i) plan->bwd_ops[i].run(c, st);
+  CUDA_TRY(cudaGetLastError());
+  if (launch_err) return fail(LCM_ERR_INVALID, "a backward kernel rejected its shape (unsupported configuration)");
+  return 0;
+}
+
+int lcm_train_loss(const float* eps_dev, const float* target_dev, int64_t numel, int loss_type, double* loss_dev, void* stream) {
+  if (!eps_dev || !target_dev || !loss_dev || numel < 1) return fail(LCM_ERR_INVALID, "null argument");
+  if (loss_type < 0 || loss_type > 2) return fail(LCM_ERR_INVALID, "Unknown loss type: %d", loss_type);
+  launch_loss(eps_dev, target_dev, numel, loss_type, loss_dev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_plan_set_weights_flat(lcm_plan* plan, const float* flat_dev, void* stream) {
+  if (!plan || !flat_dev) return fail(LCM_ERR_INVALID, "null argument");
+  if (!plan->train) return fail(LCM_ERR_INVALID, "plan was created without LCM_FLAG_TRAIN");
+  if (!plan->wbase) return fail(LCM_ERR_INVALID, "plan was created with LCM_FLAG_DRY: it describes the layout only");
+  for (const std::string& name : plan->weight_order) {
+    WeightSlot& slot = plan->weights.at(name);
+    const float* src = flat_dev + plan->wgrad_off.at(name);
+    for (PackJob j : slot.jobs) {
+      j.dst = plan->wbase + (size_t)j.dst;
+      launch_pack(j, src, (cudaStream_t)stream);
+    }
+    slot.set = true;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_grad_sumsq(const float* grads_dev, int64_t n, double* out_dev, void* stream) {
+  if (!grads_dev || !out_dev || n < 1) return fail(LCM_ERR_INVALID, "null argument");
+  launch_sumsq(grads_dev, n, out_dev, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_adamw_ema_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, float* ema_dev,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                       const double* grad_sumsq_dev, float grad_div, float max_norm, void* stream) {
+  if (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev || n < 1 || step < 1 || grad_div <= 0.f)
+    return fail(LCM_ERR_INVALID, "bad optimizer arguments");
+  if (max_norm > 0.f && !grad_sumsq_dev) return fail(LCM_ERR_INVALID, "clipping needs the gradient sum of squares");
+  launch_adamw_ema(params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev, ema_dev, n, lr, beta1, beta2, eps, weight_decay, step,
+                   ema_decay, grad_sumsq_dev, grad_div, max_norm, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int lcm_train_read_grad_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, void* workspace, void* stream) {
+  if (!plan || !name || !out_nchw_dev || !workspace) return fail(LCM_ERR_INVALID, "null argument");
+  auto it = plan->gtap_map.find(name);
+  if (it == plan->gtap_map.end()) return fail(LCM_ERR_INVALID, "unknown gradient tap '%s' (needs LCM_FLAG_TRAIN | LCM_FLAG_TAPS)", name);
+  RunCtx c = make_ctx(plan, workspace);
+  const TensorP& t = it->second;
+  launch_nhwc_to_nchw(c.g + t->g_off, out_nchw_dev, plan->N, t->H, t->W, t->C, plan->dt_grad == DT_BF16 ? 1 : 0, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -163,6 +163,9 @@ class EfficientUNet(nn.Module):
     def forward(self, x: torch.Tensor, timestep: torch.Tensor, return_features: bool = False):
         if return_features:
             raise NotImplementedError("return_features is an analysis hook of the reference; not on the hot path")
+        if torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
+            from .training import native_unet_forward   # training: activations are kept, eps carries autograd
+            return native_unet_forward(self, x, timestep)
         from .engine import unet_forward  # late import: needs the CUDA library
         return unet_forward(self, x, timestep)
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "liblcmunet.so")
 LCM_MAX_LEVELS = 8
 PREC_FP32, PREC_BF16 = 0, 1
 ACT_F16 = 2   # single-kernel entry points: fp16 hidden tensors of the tensor-core plan
-FLAG_SIMT_GEMM, FLAG_TAPS = 1, 2
+FLAG_SIMT_GEMM, FLAG_TAPS, FLAG_TRAIN, FLAG_DRY = 1, 2, 4, 8
 ERR_INVALID, ERR_CUDA, ERR_UNKNOWN_WEIGHT, ERR_MISSING_WEIGHT, ERR_WORKSPACE = -1, -2, -3, -4, -5
 
 
@@ -60,6 +60,22 @@ SIGNATURES = {
     "lcm_image_resize_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lcm_scheduler_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                     C.c_int, C.c_void_p]),
+    "lcm_train_num_backward_ops": (C.c_int, [C.c_void_p]),
+    "lcm_train_backward_op_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]),
+    "lcm_train_grad_elems": (C.c_int64, [C.c_void_p]),
+    "lcm_train_grad_offset_bytes": (C.c_size_t, [C.c_void_p]),
+    "lcm_train_grad_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int)]),
+    "lcm_train_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "lcm_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "lcm_plan_set_weights_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lcm_grad_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lcm_adamw_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_float,
+                                     C.c_float, C.c_void_p]),
+    "lcm_train_read_grad_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcm_plan_num_taps": (C.c_int, [C.c_void_p]),
     "lcm_plan_tap_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int)]),

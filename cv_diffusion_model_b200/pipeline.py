@@ -107,7 +107,8 @@ class LowLightDiffusion(nn.Module):
     def forward(self, low_light: torch.Tensor, normal_light: Optional[torch.Tensor] = None,
                 timesteps: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                 return_dict: bool = True):
-        """Training-style forward (reference :115-171), inference-only here: noise prediction without autograd."""
+        """Training forward (reference :115-171): random timesteps, noise, ``add_noise``, concat conditioning, noise
+        prediction.  With autograd enabled ``noise_pred`` carries gradients to the UNet parameters (native backward)."""
         if normal_light is None:
             return self.enhance(low_light)
         b, device = low_light.shape[0], low_light.device
@@ -116,21 +117,34 @@ class LowLightDiffusion(nn.Module):
         if noise is None:
             noise = torch.randn_like(normal_light)
         noisy = self.scheduler.add_noise(normal_light, noise, timesteps)
-        with torch.no_grad():
-            noise_pred = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
+        noise_pred = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
         if return_dict:
             return {"noise_pred": noise_pred, "noise": noise, "timesteps": timesteps}
         return noise_pred
 
-    def compute_loss(self, low_light: torch.Tensor, normal_light: torch.Tensor, loss_type: str = "mse") -> torch.Tensor:
-        """Loss value of the reference (:250-277).  NOTE: forward-only — the backward kernels of the
-        data-parallel training config are not part of this round ('out of scope')."""
-        import torch.nn.functional as F
-        if loss_type not in ("mse", "huber", "l1"):
+    def compute_loss(self, low_light: torch.Tensor, normal_light: torch.Tensor, loss_type: str = "mse",
+                     timesteps: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Training loss (reference :250-277) as ONE native forward + loss; ``loss.backward()`` runs the native backward
+        pass and fills ``param.grad`` of every UNet parameter, so the reference's loop (trainer.py:283-322: GradScaler,
+        ``clip_grad_norm_``, any torch optimizer) works unchanged.  ``timesteps`` / ``noise`` are optional injection points
+        (the reference draws them inside ``forward``)."""
+        from .training import LOSS_TYPES, native_loss
+        if loss_type not in LOSS_TYPES:
             raise ValueError(f"Unknown loss type: {loss_type}")
-        out = self.forward(low_light, normal_light)
-        fn = {"mse": F.mse_loss, "huber": F.huber_loss, "l1": F.l1_loss}[loss_type]
-        return fn(out["noise_pred"], out["noise"])
+        if not low_light.is_cuda:
+            raise RuntimeError("low_light must be a CUDA tensor: the B200 path has no CPU fallback")
+        b, device = low_light.shape[0], low_light.device
+        if timesteps is None:
+            timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (b,), device=device)
+        if noise is None:
+            noise = torch.randn_like(normal_light)
+        noisy = self.scheduler.add_noise(normal_light.contiguous(), noise.contiguous(), timesteps)
+        if not torch.is_grad_enabled():
+            import torch.nn.functional as F
+            eps = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
+            return {"mse": F.mse_loss, "huber": F.huber_loss, "l1": F.l1_loss}[loss_type](eps, noise)
+        loss, _ = native_loss(self.unet, noisy, low_light, timesteps, noise, loss_type)
+        return loss
 
     def get_model_size(self) -> Dict[str, float]:
         return self.unet.get_memory_footprint()

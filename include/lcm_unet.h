@@ -46,6 +46,9 @@ typedef enum { LCM_PREC_FP32 = 0, LCM_PREC_BF16 = 1 } lcm_precision;
 /* plan flags */
 #define LCM_FLAG_SIMT_GEMM 1u     /* bf16 plans: use the CUDA-core GEMM/conv kernels instead of tcgen05 (cross-check) */
 #define LCM_FLAG_TAPS 2u          /* keep every intermediate alive (no buffer reuse) so lcm_plan_read_tap works */
+#define LCM_FLAG_DRY 8u           /* describe only: op lists, workspace and gradient layout, no device needed; cannot run */
+#define LCM_FLAG_TRAIN 4u         /* training plan: forward keeps every activation, the plan also holds the backward op list,
+                                     gradient buffers and a flat fp32 weight-gradient buffer inside the workspace */
 
 /* Mirrors EfficientUNetConfig (src/models/efficient_unet.py:24-57). */
 typedef struct {
@@ -126,6 +129,46 @@ int lcm_image_postprocess_u8(const float* nchw_dev, uint8_t* hwc_dev, int batch,
  * bit-identical to OpenCV 4.x including the exact-2x shrink (where OpenCV switches to area averaging: same values). */
 int lcm_image_resize_u8(const uint8_t* src_hwc_dev, int batch, int src_h, int src_w, uint8_t* dst_hwc_dev, int dst_h,
                         int dst_w, void* stream);
+
+/* ---- training step (BASELINE config 5) -----------------------------------------------------------------
+ * Replaces, for a plan created with LCM_FLAG_TRAIN (precision fp32, or bf16 on the tensor-core path):
+ *   loss.backward() of LowLightDiffusion.compute_loss (src/models/low_light_diffusion.py:250-277, the UNet part of
+ *   forward :143-163) and, optionally, clip_grad_norm_ + AdamW.step + EMAModel.update (src/training/trainer.py:296-322,
+ *   :98-104, :152-156).
+ * Protocol per step:  lcm_unet_forward (x = cat([noisy, low_light]), per-sample t)  ->  lcm_train_loss  ->
+ *   lcm_train_backward  ->  [all-reduce of the flat gradient buffer by the caller]  ->  lcm_grad_sumsq +
+ *   lcm_adamw_ema_step on flat fp32 buffers  ->  lcm_plan_set_weights_flat.
+ * The flat gradient buffer lives inside the workspace at lcm_train_grad_offset_bytes(); it holds every weight's gradient
+ * in the reference's state_dict layout at the element offset lcm_train_grad_info reports (16-byte aligned slices, zero
+ * padding), in lcm_plan_weight_info order.  A flat PARAMETER buffer with the same offsets feeds lcm_plan_set_weights_flat. */
+int lcm_train_num_backward_ops(const lcm_plan* plan);
+int lcm_train_backward_op_info(const lcm_plan* plan, int index, const char** name, const char** kernel);
+int64_t lcm_train_grad_elems(const lcm_plan* plan);
+size_t lcm_train_grad_offset_bytes(const lcm_plan* plan);
+/* ready_after_op: index of the last backward op that writes this gradient (it is complete once ops [0, index] have
+ * run) — lets the caller all-reduce buckets while the rest of the backward pass executes. */
+int lcm_train_grad_info(const lcm_plan* plan, int index, const char** name, int64_t* offset, int64_t* numel, int* ready_after_op);
+/* loss (mean over all elements; loss_type 0 mse, 1 l1, 2 huber(delta 1): low_light_diffusion.py:268-275) -> *loss_dev */
+int lcm_train_loss(const float* eps_dev, const float* target_dev, int64_t numel, int loss_type, double* loss_dev, void* stream);
+/* Backward ops [op_begin, op_end) of the most recent lcm_unet_forward on this plan/workspace (op_end < 0: all).  Inputs
+ * are the forward's (xa/xb/t) plus its output eps and the regression target (the noise).  d loss/d eps is
+ * grad_scale * (*grad_scale_dev, if given) * loss'(eps - target) / numel.  loss_type 3: target_dev IS the upstream gradient
+ * d loss / d eps (autograd through EfficientUNet.forward; no division by numel).  op_begin == 0 zeroes the gradient buffer. */
+int lcm_train_backward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride, const float* xb_dev, int cb,
+                       int64_t xb_batch_stride, const int64_t* t_dev, const float* eps_dev, const float* target_dev, int loss_type,
+                       float grad_scale, const float* grad_scale_dev, int op_begin, int op_end, void* workspace, void* stream);
+/* re-pack every weight from a flat fp32 parameter buffer laid out like the gradient buffer */
+int lcm_plan_set_weights_flat(lcm_plan* plan, const float* flat_dev, void* stream);
+/* sum of squares of a flat gradient buffer -> *out_dev (fp64) */
+int lcm_grad_sumsq(const float* grads_dev, int64_t n, double* out_dev, void* stream);
+/* clip_grad_norm_(max_norm) + AdamW + EMA in one pass: g' = g / grad_div ; g' *= min(1, max_norm / (||g'|| + 1e-6)) ;
+ * p *= 1 - lr wd ; m, v updates ; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps) ; ema = d ema + (1 - d) p.
+ * ema_dev may be NULL; max_norm <= 0 disables clipping. */
+int lcm_adamw_ema_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, float* ema_dev,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay,
+                       const double* grad_sumsq_dev, float grad_div, float max_norm, void* stream);
+/* gradient of a named forward intermediate after a full backward pass (LCM_FLAG_TRAIN | LCM_FLAG_TAPS), fp32 NCHW */
+int lcm_train_read_grad_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, void* workspace, void* stream);
 
 /* ---- debugging / unit parity --------------------------------------------------------------------
  * Copy a named intermediate of the most recent forward (e.g. "encoder_blocks.0.0.expand",
