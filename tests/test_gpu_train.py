@@ -120,7 +120,15 @@ def test_backward_bf16_vs_autograd(variant, cfg_size, size, b, patched):
     print(f"bf16 training plan [{variant} cfg {cfg_size} in {size}]: loss {loss:.6f} vs {want_loss:.6f}; global gradient cosine "
           f"{cos:.5f} (oracle under torch bf16 autocast: {acos:.5f}), norm ratio {gn / tot:.4f}")
     assert cos >= min(0.99, acos - 0.02), (cos, acos)
-    bad = [(r[3], r[1]) for r in rows if r[2] >= 1e-2 and r[1] < min(0.9, acos - 0.1)]
+    # per parameter: in the same class as torch's bf16 autocast (an ill-conditioned case drags both down)
+    bad = []
+    for rel, c, share, k in rows:
+        if share < 1e-2:
+            continue
+        a = ac[k].double().flatten()
+        ak = (a @ want[k].double().flatten()).item() / max(a.norm().item() * want[k].double().norm().item(), 1e-300)
+        if c < min(0.9, ak - 0.1):
+            bad.append((k, c, ak))
     assert not bad, bad[:10]
 
 
@@ -190,7 +198,9 @@ def test_reference_two_step_kat_native_trainer():
     assert np.all(np.abs(delta - want) <= 0.02 * want + 1e-7), np.max(np.abs(delta - want) / (want + 1e-9))
     ema = tr.ema_state()
     edelta = np.array([(ema[n] - w0[n]).norm().item() for n in names])
-    assert np.all(np.abs(edelta - kat["ema_delta_norms"]) <= 0.02 * kat["ema_delta_norms"] + 1e-9)
+    # the shadow moves by (1 - decay) * update ~ 1e-8 .. 1e-6 per tensor: allow fp32 rounding of the shadow itself
+    w0n = np.array([w0[n].norm().item() for n in names])
+    assert np.all(np.abs(edelta - kat["ema_delta_norms"]) <= 0.02 * kat["ema_delta_norms"] + 1e-7 * w0n + 1e-9)
     # the updated weights are what the inference path now uses (epoch bump -> re-pack)
     with torch.no_grad():
         y = pipe.unet(torch.randn(2, 6, 64, 64, device="cuda"), torch.tensor([5, 700], device="cuda"))
