@@ -8,11 +8,12 @@ See DESIGN.md for the path, include/lcm_unet.h for the C ABI.
 """
 from .config import EfficientUNetConfig, variant_config
 from .modules import EfficientUNet, create_efficient_unet
+from .distillation import LowLightLCMDistillation
 from .pipeline import LowLightDiffusion, LowLightDiffusionOutput, denormalize_image, normalize_image
 from .scheduler import LCMScheduler, LCMSchedulerOutput, get_lcm_timesteps
 
 __all__ = [
     "EfficientUNetConfig", "variant_config", "EfficientUNet", "create_efficient_unet", "LowLightDiffusion",
-    "LowLightDiffusionOutput", "LCMScheduler", "LCMSchedulerOutput", "get_lcm_timesteps", "normalize_image",
+    "LowLightDiffusionOutput", "LowLightLCMDistillation", "LCMScheduler", "LCMSchedulerOutput", "get_lcm_timesteps", "normalize_image",
     "denormalize_image",
 ]

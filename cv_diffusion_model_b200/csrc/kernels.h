@@ -89,6 +89,11 @@ void launch_lcm_step(const float* eps, const float* sample, const float* noise, 
 void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st);
 void launch_image_post_u8(const float* nchw, uint8_t* hwc, int N, int H, int W, cudaStream_t st);
 void launch_image_resize_u8(const uint8_t* src, int N, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st);
+void launch_ddim_step(const float* x_t, const float* eps, const long long* t, const long long* t_next, const float* abar,
+                      float* x_next, int batch, long long per_sample, cudaStream_t st);
+void launch_consistency_loss(const float* x_t, const float* eps_s, const long long* t, const float* x_next, const float* eps_tgt,
+                             const long long* t_next, const float* abar, double* loss, float* d_eps, int batch, long long per_sample,
+                             cudaStream_t st);
 void launch_lcm_mix(const float* a, const float* b, const long long* t, const float* abar, float* out, int batch,
                     long long per_sample, int velocity, cudaStream_t st);
 

@@ -377,6 +377,68 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Consistency distillation (low_light_diffusion.py:325-408), the element-wise parts around the three UNet forwards.
+// DDIM step of the teacher (:372-381): x0 = (x_t - sqrt(1 - a_t) eps) / sqrt(a_t) ; x_next = sqrt(a_n) x0 + sqrt(1 - a_n) eps,
+// per-sample timesteps t, t_next.
+__global__ void ddim_step_kernel(const float* __restrict__ x_t, const float* __restrict__ eps, const long long* __restrict__ t,
+                                 const long long* __restrict__ t_next, const float* __restrict__ abar, float* __restrict__ x_next,
+                                 long long per_sample) {
+  const int n = blockIdx.y;
+  const float at = abar[t[n]], an = abar[t_next[n]];
+  const float sa = sqrtf(at), sb = sqrtf(1.f - at), na = sqrtf(an), nb = sqrtf(1.f - an);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = (long long)n * per_sample + i;
+    const float e = eps[j];
+    const float x0 = (x_t[j] - sb * e) / sa;
+    x_next[j] = na * x0 + nb * e;
+  }
+}
+void launch_ddim_step(const float* x_t, const float* eps, const long long* t, const long long* t_next, const float* abar,
+                      float* x_next, int batch, long long per_sample, cudaStream_t st) {
+  int bx = (int)((per_sample + 255) / 256);
+  if (bx > 1024) bx = 1024;
+  ddim_step_kernel<<<dim3(bx, batch), 256, 0, st>>>(x_t, eps, t, t_next, abar, x_next, per_sample);
+}
+// loss = huber(student_x0, target_x0) (mean, delta 1; :399-406) and d loss / d eps_student:
+//   student_x0 = (x_t - sqrt(1 - a_t) eps_s) / sqrt(a_t) ; target_x0 = (x_next - sqrt(1 - a_n) eps_tgt) / sqrt(a_n)
+__global__ void consistency_loss_kernel(const float* __restrict__ x_t, const float* __restrict__ eps_s, const long long* __restrict__ t,
+                                        const float* __restrict__ x_next, const float* __restrict__ eps_tgt,
+                                        const long long* __restrict__ t_next, const float* __restrict__ abar, double inv_numel,
+                                        double* __restrict__ loss, float* __restrict__ d_eps, long long per_sample) {
+  __shared__ double s_part[8];
+  const int n = blockIdx.y;
+  const float at = abar[t[n]], an = abar[t_next[n]];
+  const float sa = sqrtf(at), sb = sqrtf(1.f - at), na = sqrtf(an), nb = sqrtf(1.f - an);
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = (long long)n * per_sample + i;
+    const float xs = (x_t[j] - sb * eps_s[j]) / sa;
+    const float xt = (x_next[j] - nb * eps_tgt[j]) / na;
+    const float d = xs - xt, a = fabsf(d);
+    acc += a < 1.f ? 0.5 * (double)d * d : (double)a - 0.5;
+    const float g = a < 1.f ? d : (d > 0.f ? 1.f : -1.f);
+    d_eps[j] = g * (-sb / sa) * (float)inv_numel;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += s_part[i];
+    atomicAdd(loss, s * inv_numel);
+  }
+}
+void launch_consistency_loss(const float* x_t, const float* eps_s, const long long* t, const float* x_next, const float* eps_tgt,
+                             const long long* t_next, const float* abar, double* loss, float* d_eps, int batch, long long per_sample,
+                             cudaStream_t st) {
+  cudaMemsetAsync(loss, 0, sizeof(double), st);
+  int bx = (int)((per_sample + 255) / 256);
+  if (bx > 256) bx = 256;
+  consistency_loss_kernel<<<dim3(bx, batch), 256, 0, st>>>(x_t, eps_s, t, x_next, eps_tgt, t_next, abar,
+                                                          1.0 / ((double)batch * (double)per_sample), loss, d_eps, per_sample);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Image formats either side of the path (scripts/inference.py:111-116, 121-127): byte work, HBM-bound.
 // One thread per pixel: 3 interleaved bytes <-> one element of each of the three planes (plane accesses coalesced,
 // the 3-byte pixel accesses are consecutive across the warp: 96 contiguous bytes).

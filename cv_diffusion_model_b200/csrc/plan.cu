@@ -1448,6 +1448,26 @@ int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_d
   return 0;
 }
 
+int lcm_ddim_step(const float* x_t_dev, const float* eps_dev, const int64_t* t_dev, const int64_t* t_next_dev, const float* abar_dev,
+                  float* x_next_dev, int batch, int64_t per_sample, void* stream) {
+  if (!x_t_dev || !eps_dev || !t_dev || !t_next_dev || !abar_dev || !x_next_dev) return fail(LCM_ERR_INVALID, "null argument");
+  launch_ddim_step(x_t_dev, eps_dev, (const long long*)t_dev, (const long long*)t_next_dev, abar_dev, x_next_dev, batch, per_sample,
+                   (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int lcm_consistency_loss(const float* x_t_dev, const float* eps_student_dev, const int64_t* t_dev, const float* x_next_dev,
+                         const float* eps_target_dev, const int64_t* t_next_dev, const float* abar_dev, double* loss_dev,
+                         float* d_eps_student_dev, int batch, int64_t per_sample, void* stream) {
+  if (!x_t_dev || !eps_student_dev || !t_dev || !x_next_dev || !eps_target_dev || !t_next_dev || !abar_dev || !loss_dev ||
+      !d_eps_student_dev)
+    return fail(LCM_ERR_INVALID, "null argument");
+  launch_consistency_loss(x_t_dev, eps_student_dev, (const long long*)t_dev, x_next_dev, eps_target_dev, (const long long*)t_next_dev,
+                          abar_dev, loss_dev, d_eps_student_dev, batch, per_sample, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int lcm_image_preprocess_u8(const uint8_t* hwc_dev, float* nchw_dev, int batch, int height, int width, void* stream) {
   if (!hwc_dev || !nchw_dev || batch < 1 || height < 1 || width < 1) return fail(LCM_ERR_INVALID, "null argument or empty image");
   launch_image_pre_u8(hwc_dev, nchw_dev, batch, height, width, (cudaStream_t)stream);

@@ -162,12 +162,33 @@ class EfficientUNet(nn.Module):
     # ---- reference surface --------------------------------------------------
     def forward(self, x: torch.Tensor, timestep: torch.Tensor, return_features: bool = False):
         if return_features:
-            raise NotImplementedError("return_features is an analysis hook of the reference; not on the hot path")
-        if torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
+            # analysis hook of the reference (:595-596,604-605): the output of every decoder level, read back from a
+            # plan that keeps its intermediates (no buffer reuse; slower, inference only)
+            from .engine import get_engine
+            eng = get_engine(self, x.shape[0], x.shape[2], x.shape[3], x.device, taps=True)
+            with torch.no_grad():
+                out = eng.forward(x, timestep)
+                last = {}
+                for name in eng.taps():
+                    if name.startswith("decoder_blocks.") and name.endswith(".out"):
+                        last[int(name.split(".")[1])] = name          # the level's last block / attention output
+                feats = [eng.read_tap(last[k]) for k in sorted(last)]
+            return out, feats
+        if self.training and torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
             from .training import native_unet_forward   # training: activations are kept, eps carries autograd
             return native_unet_forward(self, x, timestep)
         from .engine import unet_forward  # late import: needs the CUDA library
         return unet_forward(self, x, timestep)
+
+    def __deepcopy__(self, memo):
+        """Copies parameters and configuration; native plans (device handles, workspaces) are never shared or copied
+        (``copy.deepcopy(student_model)`` in the distillation wrapper, low_light_diffusion.py:311-313)."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = OrderedDict() if k == "_engines" else copy.deepcopy(v, memo)
+        return new
 
     def get_num_params(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

@@ -76,6 +76,9 @@ SIGNATURES = {
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_float,
                                      C.c_float, C.c_void_p]),
     "lcm_train_read_grad_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lcm_ddim_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "lcm_consistency_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "lcm_plan_num_taps": (C.c_int, [C.c_void_p]),
     "lcm_plan_tap_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int)]),

@@ -117,6 +117,16 @@ int lcm_scheduler_step(const float* model_out_dev, const float* sample_dev, cons
 int lcm_scheduler_mix(const float* a_dev, const float* b_dev, const int64_t* t_dev, const float* abar_dev,
                       float* out_dev, int batch, int64_t per_sample, int velocity, void* stream);
 
+/* ---- consistency distillation (LowLightLCMDistillation.consistency_distillation_loss, low_light_diffusion.py:325-408):
+ * the element-wise steps around its three UNet forwards; per-sample timesteps index abar_dev.
+ * lcm_ddim_step (:372-381): x0 = (x_t - sqrt(1-a_t) eps) / sqrt(a_t); x_next = sqrt(a_next) x0 + sqrt(1-a_next) eps.
+ * lcm_consistency_loss (:399-406): *loss_dev = mean huber(student_x0, target_x0), d_eps_student = d loss / d eps_student. */
+int lcm_ddim_step(const float* x_t_dev, const float* eps_dev, const int64_t* t_dev, const int64_t* t_next_dev, const float* abar_dev,
+                  float* x_next_dev, int batch, int64_t per_sample, void* stream);
+int lcm_consistency_loss(const float* x_t_dev, const float* eps_student_dev, const int64_t* t_dev, const float* x_next_dev,
+                         const float* eps_target_dev, const int64_t* t_next_dev, const float* abar_dev, double* loss_dev,
+                         float* d_eps_student_dev, int batch, int64_t per_sample, void* stream);
+
 /* ---- image formats either side of the path -----------------------------------
  * preprocess (scripts/inference.py:111-116): uint8 RGB HWC [N][H][W][3] -> fp32 NCHW, x / 127.5 - 1 (fp32 division, then
  * fp32 subtraction: bit-identical to the reference's numpy expression).

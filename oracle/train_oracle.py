@@ -63,3 +63,25 @@ def train_steps(sd0: Dict[str, torch.Tensor], cfg, abar, batches, lr=1e-4, weigh
         losses.append(loss.item())
         norms.append(float(gn))
     return losses, norms, {k: v.detach() for k, v in params.items()}, shadow
+
+
+def distillation_loss(teacher_sd, student_sd, ema_sd, cfg, abar, low, high, noise, idx, num_ddim_timesteps: int = 50,
+                      num_inference_steps: int = 4, num_train_timesteps: int = 1000, strict_groupnorm: bool = True):
+    """LowLightLCMDistillation.consistency_distillation_loss (low_light_diffusion.py:325-408), concat conditioning, with the
+    two random draws (noise, idx) injected.  student_sd tensors may require grad."""
+    c = num_train_timesteps // num_ddim_timesteps
+    k = num_ddim_timesteps // num_inference_steps
+    t = idx * c + c - 1
+    t_next = (idx + k) * c + c - 1
+    x_t = add_noise(high, noise, t, abar)
+    ab = abar.to(high.device)
+    a_t, a_n = ab[t].view(-1, 1, 1, 1), ab[t_next].view(-1, 1, 1, 1)
+    with torch.no_grad():
+        teacher_eps = unet_oracle.unet_forward(teacher_sd, cfg, torch.cat([x_t, low], dim=1), t, strict_groupnorm)
+        x0_pred = (x_t - (1 - a_t).sqrt() * teacher_eps) / a_t.sqrt()
+        x_next = a_n.sqrt() * x0_pred + (1 - a_n).sqrt() * teacher_eps
+        target = unet_oracle.unet_forward(ema_sd, cfg, torch.cat([x_next, low], dim=1), t_next, strict_groupnorm)
+    student = unet_oracle.unet_forward(student_sd, cfg, torch.cat([x_t, low], dim=1), t, strict_groupnorm)
+    student_x0 = (x_t - (1 - a_t).sqrt() * student) / a_t.sqrt()
+    target_x0 = (x_next - (1 - a_n).sqrt() * target) / a_n.sqrt()
+    return F.huber_loss(student_x0, target_x0)

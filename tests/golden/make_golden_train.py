@@ -55,6 +55,43 @@ def load_ema_class():
     return mod.EMAModel
 
 
+def distill(out):
+    """One consistency-distillation loss + backward of the unmodified reference wrapper (low_light_diffusion.py:284-408)."""
+    from src.models.low_light_diffusion import LowLightLCMDistillation as RefDistill
+    S, B = 64, 2
+    torch.manual_seed(0)
+    teacher = RefPipeline(unet_variant="small", image_size=S, num_inference_steps=4)
+    randomise_affine(teacher.unet)
+    torch.manual_seed(1)
+    student = RefPipeline(unet_variant="small", image_size=S, num_inference_steps=4)
+    randomise_affine(student.unet, seed=2)
+    wrap = RefDistill(teacher, student)
+    with torch.no_grad():      # make the EMA target differ from the student, like after some updates
+        for e in wrap.ema_student.parameters():
+            e.mul_(0.98)
+    g = torch.Generator().manual_seed(555)
+    high = torch.rand(B, 3, S, S, generator=g) * 2 - 1
+    low = ((high + 1) / 2) ** 3 * 2 - 1
+    torch.manual_seed(99)
+    loss = wrap.consistency_distillation_loss(low, high, num_inference_steps=4)
+    loss.backward()
+    torch.manual_seed(99)      # the same two draws, made explicitly (randn_like, then randint: :341,348)
+    noise = torch.randn(B, 3, S, S)
+    idx = torch.randint(0, 50 - 50 // 4, (B,))
+    ssd = {k: v.detach().clone().requires_grad_(True) for k, v in student.unet.state_dict().items()}
+    o = train_oracle.distillation_loss(teacher.unet.state_dict(), ssd, wrap.ema_student.unet.state_dict(), student.unet.config,
+                                       teacher.scheduler.alphas_cumprod, low, high, noise, idx)
+    assert abs(o.item() - loss.item()) <= 1e-6 * abs(loss.item()), (o.item(), loss.item())
+    og = torch.autograd.grad(o, list(ssd.values()))
+    names = [n for n, _ in student.unet.named_parameters()]
+    worst = max((student.unet.get_parameter(n).grad - gk).abs().max().item() / (gk.abs().max().item() + 1e-30) for n, gk in zip(names, og))
+    print(f"distillation: loss {loss.item():.6f}, oracle vs reference gradients worst relative max-diff {worst:.2e}")
+    assert worst <= 1e-4
+    out.update(distill_low=low.numpy(), distill_high=high.numpy(), distill_noise=noise.numpy(), distill_idx=idx.numpy(),
+               distill_loss=np.array(loss.item()),
+               distill_grad_norms=np.array([student.unet.get_parameter(n).grad.norm().item() for n in names], dtype=np.float64))
+
+
 def main():
     S, B, steps = 64, 2, 2
     torch.manual_seed(0)
@@ -108,6 +145,7 @@ def main():
     out["delta_norms"] = np.array([(sd1[n] - sd0[n]).norm().item() for n in names], dtype=np.float64)
     out["ema_delta_norms"] = np.array([(ema.shadow["unet." + n] - sd0[n]).norm().item() for n in names], dtype=np.float64)
     out["weights_sha256"] = np.array(sd_digest(sd0))
+    distill(out)
     np.savez_compressed(os.path.join(HERE, "train_kat.npz"), **out)
     print("wrote train_kat.npz", os.path.getsize(os.path.join(HERE, "train_kat.npz")) // 1024, "KiB")
 

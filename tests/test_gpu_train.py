@@ -232,3 +232,59 @@ def test_unet_forward_autograd_upstream_gradient():
     got = {n: p.grad.cpu() for n, p in m.named_parameters()}
     rows, _ = _report(got, {k: g.cpu() for k, g in zip(sd, ref)})
     assert not [(r[3], r[0]) for r in rows if r[0] > 3e-2 and r[2] > 1e-6]
+
+
+def test_distillation_loss_kat_from_reference():
+    """LowLightLCMDistillation.consistency_distillation_loss (teacher DDIM jump, EMA target, student Huber on x0) against the
+    loss and per-parameter student gradient norms recorded from the unmodified reference wrapper; fp32 plans."""
+    from cv_diffusion_model_b200 import LowLightDiffusion, LowLightLCMDistillation
+    kat = _kat()
+    torch.manual_seed(0)
+    teacher = LowLightDiffusion(unet_variant="small", image_size=64, num_inference_steps=4, precision="fp32")
+    randomise_affine(teacher.unet)
+    torch.manual_seed(1)
+    student = LowLightDiffusion(unet_variant="small", image_size=64, num_inference_steps=4, precision="fp32")
+    randomise_affine(student.unet, seed=2)
+    wrap = LowLightLCMDistillation(teacher, student).cuda()
+    with torch.no_grad():
+        for e in wrap.ema_student.parameters():
+            e.mul_(0.98)
+    assert not any(p.requires_grad for p in wrap.teacher.parameters()) and not any(p.requires_grad for p in wrap.ema_student.parameters())
+    low, high = torch.from_numpy(kat["distill_low"]).cuda(), torch.from_numpy(kat["distill_high"]).cuda()
+    noise, idx = torch.from_numpy(kat["distill_noise"]).cuda(), torch.from_numpy(kat["distill_idx"]).cuda()
+    loss = wrap.consistency_distillation_loss(low, high, num_inference_steps=4, noise=noise, idx=idx)
+    loss.backward()
+    want = float(kat["distill_loss"])
+    assert abs(loss.item() - want) <= 1e-4 * want, (loss.item(), want)
+    names = [str(n) for n in kat["names"]]
+    params = dict(wrap.student.unet.named_parameters())
+    norms = np.array([params[n].grad.norm().item() for n in names])
+    scale = kat["distill_grad_norms"]
+    dev = np.abs(norms - scale) / (scale + 1e-12)
+    print(f"distillation KAT: loss {loss.item():.6f} vs {want:.6f}; worst per-parameter gradient-norm deviation {dev.max():.2e}")
+    assert np.all(np.abs(norms - scale) <= 3e-2 * scale + 1e-9), dev.max()
+    # update_ema moves the target towards the student and the native plans pick the new weights up (:317-323)
+    before = [p.detach().clone() for p in wrap.ema_student.parameters()]
+    wrap.update_ema(0.5)
+    for b_, e, s_ in zip(before, wrap.ema_student.parameters(), wrap.student.parameters()):
+        assert torch.allclose(e, 0.5 * b_ + 0.5 * s_.detach(), atol=1e-6)
+    loss2 = wrap.consistency_distillation_loss(low, high, num_inference_steps=4, noise=noise, idx=idx)
+    assert loss2.item() != loss.item()
+
+
+def test_return_features_surface():
+    """`unet(x, t, return_features=True)` -> (eps, [output of every decoder level]) like the reference (:595-605)."""
+    from oracle import unet_oracle
+    m = seeded_unet("small", 256, affine=True).cuda().eval()
+    x = torch.randn(2, 6, 64, 64, generator=torch.Generator().manual_seed(4))
+    t = torch.tensor([739, 19])
+    eps, feats = m(x.cuda(), t.cuda(), return_features=True)
+    taps = {}
+    with torch.no_grad():
+        want = unet_oracle.unet_forward({k: v.cpu() for k, v in m.state_dict().items()}, m.config, x, t,
+                                        tap=lambda k, v: taps.__setitem__(k.rstrip("."), v))
+    from tests.util import rel_rms
+    assert rel_rms(eps.cpu(), want) <= 0.03
+    assert [tuple(f.shape) for f in feats] == [(2, 256, 8, 8), (2, 128, 16, 16), (2, 64, 32, 32), (2, 32, 64, 64)]
+    for li, f in enumerate(feats):
+        assert rel_rms(f.cpu(), taps[f"decoder_blocks.{li}.2.out"]) <= 0.03
