@@ -189,6 +189,9 @@ void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const voi
                        void* du, double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st);
 void launch_wgrad_1x1(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
                       int num_sms, cudaStream_t st);
+// the same on the tensor cores (wgrad_tc.cu, bf16 plan); non-zero = shape not covered, use the CUDA-core kernel
+int launch_wgrad_tc(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
+                    int num_sms, cudaStream_t st);
 void launch_wgrad_conv3(const void* in, int dti, const void* dY, int dty, float* dW, float* dbias, int N, int Hin, int Win, int Ci,
                         int Co, int mode, int num_sms, cudaStream_t st);
 void launch_upsample2x_any(const void* in, void* out, int dt, int N, int H, int W, int C, cudaStream_t st);

@@ -606,6 +606,7 @@ struct Builder {
             col += xv.part[i]->C;
           }
           gp.Ktot = Ch + Ci; gp.P = P; gp.M = (long long)n * P; gp.Nc = Co;
+          if (pl->tc && launch_wgrad_tc(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st) == 0) return;
           launch_wgrad_1x1(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st);
         });
       }
@@ -678,6 +679,7 @@ struct Builder {
             col += xv.part[i]->C;
           }
           gp.Ktot = Ci; gp.P = P; gp.M = (long long)n * P; gp.Nc = Ch;
+          if (pl->tc && launch_wgrad_tc(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st) == 0) return;
           launch_wgrad_1x1(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st);
         });
       }
@@ -796,7 +798,8 @@ struct Builder {
             int dst_ld[LCM_MAX_SEGS] = {inner, 0, 0, 0};
             gp.nseg = 1; gp.seg[0].A = c.a + o->off; gp.seg[0].K = inner; gp.seg[0].ld = inner; gp.seg[0].mode = XF_NONE;
             gp.Ktot = inner; gp.P = P; gp.M = (long long)n * P; gp.Nc = C;
-            launch_wgrad_1x1(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st);
+            if (pl->tc && launch_wgrad_tc(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st) == 0) return;
+          launch_wgrad_1x1(gp, seg_dt, c.g + du, dtg, dst, dst_ld, pl->num_sms, st);
           });
         }
         const size_t dO = galloc(M * inner * gsz);
@@ -822,6 +825,7 @@ struct Builder {
             gp.nseg = 1; gp.seg[0].A = c.a + x->off; gp.seg[0].K = C; gp.seg[0].ld = C; gp.seg[0].mode = XF_AFFINE;
             gp.seg[0].coef = (const float2*)(c.f + gnn.coef); gp.seg[0].coef_ld = C; gp.seg[0].coef_off = 0;
             gp.Ktot = C; gp.P = P; gp.M = (long long)n * P; gp.Nc = 3 * inner;
+            if (pl->tc && launch_wgrad_tc(gp, seg_dt, c.g + dqkv, dtg, dst, dst_ld, pl->num_sms, st) == 0) return;
             launch_wgrad_1x1(gp, seg_dt, c.g + dqkv, dtg, dst, dst_ld, pl->num_sms, st);
           });
         }
