@@ -71,8 +71,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_enhance_fn(batch, threads):
-    """The reference algorithm on CPU: oracle port (fp32 torch ops, same as the reference's own CPU path)."""
+def cpu_enhance_fn(batch, threads, inputs=None):
+    """The reference algorithm on CPU: oracle port (fp32 torch ops, same as the reference's own CPU path).
+    inputs = (low, lat0, noises[steps-1]) host tensors to run on (the bench's own image 0 for the parity block)."""
     import torch
     from cv_diffusion_model_b200 import LowLightDiffusion
     from oracle import lcm_oracle
@@ -81,11 +82,115 @@ def cpu_enhance_fn(batch, threads):
     pipe = LowLightDiffusion(unet_variant=VARIANT, image_size=SIZE, num_inference_steps=LCM_STEPS)
     sd = {k[5:]: v for k, v in pipe.state_dict().items()}
     cfg = pipe.unet.config
-    low = torch.rand(batch, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(1234)) * 0.4 - 1
-    lat0 = torch.randn(batch, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(9))
-    torch.manual_seed(5)
-    noises = [torch.randn(batch, 3, SIZE, SIZE) for _ in range(LCM_STEPS - 1)]
-    return lambda: lcm_oracle.enhance(sd, cfg, low, lat0, noises, LCM_STEPS)
+    if inputs is None:
+        low = torch.rand(batch, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(1234)) * 0.4 - 1
+        lat0 = torch.randn(batch, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(9))
+        torch.manual_seed(5)
+        noises = [torch.randn(batch, 3, SIZE, SIZE) for _ in range(LCM_STEPS - 1)]
+    else:
+        low, lat0, noises = inputs
+    return lambda: lcm_oracle.enhance(sd, cfg, low, lat0, list(noises), LCM_STEPS, return_all=True)
+
+
+def gpu_eager_leg(dev, B):
+    """the bar to beat is PyTorch eager of the reference's op sequence on the SAME B200 (the oracle port: the
+    same torch ops in the same order, library kernels).  One timed 4-step enhance of the bench batch per mode, after one
+    warm-up call.  Test infrastructure measured beside the product, never part of it."""
+    import torch
+    from cv_diffusion_model_b200 import LowLightDiffusion
+    from oracle import lcm_oracle
+    torch.manual_seed(0)
+    pipe = LowLightDiffusion(unet_variant=VARIANT, image_size=SIZE, num_inference_steps=LCM_STEPS)
+    cfg = pipe.unet.config
+    sd = {k[5:]: v.detach().to(dev) for k, v in pipe.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    low = (torch.rand(B, 3, SIZE, SIZE, generator=g) * 0.4 - 1).to(dev)
+    lat = torch.randn(B, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(9)).to(dev)
+    noises = [torch.randn(B, 3, SIZE, SIZE, generator=g).to(dev) for _ in range(LCM_STEPS - 1)]
+    out = {"what": "oracle port (reference op sequence) as PyTorch eager on this GPU, 1 timed call after 1 warm-up, "
+                   f"batch {B}", "unit": "images/s"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tag, tf32, autocast in (("fp32_tf32_off", False, False), ("bf16_autocast", True, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+
+            def once():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return lcm_oracle.enhance(sd, cfg, low, lat, noises, LCM_STEPS)
+            once()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            once()
+            b.record()
+            torch.cuda.synchronize()
+            out[tag] = B / (a.elapsed_time(b) / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+# images/s/GPU at the speed of light of SURVEY App. A's accounting (BASELINE.md table), for the other named configs
+OTHER = {
+    "config3_base512_8step": dict(variant="base", size=512, batch=32, steps=8, groupnorm="gcd", sol=116.0,
+                                  workload="Base* (gcd-GroupNorm patch), 512x512, 32 images per GPU, 8-step LCM enhance"),
+    "config4_large1024_4step": dict(variant="large", size=1024, batch=8, steps=4, groupnorm="strict", sol=33.0,
+                                    workload="Large, 1024x1024, 8 images per GPU, 4-step LCM enhance"),
+}
+
+
+def other_configs_leg(dev, world, rank, timed, hbm_gbs):
+    """Bounded runs (1 warm-up + 2 timed enhance calls) of BASELINE configs 3 and 4 at their per-GPU shapes, and one
+    data-parallel training step config (config 5) — so that these get driver-side numbers too."""
+    import torch
+    from cv_diffusion_model_b200 import LowLightDiffusion
+    from cv_diffusion_model_b200.engine import get_engine
+    res = {}
+    for tag, c in OTHER.items():
+        torch.manual_seed(0)
+        pipe = LowLightDiffusion(unet_variant=c["variant"], image_size=c["size"], num_inference_steps=c["steps"],
+                                 groupnorm=c["groupnorm"], precision="bf16").to(dev).eval()
+        B, S = c["batch"], c["size"]
+        g = torch.Generator().manual_seed(77 + rank)
+        low = (torch.rand(B, 3, S, S, generator=g) * 0.4 - 1).to(dev)
+        lat0 = torch.randn(B, 3, S, S, generator=g).to(dev)
+        noises = torch.randn(c["steps"] - 1, B, 3, S, S, generator=g).to(dev)
+        fn = lambda: pipe.enhance(low, latents=lat0, noises=noises)
+        fn()
+        n = 2
+        ms = timed(fn, n)
+        eng = get_engine(pipe.unet, B, S, S, dev)
+        v = world * B * n / (ms / 1e3)
+        gbs = v / world * c["steps"] * eng.algorithmic_bytes / B / 1e9
+        res[tag] = {"workload": c["workload"], "value": v, "unit": "images/s", "ms_per_enhance": ms / n,
+                    "whole_model_algorithmic_gbs": gbs, "whole_model_frac_of_hbm": gbs / hbm_gbs,
+                    "frac_of_speed_of_light": v / world / c["sol"], "timed_calls": n}
+        pipe.unet.invalidate_engines()
+        del pipe, low, lat0, noises
+        torch.cuda.empty_cache()
+    # config 5: Small data-parallel training step, 256x256, 64 image pairs per GPU, bf16, NCCL gradient all-reduce
+    from cv_diffusion_model_b200.training import NativeTrainer
+    torch.manual_seed(0)
+    pipe = LowLightDiffusion(unet_variant=VARIANT, image_size=SIZE, num_inference_steps=LCM_STEPS, precision="bf16").to(dev).train()
+    tr = NativeTrainer(pipe, batch=64, precision="bf16")
+    g = torch.Generator().manual_seed(5 + rank)
+    high = (torch.rand(64, 3, SIZE, SIZE, generator=g) * 2 - 1).to(dev)
+    low = ((high + 1) / 2) ** 3 * 2 - 1
+    losses = [tr.train_step(low, high).item()]
+    n = 2
+    ms = timed(lambda: losses.append(tr.train_step(low, high).item()), n)
+    res["config5_small256_train_step"] = {
+        "workload": "Small, 256x256, 64 image pairs per GPU, one training step = loss forward + backward + gradient all-reduce "
+                    "(NCCL, bucketed, overlapped) + clip + AdamW + EMA, bf16 activations / fp32 master weights",
+        "value": world * 64 * n / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / n, "global_batch": 64 * world,
+        "losses": losses, "timed_steps": n, "backward_ops": tr.engine.num_backward_ops}
+    tr.engine.close()
+    del tr, pipe
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
@@ -94,21 +199,30 @@ def run_reference(args):
         return
     import torch
     threads = os.cpu_count() or 1
+    # a step of this arm is a BOUNDED SAMPLE of the workload: one enhance call of `b` images (same variant / size / LCM steps);
+    # the CPU needs ~1 s per image, so the sample is sized for --steps K --warmup W to end within a few minutes
     b = 2
+    warm = max(0, args.warmup)
+    steps = max(1, args.steps)
+    budget_calls = 40                      # ~2 s per call on 16 cores
+    if warm + steps > budget_calls:
+        warm = max(1, min(warm, budget_calls // 4))
+        steps = max(1, budget_calls - warm)
     fn = cpu_enhance_fn(b, threads)
-    for _ in range(max(1, min(args.warmup, 1))):
+    for _ in range(warm):
         fn()
-    steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     dt = (time.perf_counter() - t0) / steps
     v = b / dt
-    sample = f"{steps} timed enhance calls of batch {b} (same variant/size/steps), torch {torch.__version__} CPU fp32"
+    sample = (f"{steps} timed enhance calls of batch {b} after {warm} warm-up calls (same variant/size/LCM steps as the GPU arm; "
+              f"oracle port = the reference's torch CPU ops), torch {torch.__version__} CPU fp32")
+    workload = f"Small variant, {SIZE}x{SIZE}, {LCM_STEPS}-step LCM enhance (BASELINE config[1]); CPU sample: batch {b} per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": b},
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "batch_per_step": b},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -122,6 +236,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the gpu_eager / other_configs / fp32 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -216,7 +331,8 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one representative launch)
     traffic, traffic_of = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tname = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+        tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
         if top in tj:
             traffic, traffic_of = tj[top]["dram_bytes_per_launch"], tj[top]
     except Exception:
@@ -232,19 +348,50 @@ def main():
                                    "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["ms"] else 0} for k, v in by_kernel.items()}}
     launches = LCM_STEPS * eng.launches_per_forward
 
-    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ---------------------------------
-    cpu = None
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) + parity of the bench's own image 0 --------
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        fn = cpu_enhance_fn(1, threads)
+        inputs = (low_host[:1].clone(), lat0[:1].cpu(), noises[:, :1].cpu())
+        fn = cpu_enhance_fn(1, threads, inputs)
         fn()
         t0 = time.perf_counter()
         n = 2
         for _ in range(n):
-            fn()
+            want, trace = fn()
         dt = (time.perf_counter() - t0) / n
         cpu = {"value": 1 / dt, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{n} timed 4-step enhance calls of batch 1 at 256x256 after 1 warm-up (oracle port, torch CPU fp32)"}
+               "sample": f"{n} timed 4-step enhance calls of batch 1 (image 0 of the bench batch) at 256x256 after 1 warm-up "
+                         "(oracle port, torch CPU fp32)"}
+        # the GPU run of the timed region on the same image: teacher-forced eps of step 0 and the free-running loop
+        import math
+        res = pipe.enhance(low, latents=lat0, noises=noises, return_intermediate=True)
+        t0_ = torch.full((B,), int(pipe.scheduler._host_timesteps[0]), device=dev, dtype=torch.long)
+        with torch.no_grad():
+            eps0 = pipe.unet(torch.cat([lat0, low], dim=1), t0_)[:1].cpu()
+        pre = res.intermediate[-1][:1].cpu()
+        ref_eps, ref_pre = trace[0][0], trace[-1][1]
+        mse = (pre.double() - ref_pre.double()).pow(2).mean().item()
+        parity = {"image": 0, "vs": "oracle port fp32 (pinned bit-for-bit against the reference)",
+                  "eps_rel_rms_step0": ((eps0.double() - ref_eps.double()).pow(2).mean().sqrt() / ref_eps.double().pow(2).mean().sqrt()).item(),
+                  "preclamp_psnr_db_peak2": 10 * math.log10(4.0 / mse) if mse > 0 else None,
+                  "enhanced_max_abs": (res.enhanced[:1].cpu() - want).abs().max().item(),
+                  "gates": "eps rel-RMS <= 3 %, PSNR >= 33 dB (tests/test_gpu_parity.py)"}
+
+    # ---- extras: the eager-GPU bar, fp32 mode once, the other named configs (bounded) ------------------------
+    gpu_eager, fp32_mode, others = None, None, None
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            gpu_eager = gpu_eager_leg(dev, B)
+            pipe32 = LowLightDiffusion(unet=pipe.unet, image_size=SIZE, num_inference_steps=LCM_STEPS, precision="fp32")
+            f32 = lambda: pipe32.enhance(low, latents=lat0, noises=noises)
+            f32()
+            fp32_mode = {"value": B / (timed(f32, 1) / 1e3), "unit": "images/s",
+                         "what": "precision='fp32' (verification mode: fp32 activations, CUDA-core GEMMs), 1 timed call"}
+            pipe.unet.precision = "bf16"
+        pipe.unet.invalidate_engines()
+        torch.cuda.empty_cache()
+        others = other_configs_leg(dev, world, rank, timed, hbm_gbs)
 
     if rank == 0:
         print(json.dumps({
@@ -252,11 +399,14 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu_per_step": B, "lcm_steps": LCM_STEPS,
+                       "storage": "residual stream bf16, hidden tensors of every block fp16, latents / statistics fp32, "
+                                  "fp32 accumulation (tcgen05)",
                        "l2": "activations (GBs per forward) far exceed the 126 MB L2; no flush needed",
                        "weights": "random-init (torch.manual_seed(0)), the reference's layer order"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": low_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, "gpu_eager": gpu_eager, "fp32_mode": fp32_mode, "other_configs": others,
         }))
     if world > 1:
         dist.destroy_process_group()
