@@ -934,6 +934,11 @@ struct Builder {
         const size_t g_w = wg(wname + ".weight"), g_b = wg(wname + ".bias");
         // weight + bias gradient; the fp32 plan recomputes the bilinear blend inside the loader (mode UP2 on the low-res input)
         pushb(name + ".wgrad", "wgrad_simt", {wname + ".weight", wname + ".bias"}, [=](const RunCtx& c, cudaStream_t st) {
+          if (pl->tc && mode == CONV_S1 &&
+              launch_wgrad_conv3_tc(c.a + x->off, c.g + dY, c.wg + g_w, n, Hin, Win, C, C, pl->num_sms, st) == 0) {
+            launch_colsum(c.g + dY, dtg, (long long)n * Ho * Wo, C, c.wg + g_b, st);
+            return;
+          }
           launch_wgrad_conv3(c.a + x->off, dta, c.g + dY, dtg, c.wg + g_w, c.wg + g_b, n, Hin, Win, C, C, mode, pl->num_sms, st);
         });
         if (mode_in == CONV_S2) {

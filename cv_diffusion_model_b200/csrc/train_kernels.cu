@@ -119,21 +119,34 @@ __global__ void __launch_bounds__(256) bwd_mask_reduce_kernel(void* g, int dtg, 
       for (int j = 0; j < 8; ++j) ab[j] = coef[(size_t)n * coef_ld + goff + cv * 8 + j];
     }
     if (act) {
-      for (int p = p0 + G.lane; p < p1; p += G.pl) {
-        const size_t row = (size_t)n * P + p;
-        float gv[8], xv[8];
-        ld8(g, dtg, row * ldg + goff + cv * 8, gv);
-        ld8(x, dtx, row * ldx + xoff + cv * 8, xv);
-        if (mode == 1) {
+      // four pixels in flight per thread (all loads issued before the first use)
+      for (int pb = p0 + G.lane; pb < p1; pb += 4 * G.pl) {
+        float gv[4][8], xv[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float u = fmaf(ab[j].x, xv[j], ab[j].y);
-            gv[j] = (u > 0.f && u < 6.f) ? gv[j] : 0.f;
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int p = pb + u4 * G.pl;
+          if (p < p1) {
+            const size_t row = (size_t)n * P + p;
+            ld8(g, dtg, row * ldg + goff + cv * 8, gv[u4]);
+            ld8(x, dtx, row * ldx + xoff + cv * 8, xv[u4]);
           }
-          st8(g, dtg, row * ldg + goff + cv * 8, gv);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += gv[j]; s2[j] = fmaf(gv[j], xv[j], s2[j]); }
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int p = pb + u4 * G.pl;
+          if (p >= p1) continue;
+          const size_t row = (size_t)n * P + p;
+          if (mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float u = fmaf(ab[j].x, xv[u4][j], ab[j].y);
+              gv[u4][j] = (u > 0.f && u < 6.f) ? gv[u4][j] : 0.f;
+            }
+            st8(g, dtg, row * ldg + goff + cv * 8, gv[u4]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] += gv[u4][j]; s2[j] = fmaf(gv[u4][j], xv[u4][j], s2[j]); }
+        }
       }
     }
     const int ncv = min(G.cvp, cvecs - cvb);
@@ -165,26 +178,33 @@ __global__ void __launch_bounds__(256) bwd_affine3_kernel(const void* g, int dtg
     float4 k[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) k[j] = coef4[(size_t)n * coef_ld + coff + cv * 8 + j];
-    for (int p = p0 + G.lane; p < p1; p += G.pl) {
-      const size_t row = (size_t)n * P + p;
-      float gv[8], xv[8], o[8];
-      ld8(g, dtg, row * ldg + goff + cv * 8, gv);
-      ld8(x, dtx, row * ldx + xoff + cv * 8, xv);
+    for (int pb = p0 + G.lane; pb < p1; pb += 2 * G.pl) {     // two pixels in flight per thread
+      float gv[2][8], xv[2][8], rv[2][8], dv[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(k[j].x, gv[j], fmaf(k[j].y, xv[j], k[j].z));
-      if (r) {
-        float rv[8];
-        ld8(r, dtr, row * ldr + roff + cv * 8, rv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += rv[j];
+      for (int u2 = 0; u2 < 2; ++u2) {
+        const int p = pb + u2 * G.pl;
+        if (p < p1) {
+          const size_t row = (size_t)n * P + p;
+          ld8(g, dtg, row * ldg + goff + cv * 8, gv[u2]);
+          ld8(x, dtx, row * ldx + xoff + cv * 8, xv[u2]);
+          if (r) ld8(r, dtr, row * ldr + roff + cv * 8, rv[u2]);
+          if (accumulate) ld8(dst, dtd, row * ldd + doff + cv * 8, dv[u2]);
+        }
       }
-      if (accumulate) {
-        float dv[8];
-        ld8(dst, dtd, row * ldd + doff + cv * 8, dv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += dv[j];
+      for (int u2 = 0; u2 < 2; ++u2) {
+        const int p = pb + u2 * G.pl;
+        if (p >= p1) continue;
+        const size_t row = (size_t)n * P + p;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = fmaf(k[j].x, gv[u2][j], fmaf(k[j].y, xv[u2][j], k[j].z));
+          if (r) o[j] += rv[u2][j];
+          if (accumulate) o[j] += dv[u2][j];
+        }
+        st8(dst, dtd, row * ldd + doff + cv * 8, o);
       }
-      st8(dst, dtd, row * ldd + doff + cv * 8, o);
     }
   }
 }
@@ -391,17 +411,18 @@ void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* d
 //   v   = relu6(a2 h1 + b2)                       (coef2, zero outside the image: the forward conv pads v)
 //   dv[p] = sum_tap w[tap] dh2[p - off(tap)] ;  du = dv [0 < a2 h1 + b2 < 6]
 //   dW[c][tap] += sum_p dh2[p] v[p + off(tap)] ;  S1 += sum_p du ; S2 += sum_p du h1
-// A block owns a 32-channel slice and a contiguous range of (image, 16x16 tile) items; weight gradients stay in
-// registers over the whole range, the per-image sums are flushed when the image changes.
+// A block owns a 32-channel slice and a contiguous range of (image, 8x16 tile) items; weight gradients stay in
+// registers over the whole range, the per-image sums are flushed when the image changes.  Two fp32 halo tiles of
+// 10 x 18 x 32 = 46 KB: four blocks per SM overlap one another's load and compute phases.
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float2* __restrict__ coef_se,
                                                          const void* __restrict__ h1, int dth, const float2* __restrict__ coef2,
                                                          const float* __restrict__ w, void* __restrict__ du,
                                                          double* __restrict__ t12, float* __restrict__ dW, int N, int H, int W,
                                                          int C, int tilesX, int tilesY, int items_per_block) {
-  constexpr int TS = 16, HS = TS + 2, CB = 32;
+  constexpr int TSY = 8, TSX = 16, HSY = TSY + 2, HS = TSX + 2, CB = 32;
   extern __shared__ __align__(16) float dsm[];
-  float* tg = dsm;                     // [HS*HS*CB] dh2 halo tile
-  float* tv = dsm + HS * HS * CB;      // [HS*HS*CB] v halo tile
+  float* tg = dsm;                      // [HSY*HS*CB] dh2 halo tile
+  float* tv = dsm + HSY * HS * CB;      // [HSY*HS*CB] v halo tile
   __shared__ float s_w[9 * CB];
   __shared__ float s_red[8][2 * CB];
   const int tid = threadIdx.x;
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict_
       if (cur_n >= 0) flush(cur_n);
       cur_n = n;
     }
-    const int ty0 = (tile / tilesX) * TS, tx0 = (tile % tilesX) * TS;
+    const int ty0 = (tile / tilesX) * TSY, tx0 = (tile % tilesX) * TSX;
     float2 cse[8], c2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -458,7 +479,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict_
       c2[j] = coef2[(size_t)n * C + c0 + cg * 8 + j];
     }
     __syncthreads();   // previous tile fully consumed
-    for (int i = tid; i < HS * HS * 4; i += 256) {
+    for (int i = tid; i < HSY * HS * 4; i += 256) {
       const int px = i >> 2;
       const int yy = px / HS, xx = px - yy * HS;
       const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
@@ -484,11 +505,11 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict_
       e[1] = make_float4(b[4], b[5], b[6], b[7]);
     }
     __syncthreads();
-    const int strip = tid >> 2;
-    const int row = strip >> 2, xs = (strip & 3) * 4;
+    const int strip = tid >> 2;           // 64 strips of 2 pixels: 8 rows x 8 strips
+    const int row = strip >> 3, xs = (strip & 7) * 2;
     const int gy = ty0 + row;
-#pragma unroll 1
-    for (int px = 0; px < 4; ++px) {
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
       const int gx = tx0 + xs + px;
       if (gy >= H || gx >= W) continue;
       float dv[8];
@@ -567,15 +588,15 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict_
 
 void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
                        void* du, double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st) {
-  const int tilesX = (W + 15) / 16, tilesY = (H + 15) / 16;
+  const int tilesX = (W + 15) / 16, tilesY = (H + 7) / 8;
   const long long total = (long long)N * tilesX * tilesY;
   const int cblocks = C / 32;
-  long long bx = ((long long)num_sms * 4 + cblocks - 1) / cblocks;   // ~4 blocks per SM in total
+  long long bx = ((long long)num_sms * 8 + cblocks - 1) / cblocks;   // ~8 blocks per SM in total (4 resident)
   if (bx < 1) bx = 1;
   if (bx > total) bx = total;
   const int per = (int)((total + bx - 1) / bx);
   bx = (total + per - 1) / per;
-  const size_t smem = (size_t)2 * 18 * 18 * 32 * sizeof(float);
+  const size_t smem = (size_t)2 * 10 * 18 * 32 * sizeof(float);
   if (ensure_dyn_smem_fn(dwconv_bwd_kernel, smem)) return;
   dwconv_bwd_kernel<<<dim3((unsigned)bx, cblocks), 256, smem, st>>>(dq, dtg, coef_se, h1, dth, coef2, w, du, t12, dW, N, H, W, C,
                                                               tilesX, tilesY, per);
@@ -760,6 +781,44 @@ void launch_wgrad_conv3(const void* in, int dti, const void* dY, int dty, float*
   dim3 grid; long long rows;
   wgrad_grid(M, Co, 9 * Ci, num_sms, grid, rows);
   wgrad_simt_kernel<WLoaderConv3><<<grid, 256, 0, st>>>(ld, dY, dty, d, M, Co, 9 * Ci, rows);
+}
+
+// bias gradient of a conv: out[c] += sum over rows of g[row][c]
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ g, int dt, long long rows, int C, float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int cvecs = C / 8;
+  RowGeom G(cvecs);
+  const long long r0 = (long long)blockIdx.x * kRowChunk, r1 = r0 + kRowChunk < rows ? r0 + kRowChunk : rows;
+  for (int cvb = 0; cvb < cvecs; cvb += G.cvp) {
+    const int cv = cvb + G.cv;
+    const bool act = G.active && cv < cvecs;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (act) {
+      for (long long r = r0 + G.lane; r < r1; r += G.pl) {
+        float v[8];
+        ld8(g, dt, (size_t)r * C + cv * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
+      }
+    }
+    const int ncv = min(G.cvp, cvecs - cvb);
+    __syncthreads();
+    if (G.active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(G.lane * G.cvp + G.cv) * 8 + j] = act ? s[j] : 0.f;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncv * 8; t += 256) {
+      float a = 0.f;
+      for (int l = 0; l < G.pl; ++l) a += red[l * G.cvp * 8 + t];
+      atomicAdd(out + cvb * 8 + t, a);
+    }
+  }
+}
+void launch_colsum(const void* g, int dt, long long rows, int C, float* out, cudaStream_t st) {
+  colsum_kernel<<<(unsigned)((rows + kRowChunk - 1) / kRowChunk), 256, 0, st>>>(g, dt, rows, C, out);
 }
 
 // =================================================================================================

@@ -52,12 +52,23 @@ struct WTParams {
   int n_mblocks, n_nblocks, nychunks, Nc;
   int m_tiles, P, splits, stages;
   uint32_t stage_bytes, y_off, coef_smem_off, misc_off;
+  // dense 3x3 conv (stride 1): achunk's segment field is the TAP, the A chunk of tap (ky, kx) is the image box shifted by
+  // (kx - 1, ky - 1) (out-of-image elements zero-filled by TMA = the conv's padding); dW layout [Co][Ci][3][3]
+  int conv, Wimg, box_w, box_h, Ci;
+  CUtensorMap tmap_img;
+  float* conv_dst;
 };
 
 __device__ __forceinline__ void tma_load_2d_wt(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_wt(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
 // MN-major operand, 128-byte swizzle (see gemm_expand.cu): 64 channels contiguous, 8-pixel groups 1024 B apart along K,
@@ -178,9 +189,9 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
       const bool lane_ok = ci < nA;
       const uint32_t cd = p.achunk[a0 + (lane_ok ? ci : 0)];
       const int s = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = p.achunk_c0[a0 + (lane_ok ? ci : 0)];
-      float* dst = p.dst[s];
+      float* dst = p.conv ? p.conv_dst : p.dst[s];
       const bool ok = lane_ok && cc < kvalid && dst != nullptr;
-      const int ldd = p.dst_ld[s];
+      const int ldd = p.conv ? 0 : p.dst_ld[s];
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
       const int ncols = nY * 64;
       for (int c = 0; c < ncols; c += 16) {
@@ -191,7 +202,10 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = y0 * 64 + c + j;
-            if (n < p.Nc) atomicAdd(dst + (size_t)n * ldd + c0 + cc, __uint_as_float(r[j]));
+            if (n < p.Nc) {
+              if (p.conv) atomicAdd(dst + ((size_t)n * p.Ci + c0 + cc) * 9 + s, __uint_as_float(r[j]));   // s = tap
+              else atomicAdd(dst + (size_t)n * ldd + c0 + cc, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -206,9 +220,22 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
       if (elect_one()) {
         mbar_expect_tx(raw_bar(stage), bytes);
         const uint32_t sb = sbase + (uint32_t)stage * p.stage_bytes;
-        for (int ci = 0; ci < nA; ++ci) {
-          const uint32_t cd = p.achunk[a0 + ci];
-          tma_load_2d_wt(sb + (uint32_t)ci * kChunkWT, &p.tmap_a[cd & 0xff], (int)p.achunk_c0[a0 + ci], t * 128, raw_bar(stage));
+        if (p.conv) {
+          const int tpi = p.P >> 7;
+          const int n = t / tpi, tin = t - n * tpi;
+          int x0, y0;
+          if (p.box_h == 1) { const int tpr = p.Wimg >> 7; y0 = tin / tpr; x0 = (tin - y0 * tpr) << 7; }
+          else { y0 = tin * p.box_h; x0 = 0; }
+          for (int ci = 0; ci < nA; ++ci) {
+            const uint32_t cd = p.achunk[a0 + ci];
+            const int tap = cd & 0xff, ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d_wt(sb + (uint32_t)ci * kChunkWT, &p.tmap_img, (int)p.achunk_c0[a0 + ci], x0 + kx - 1, y0 + ky - 1, n, raw_bar(stage));
+          }
+        } else {
+          for (int ci = 0; ci < nA; ++ci) {
+            const uint32_t cd = p.achunk[a0 + ci];
+            tma_load_2d_wt(sb + (uint32_t)ci * kChunkWT, &p.tmap_a[cd & 0xff], (int)p.achunk_c0[a0 + ci], t * 128, raw_bar(stage));
+          }
         }
         for (int j = 0; j < nY; ++j)
           tma_load_2d_wt(sb + p.y_off + (uint32_t)j * kChunkWT, &p.tmap_y, (y0 + j) * 64, t * 128, raw_bar(stage));
@@ -249,6 +276,8 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
+int launch_common(WTParams& p, int num_sms, cudaStream_t st);
+
 }  // namespace
 
 // Returns 0 when launched, non-zero when the shape is not covered (the caller falls back to the CUDA-core kernel):
@@ -287,10 +316,16 @@ int launch_wgrad_tc(const GemmParams& g, const int* seg_dt, const void* dY, int 
   }
   if (!tmap_rows128(dY, g.M, g.Nc, g.Nc, TMAP_BF16, &p.tmap_y)) return -3;
   p.n_mblocks = nmb;
-  p.nychunks = (g.Nc + 63) / 64;
-  p.n_nblocks = (p.nychunks + 3) / 4;
   p.Nc = g.Nc;
   p.m_tiles = (int)(g.M / 128); p.P = g.P;
+  return launch_common(p, num_sms, st);
+}
+
+namespace {
+int launch_common(WTParams& p, int num_sms, cudaStream_t st) {
+  const int nmb = p.n_mblocks;
+  p.nychunks = (p.Nc + 63) / 64;
+  p.n_nblocks = (p.nychunks + 3) / 4;
   int maxA = 1;
   for (int i = 0; i < nmb; ++i) if (p.mb_count[i] > maxA) maxA = p.mb_count[i];
   const int maxY = p.nychunks < 4 ? p.nychunks : 4;
@@ -312,6 +347,46 @@ int launch_wgrad_tc(const GemmParams& g, const int* seg_dt, const void* dY, int 
   if (ensure_dyn_smem_fn(wgrad_tc_kernel, kSmemLimitWT)) return -2;
   wgrad_tc_kernel<<<out_tiles * splits, kThreadsWT, smem, st>>>(p);
   return 0;
+}
+}  // namespace
+
+// dense 3x3, stride 1, pad 1 (the up-convolutions on the materialised bilinear output): in [N][H][W][Ci] bf16,
+// dY [N][H][W][Co] bf16 -> dW [Co][Ci][3][3] (+=).  Tiles of 128 output pixels must be image boxes (128 | W, or W | 128
+// with whole rows).  Returns non-zero when the shape is not covered.
+int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int num_sms,
+                          cudaStream_t st) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("LCM_NO_WGRAD_TC"); off = (e && atoi(e)) ? 1 : 0; }
+  const long long P = (long long)H * W, M = P * N;
+  const bool boxable = (W >= 128 ? W % 128 == 0 : 128 % W == 0) && P % 128 == 0;
+  if (off || !boxable || Ci % 16 || Co % 16 || M > 0x7fffff00LL || 9 * ((Ci + 63) / 64) > kMaxAChunksWT) return -1;
+  WTParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = 1; p.Wimg = W; p.Ci = Ci; p.conv_dst = dW;
+  p.box_w = W >= 128 ? 128 : W; p.box_h = 128 / p.box_w;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstride[3] = {(cuuint64_t)Ci * 2, (cuuint64_t)W * Ci * 2, (cuuint64_t)H * W * Ci * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.box_w, (cuuint32_t)p.box_h, 1};
+    if (!encode_tmap(&p.tmap_img, TMAP_BF16, 4, in, gdim, gstride, box, true)) return -3;
+  }
+  int nch = 0, nmb = 0;
+  for (int tap = 0; tap < 9; ++tap)
+    for (int c0 = 0; c0 < Ci; c0 += 64) {
+      const int kv = Ci - c0 < 64 ? Ci - c0 : 64;
+      p.achunk_c0[nch] = (uint16_t)c0;
+      p.achunk[nch++] = (uint32_t)tap | ((uint32_t)kv << 8);     // mode XF_NONE, bf16
+    }
+  for (int c = 0; c < nch; c += 2) {
+    p.mb_first[nmb] = (uint8_t)c;
+    p.mb_count[nmb] = (uint8_t)(c + 1 < nch ? 2 : 1);
+    ++nmb;
+  }
+  if (!tmap_rows128(dY, M, Co, Co, TMAP_BF16, &p.tmap_y)) return -3;
+  p.n_mblocks = nmb;
+  p.Nc = Co;
+  p.m_tiles = (int)(M / 128); p.P = (int)P;
+  return launch_common(p, num_sms, st);
 }
 
 }  // namespace lcm
