@@ -597,7 +597,8 @@ void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const voi
   const int per = (int)((total + bx - 1) / bx);
   bx = (total + per - 1) / per;
   const size_t smem = (size_t)2 * 10 * 18 * 32 * sizeof(float);
-  if (ensure_dyn_smem_fn(dwconv_bwd_kernel, smem)) return;
+  // static (3.2 KB) + dynamic (45 KB) shared memory together exceed the 48 KB default: opt in explicitly
+  if (ensure_dyn_smem_fn(dwconv_bwd_kernel, 64 * 1024)) return;
   dwconv_bwd_kernel<<<dim3((unsigned)bx, cblocks), 256, smem, st>>>(dq, dtg, coef_se, h1, dth, coef2, w, du, t12, dW, N, H, W, C,
                                                               tilesX, tilesY, per);
 }
