@@ -75,7 +75,13 @@ struct RowGeom {
     active = lane < pl;
   }
 };
-constexpr int kRowChunk = 2048;   // pixels per block
+constexpr int kRowChunk = 2048;   // pixels per block at the high-resolution levels
+// enough blocks to fill the machine at the low-resolution levels too (a block reduces `chunk` pixels before its atomics)
+static inline int row_chunk(long long P, int N) {
+  int c = kRowChunk;
+  while (c > 128 && ((P + c - 1) / c) * N < 148 * 6) c >>= 1;
+  return c;
+}
 
 // sum v[8] over the pixel lanes of the block and add to dst[(cbase + cv*8 + j) * stride] in fp64.  red: 256*8 floats.
 // ncv: channel vectors of this pass that exist (<= cvp); `act` = this thread holds a valid partial.
@@ -101,10 +107,10 @@ __device__ __forceinline__ void lanes_reduce_add(const float (&v)[8], float* red
 //     g: [N][P][ldg] slice starting at channel goff; x: [N][P][ldx] starting at xoff; coef / t12 indexed with goff.
 __global__ void __launch_bounds__(256) bwd_mask_reduce_kernel(void* g, int dtg, int ldg, int goff, const void* x, int dtx,
                                                               int ldx, int xoff, const float2* __restrict__ coef, int coef_ld,
-                                                              double* __restrict__ t12, int t_ld, int P, int Cs, int mode) {
+                                                              double* __restrict__ t12, int t_ld, int P, int Cs, int mode, int chunk) {
   __shared__ float red[256 * 8];
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * kRowChunk, p1 = min(P, p0 + kRowChunk);
+  const int p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
   const int cvecs = Cs / 8;
   RowGeom G(cvecs);
   for (int cvb = 0; cvb < cvecs; cvb += G.cvp) {
@@ -119,34 +125,21 @@ __global__ void __launch_bounds__(256) bwd_mask_reduce_kernel(void* g, int dtg, 
       for (int j = 0; j < 8; ++j) ab[j] = coef[(size_t)n * coef_ld + goff + cv * 8 + j];
     }
     if (act) {
-      // four pixels in flight per thread (all loads issued before the first use)
-      for (int pb = p0 + G.lane; pb < p1; pb += 4 * G.pl) {
-        float gv[4][8], xv[4][8];
+      for (int p = p0 + G.lane; p < p1; p += G.pl) {
+        const size_t row = (size_t)n * P + p;
+        float gv[8], xv[8];
+        ld8(g, dtg, row * ldg + goff + cv * 8, gv);
+        ld8(x, dtx, row * ldx + xoff + cv * 8, xv);
+        if (mode == 1) {
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int p = pb + u4 * G.pl;
-          if (p < p1) {
-            const size_t row = (size_t)n * P + p;
-            ld8(g, dtg, row * ldg + goff + cv * 8, gv[u4]);
-            ld8(x, dtx, row * ldx + xoff + cv * 8, xv[u4]);
+          for (int j = 0; j < 8; ++j) {
+            const float u = fmaf(ab[j].x, xv[j], ab[j].y);
+            gv[j] = (u > 0.f && u < 6.f) ? gv[j] : 0.f;
           }
+          st8(g, dtg, row * ldg + goff + cv * 8, gv);
         }
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int p = pb + u4 * G.pl;
-          if (p >= p1) continue;
-          const size_t row = (size_t)n * P + p;
-          if (mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float u = fmaf(ab[j].x, xv[u4][j], ab[j].y);
-              gv[u4][j] = (u > 0.f && u < 6.f) ? gv[u4][j] : 0.f;
-            }
-            st8(g, dtg, row * ldg + goff + cv * 8, gv[u4]);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s1[j] += gv[u4][j]; s2[j] = fmaf(gv[u4][j], xv[u4][j], s2[j]); }
-        }
+        for (int j = 0; j < 8; ++j) { s1[j] += gv[j]; s2[j] = fmaf(gv[j], xv[j], s2[j]); }
       }
     }
     const int ncv = min(G.cvp, cvecs - cvb);
@@ -158,8 +151,9 @@ __global__ void __launch_bounds__(256) bwd_mask_reduce_kernel(void* g, int dtg, 
 
 void launch_bwd_mask_reduce(void* g, int dtg, int ldg, int goff, const void* x, int dtx, int ldx, int xoff, const float2* coef,
                             int coef_ld, double* t12, int t_ld, int N, int P, int Cs, int mode, cudaStream_t st) {
-  dim3 grid((P + kRowChunk - 1) / kRowChunk, N);
-  bwd_mask_reduce_kernel<<<grid, 256, 0, st>>>(g, dtg, ldg, goff, x, dtx, ldx, xoff, coef, coef_ld, t12, t_ld, P, Cs, mode);
+  const int chunk = row_chunk(P, N);
+  dim3 grid((P + chunk - 1) / chunk, N);
+  bwd_mask_reduce_kernel<<<grid, 256, 0, st>>>(g, dtg, ldg, goff, x, dtx, ldx, xoff, coef, coef_ld, t12, t_ld, P, Cs, mode, chunk);
 }
 
 // =================================================================================================
@@ -168,9 +162,9 @@ void launch_bwd_mask_reduce(void* g, int dtg, int ldg, int goff, const void* x, 
 __global__ void __launch_bounds__(256) bwd_affine3_kernel(const void* g, int dtg, int ldg, int goff, const void* x, int dtx,
                                                           int ldx, int xoff, const float4* __restrict__ coef4, int coef_ld,
                                                           int coff, const void* r, int dtr, int ldr, int roff, void* dst,
-                                                          int dtd, int ldd, int doff, int accumulate, int P, int Cs) {
+                                                          int dtd, int ldd, int doff, int accumulate, int P, int Cs, int chunk) {
   const int n = blockIdx.y;
-  const int p0 = blockIdx.x * kRowChunk, p1 = min(P, p0 + kRowChunk);
+  const int p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
   const int cvecs = Cs / 8;
   RowGeom G(cvecs);
   if (!G.active) return;
@@ -178,33 +172,26 @@ __global__ void __launch_bounds__(256) bwd_affine3_kernel(const void* g, int dtg
     float4 k[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) k[j] = coef4[(size_t)n * coef_ld + coff + cv * 8 + j];
-    for (int pb = p0 + G.lane; pb < p1; pb += 2 * G.pl) {     // two pixels in flight per thread
-      float gv[2][8], xv[2][8], rv[2][8], dv[2][8];
+    for (int p = p0 + G.lane; p < p1; p += G.pl) {
+      const size_t row = (size_t)n * P + p;
+      float gv[8], xv[8], o[8];
+      ld8(g, dtg, row * ldg + goff + cv * 8, gv);
+      ld8(x, dtx, row * ldx + xoff + cv * 8, xv);
 #pragma unroll
-      for (int u2 = 0; u2 < 2; ++u2) {
-        const int p = pb + u2 * G.pl;
-        if (p < p1) {
-          const size_t row = (size_t)n * P + p;
-          ld8(g, dtg, row * ldg + goff + cv * 8, gv[u2]);
-          ld8(x, dtx, row * ldx + xoff + cv * 8, xv[u2]);
-          if (r) ld8(r, dtr, row * ldr + roff + cv * 8, rv[u2]);
-          if (accumulate) ld8(dst, dtd, row * ldd + doff + cv * 8, dv[u2]);
-        }
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(k[j].x, gv[j], fmaf(k[j].y, xv[j], k[j].z));
+      if (r) {
+        float rv[8];
+        ld8(r, dtr, row * ldr + roff + cv * 8, rv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rv[j];
       }
+      if (accumulate) {
+        float dv[8];
+        ld8(dst, dtd, row * ldd + doff + cv * 8, dv);
 #pragma unroll
-      for (int u2 = 0; u2 < 2; ++u2) {
-        const int p = pb + u2 * G.pl;
-        if (p >= p1) continue;
-        const size_t row = (size_t)n * P + p;
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = fmaf(k[j].x, gv[u2][j], fmaf(k[j].y, xv[u2][j], k[j].z));
-          if (r) o[j] += rv[u2][j];
-          if (accumulate) o[j] += dv[u2][j];
-        }
-        st8(dst, dtd, row * ldd + doff + cv * 8, o);
+        for (int j = 0; j < 8; ++j) o[j] += dv[j];
       }
+      st8(dst, dtd, row * ldd + doff + cv * 8, o);
     }
   }
 }
@@ -212,9 +199,10 @@ __global__ void __launch_bounds__(256) bwd_affine3_kernel(const void* g, int dtg
 void launch_bwd_affine3(const void* g, int dtg, int ldg, int goff, const void* x, int dtx, int ldx, int xoff,
                         const float4* coef4, int coef_ld, int coff, const void* r, int dtr, int ldr, int roff, void* dst,
                         int dtd, int ldd, int doff, int accumulate, int N, int P, int Cs, cudaStream_t st) {
-  dim3 grid((P + kRowChunk - 1) / kRowChunk, N);
+  const int chunk = row_chunk(P, N);
+  dim3 grid((P + chunk - 1) / chunk, N);
   bwd_affine3_kernel<<<grid, 256, 0, st>>>(g, dtg, ldg, goff, x, dtx, ldx, xoff, coef4, coef_ld, coff, r, dtr, ldr, roff, dst,
-                                           dtd, ldd, doff, accumulate, P, Cs);
+                                           dtd, ldd, doff, accumulate, P, Cs, chunk);
 }
 
 // dst (=|+=) src on channel slices (gradient of an identity edge, e.g. the attention residual)
@@ -414,46 +402,46 @@ void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* d
 // A block owns a 32-channel slice and a contiguous range of (image, 8x16 tile) items; weight gradients stay in
 // registers over the whole range, the per-image sums are flushed when the image changes.  Two fp32 halo tiles of
 // 10 x 18 x 32 = 46 KB: four blocks per SM overlap one another's load and compute phases.
-__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float2* __restrict__ coef_se,
-                                                         const void* __restrict__ h1, int dth, const float2* __restrict__ coef2,
-                                                         const float* __restrict__ w, void* __restrict__ du,
-                                                         double* __restrict__ t12, float* __restrict__ dW, int N, int H, int W,
-                                                         int C, int tilesX, int tilesY, int items_per_block) {
+__global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float2* __restrict__ coef_se,
+                                                            const void* __restrict__ h1, int dth, const float2* __restrict__ coef2,
+                                                            const float* __restrict__ w, void* __restrict__ du,
+                                                            double* __restrict__ t12, float* __restrict__ dW, int N, int H, int W,
+                                                            int C, int tilesX, int tilesY, int items_per_block) {
   constexpr int TSY = 8, TSX = 16, HSY = TSY + 2, HS = TSX + 2, CB = 32;
   extern __shared__ __align__(16) float dsm[];
-  float* tg = dsm;                      // [HSY*HS*CB] dh2 halo tile
-  float* tv = dsm + HSY * HS * CB;      // [HSY*HS*CB] v halo tile
-  __shared__ float s_w[9 * CB];
+  float* tg = dsm;                      // [HSY*HS][CB] dh2 halo tile
+  float* tv = dsm + HSY * HS * CB;      // [HSY*HS][CB] v halo tile
+  __shared__ __align__(16) float s_w[9 * CB];
   __shared__ float s_red[8][2 * CB];
   const int tid = threadIdx.x;
   const int c0 = blockIdx.y * CB;
-  const int cg = tid & 3;
+  const int cg = tid & 3;               // fill phase: 8-channel group
+  // compute phase: a thread owns 4 channels x 4 consecutive pixels of one row.  The 8 lanes of a quarter warp read the 32
+  // channels (128 contiguous bytes) of ONE pixel: every LDS.128 is conflict-free; a halo row is loaded once per thread and
+  // serves all taps of that row (36 LDS.128 + 9 weight loads per 16 outputs).
+  const int q = tid & 7, pg = tid >> 3;
+  const int row = pg >> 2, xs = (pg & 3) * 4;
   const int tiles = tilesX * tilesY;
   const long long total = (long long)N * tiles;
   const long long i0 = (long long)blockIdx.x * items_per_block;
   const long long i1 = i0 + items_per_block < total ? i0 + items_per_block : total;
   for (int i = tid; i < 9 * CB; i += 256) s_w[i] = w[(size_t)(i / CB) * C + c0 + (i % CB)];
-  float dw[9][8];
+  float4 dw[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dw[t][j] = 0.f;
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int t = 0; t < 9; ++t) dw[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   int cur_n = -1;
 
   auto flush = [&](int n) {
-    // fixed-order reduction of (s1, s2) over the block, then one fp64 atomic per channel
+    // lanes with equal q (l, l^8, l^16) hold the same channels: reduce them, then the 8 warps through shared memory
+    float a[4] = {s1.x, s1.y, s1.z, s1.w}, b[4] = {s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = s1[j], b = s2[j];
-      a += __shfl_xor_sync(0xffffffffu, a, 4); b += __shfl_xor_sync(0xffffffffu, b, 4);
-      a += __shfl_xor_sync(0xffffffffu, a, 8); b += __shfl_xor_sync(0xffffffffu, b, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
-      if ((tid & 31) < 4) { s_red[tid >> 5][cg * 8 + j] = a; s_red[tid >> 5][CB + cg * 8 + j] = b; }
-      s1[j] = 0.f; s2[j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8); b[j] += __shfl_xor_sync(0xffffffffu, b[j], 8);
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16); b[j] += __shfl_xor_sync(0xffffffffu, b[j], 16);
+      if ((tid & 31) < 8) { s_red[tid >> 5][q * 4 + j] = a[j]; s_red[tid >> 5][CB + q * 4 + j] = b[j]; }
     }
+    s1 = make_float4(0.f, 0.f, 0.f, 0.f); s2 = s1;
     __syncthreads();
     if (tid < 2 * CB) {
       float s = 0.f;
@@ -472,110 +460,136 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const void* __restrict_
       cur_n = n;
     }
     const int ty0 = (tile / tilesX) * TSY, tx0 = (tile % tilesX) * TSX;
-    float2 cse[8], c2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      cse[j] = coef_se[(size_t)n * C + c0 + cg * 8 + j];
-      c2[j] = coef2[(size_t)n * C + c0 + cg * 8 + j];
-    }
     __syncthreads();   // previous tile fully consumed
-    for (int i = tid; i < HSY * HS * 4; i += 256) {
-      const int px = i >> 2;
-      const int yy = px / HS, xx = px - yy * HS;
-      const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-      float a[8], b[8];
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + cg * 8;
-        ld8(dq, dtg, o, a);
-        ld8(h1, dth, o, b);
+    {
+      float2 cse[8], c2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a[j] = fmaf(cse[j].x, a[j], cse[j].y);
-          b[j] = fminf(fmaxf(fmaf(c2[j].x, b[j], c2[j].y), 0.f), 6.f);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+      for (int j = 0; j < 8; ++j) {
+        cse[j] = coef_se[(size_t)n * C + c0 + cg * 8 + j];
+        c2[j] = coef2[(size_t)n * C + c0 + cg * 8 + j];
       }
-      float4* d = reinterpret_cast<float4*>(tg + px * CB + cg * 8);
-      d[0] = make_float4(a[0], a[1], a[2], a[3]);
-      d[1] = make_float4(a[4], a[5], a[6], a[7]);
-      float4* e = reinterpret_cast<float4*>(tv + px * CB + cg * 8);
-      e[0] = make_float4(b[0], b[1], b[2], b[3]);
-      e[1] = make_float4(b[4], b[5], b[6], b[7]);
+      for (int i = tid; i < HSY * HS * 4; i += 256) {
+        const int px = i >> 2;
+        const int yy = px / HS, xx = px - yy * HS;
+        const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+        float a[8], b[8];
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + cg * 8;
+          ld8(dq, dtg, o, a);
+          ld8(h1, dth, o, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] = fmaf(cse[j].x, a[j], cse[j].y);
+            b[j] = fminf(fmaxf(fmaf(c2[j].x, b[j], c2[j].y), 0.f), 6.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+        }
+        float4* d = reinterpret_cast<float4*>(tg + px * CB + cg * 8);
+        d[0] = make_float4(a[0], a[1], a[2], a[3]);
+        d[1] = make_float4(a[4], a[5], a[6], a[7]);
+        float4* e = reinterpret_cast<float4*>(tv + px * CB + cg * 8);
+        e[0] = make_float4(b[0], b[1], b[2], b[3]);
+        e[1] = make_float4(b[4], b[5], b[6], b[7]);
+      }
     }
     __syncthreads();
-    const int strip = tid >> 2;           // 64 strips of 2 pixels: 8 rows x 8 strips
-    const int row = strip >> 3, xs = (strip & 7) * 2;
     const int gy = ty0 + row;
+    // centre dh2 of the 4 pixels (halo coordinates (row + 1, xs + 1 + p))
+    float4 gc[4];
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      const int gx = tx0 + xs + px;
-      if (gy >= H || gx >= W) continue;
-      float dv[8];
+    for (int p = 0; p < 4; ++p) gc[p] = *reinterpret_cast<const float4*>(tg + ((row + 1) * HS + xs + 1 + p) * CB + q * 4);
+    float4 dv[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dv[j] = 0.f;
-      // centre dh2 (for the weight gradient)
-      float gc[8];
-      {
-        const float4* s = reinterpret_cast<const float4*>(tg + ((row + 1) * HS + xs + px + 1) * CB + cg * 8);
-        const float4 lo = s[0], hi = s[1];
-        gc[0] = lo.x; gc[1] = lo.y; gc[2] = lo.z; gc[3] = lo.w; gc[4] = hi.x; gc[5] = hi.y; gc[6] = hi.z; gc[7] = hi.w;
-      }
+    for (int p = 0; p < 4; ++p) dv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+    for (int hr = 0; hr < 3; ++hr) {
+      // halo row (row + hr), columns xs .. xs + 5
+      float4 v6[6];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          // dv[p] += w[ky][kx] * dh2[p - (ky-1, kx-1)]  -> halo coordinates (row + 1 - (ky - 1), x + 1 - (kx - 1))
-          const float4* s = reinterpret_cast<const float4*>(tg + ((row + 2 - ky) * HS + xs + px + 2 - kx) * CB + cg * 8);
-          const float4 lo = s[0], hi = s[1];
-          const float* wv = s_w + (ky * 3 + kx) * CB + cg * 8;
-          dv[0] = fmaf(lo.x, wv[0], dv[0]); dv[1] = fmaf(lo.y, wv[1], dv[1]);
-          dv[2] = fmaf(lo.z, wv[2], dv[2]); dv[3] = fmaf(lo.w, wv[3], dv[3]);
-          dv[4] = fmaf(hi.x, wv[4], dv[4]); dv[5] = fmaf(hi.y, wv[5], dv[5]);
-          dv[6] = fmaf(hi.z, wv[6], dv[6]); dv[7] = fmaf(hi.w, wv[7], dv[7]);
-          // dW[tap] += dh2[p] * v[p + (ky-1, kx-1)] -> halo coordinates (row + ky, x + kx)
-          const float4* q = reinterpret_cast<const float4*>(tv + ((row + ky) * HS + xs + px + kx) * CB + cg * 8);
-          const float4 vl = q[0], vh = q[1];
-          float* d = dw[ky * 3 + kx];
-          d[0] = fmaf(gc[0], vl.x, d[0]); d[1] = fmaf(gc[1], vl.y, d[1]);
-          d[2] = fmaf(gc[2], vl.z, d[2]); d[3] = fmaf(gc[3], vl.w, d[3]);
-          d[4] = fmaf(gc[4], vh.x, d[4]); d[5] = fmaf(gc[5], vh.y, d[5]);
-          d[6] = fmaf(gc[6], vh.z, d[6]); d[7] = fmaf(gc[7], vh.w, d[7]);
+      for (int i = 0; i < 6; ++i) v6[i] = *reinterpret_cast<const float4*>(tg + ((row + hr) * HS + xs + i) * CB + q * 4);
+      // dv[p] += w[ky][kx] * dh2[p - off(tap)] : halo (row + 2 - ky, x + 2 - kx)  =>  ky = 2 - hr, column index i = p + 2 - kx
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_w + ((2 - hr) * 3 + kx) * CB + q * 4);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 g4 = v6[p + 2 - kx];
+          dv[p].x = fmaf(g4.x, wv.x, dv[p].x); dv[p].y = fmaf(g4.y, wv.y, dv[p].y);
+          dv[p].z = fmaf(g4.z, wv.z, dv[p].z); dv[p].w = fmaf(g4.w, wv.w, dv[p].w);
         }
-      // ReLU6 backward needs the pre-activation u = a2 h1 + b2 of the centre pixel
-      const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + cg * 8;
-      float hc[8];
-      ld8(h1, dth, o, hc);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = fmaf(c2[j].x, hc[j], c2[j].y);
-        dv[j] = (u > 0.f && u < 6.f) ? dv[j] : 0.f;
       }
-      st8(du, dtg, o, dv);
+      // dW[ky][kx] += dh2[p] * v[p + off(tap)] : halo (row + ky, x + kx)  =>  ky = hr, column index i = p + kx
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int i = 0; i < 6; ++i) v6[i] = *reinterpret_cast<const float4*>(tv + ((row + hr) * HS + xs + i) * CB + q * 4);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float4 acc = dw[hr * 3 + kx];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 v4 = v6[p + kx];
+          acc.x = fmaf(gc[p].x, v4.x, acc.x); acc.y = fmaf(gc[p].y, v4.y, acc.y);
+          acc.z = fmaf(gc[p].z, v4.z, acc.z); acc.w = fmaf(gc[p].w, v4.w, acc.w);
+        }
+        dw[hr * 3 + kx] = acc;
+      }
+    }
+    // note: pixels of the tile that lie outside the image have dh2 = 0 in the halo tile, so their gc is 0 and they add
+    // nothing to dW; their dv is simply not stored
+    float2 ab4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ab4[j] = coef2[(size_t)n * C + c0 + q * 4 + j];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gx = tx0 + xs + p;
+      if (gy >= H || gx >= W) continue;
+      const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + q * 4;
+      // ReLU6 backward: pre-activation u = a2 h1 + b2 of the centre pixel
+      float hc[4], d4[4] = {dv[p].x, dv[p].y, dv[p].z, dv[p].w};
+      if (dth == DT_F32) {
+        const float4 t4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h1) + o);
+        hc[0] = t4.x; hc[1] = t4.y; hc[2] = t4.z; hc[3] = t4.w;
+      } else if (dth == DT_BF16) {
+        const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(h1) + o);
+        hc[0] = bf16lo(t2.x); hc[1] = bf16hi(t2.x); hc[2] = bf16lo(t2.y); hc[3] = bf16hi(t2.y);
+      } else {
+        const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(h1) + o);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t2.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t2.y));
+        hc[0] = f0.x; hc[1] = f0.y; hc[2] = f1.x; hc[3] = f1.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float u = fmaf(ab4[j].x, hc[j], ab4[j].y);
+        d4[j] = (u > 0.f && u < 6.f) ? d4[j] : 0.f;
+      }
+      if (dtg == DT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(du) + o) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+      } else {
+        uint2 pk;
+        pk.x = pack_bf16(d4[0], d4[1]); pk.y = pack_bf16(d4[2], d4[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(du) + o) = pk;
         // statistics of the STORED gradient (what the next pass reads)
-        const float d = (dtg == DT_BF16) ? __bfloat162float(__float2bfloat16_rn(dv[j])) : dv[j];
-        s1[j] += d;
-        s2[j] = fmaf(d, hc[j], s2[j]);
+        d4[0] = bf16lo(pk.x); d4[1] = bf16hi(pk.x); d4[2] = bf16lo(pk.y); d4[3] = bf16hi(pk.y);
       }
+      s1.x += d4[0]; s1.y += d4[1]; s1.z += d4[2]; s1.w += d4[3];
+      s2.x = fmaf(d4[0], hc[0], s2.x); s2.y = fmaf(d4[1], hc[1], s2.y); s2.z = fmaf(d4[2], hc[2], s2.z); s2.w = fmaf(d4[3], hc[3], s2.w);
     }
   }
   if (cur_n >= 0) flush(cur_n);
-  // weight gradients: reduce over the 64 strips of the block (lanes sharing cg, then warps), one atomic per (tap, channel)
+  // weight gradients: lanes with equal q, then the 8 warps; one atomic per (tap, channel)
   __syncthreads();
   float* red = tg;   // reuse: [8 warps][9][CB]
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t) {
+    float a[4] = {dw[t].x, dw[t].y, dw[t].z, dw[t].w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = dw[t][j];
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
-      a += __shfl_xor_sync(0xffffffffu, a, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 16);
-      if ((tid & 31) < 4) red[((tid >> 5) * 9 + t) * CB + cg * 8 + j] = a;
+    for (int j = 0; j < 4; ++j) {
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
+      a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+      if ((tid & 31) < 8) red[((tid >> 5) * 9 + t) * CB + q * 4 + j] = a[j];
     }
+  }
   __syncthreads();
   for (int i = tid; i < 9 * CB; i += 256) {
     float s = 0.f;
