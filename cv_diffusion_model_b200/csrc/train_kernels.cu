@@ -402,6 +402,7 @@ void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* d
 // A block owns a 32-channel slice and a contiguous range of (image, 8x16 tile) items; weight gradients stay in
 // registers over the whole range, the per-image sums are flushed when the image changes.  Two fp32 halo tiles of
 // 10 x 18 x 32 = 46 KB: four blocks per SM overlap one another's load and compute phases.
+template <bool F32>   // F32: the fp32 plan (all tensors fp32); else 16-bit tensors (gradients bf16, h1 bf16 or fp16)
 __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float2* __restrict__ coef_se,
                                                             const void* __restrict__ h1, int dth, const float2* __restrict__ coef2,
                                                             const float* __restrict__ w, void* __restrict__ du,
@@ -468,15 +469,61 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
         cse[j] = coef_se[(size_t)n * C + c0 + cg * 8 + j];
         c2[j] = coef2[(size_t)n * C + c0 + cg * 8 + j];
       }
-      for (int i = tid; i < HSY * HS * 4; i += 256) {
+      // 720 (pixel, channel-group) items over 256 threads: three fully unrolled rounds, every global load issued before the
+      // first use (the fill is latency-bound otherwise: one DRAM round trip per round)
+      constexpr int ROUNDS = (HSY * HS * 4 + 255) / 256;
+      uint4 ra[ROUNDS][F32 ? 2 : 1], rb[ROUNDS][F32 ? 2 : 1];
+      bool inside[ROUNDS];
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int i = tid + rd * 256;
         const int px = i >> 2;
         const int yy = px / HS, xx = px - yy * HS;
         const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-        float a[8], b[8];
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        inside[rd] = i < HSY * HS * 4 && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        if (inside[rd]) {
           const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + cg * 8;
-          ld8(dq, dtg, o, a);
-          ld8(h1, dth, o, b);
+          if (F32) {
+            ra[rd][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dq) + o);
+            ra[rd][F32 ? 1 : 0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(dq) + o + 4);
+            rb[rd][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(h1) + o);
+            rb[rd][F32 ? 1 : 0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(h1) + o + 4);
+          } else {
+            ra[rd][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dq) + o);
+            rb[rd][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(h1) + o);   // bf16 or fp16: 16 bytes
+          }
+        }
+      }
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int i = tid + rd * 256;
+        if (i >= HSY * HS * 4) continue;
+        const int px = i >> 2;
+        float a[8], b[8];
+        if (inside[rd]) {
+          if (F32) {
+            const uint4 u0 = ra[rd][0], u1 = ra[rd][F32 ? 1 : 0];
+            a[0] = __uint_as_float(u0.x); a[1] = __uint_as_float(u0.y); a[2] = __uint_as_float(u0.z); a[3] = __uint_as_float(u0.w);
+            a[4] = __uint_as_float(u1.x); a[5] = __uint_as_float(u1.y); a[6] = __uint_as_float(u1.z); a[7] = __uint_as_float(u1.w);
+          } else {
+            const uint4 u = ra[rd][0];
+            a[0] = bf16lo(u.x); a[1] = bf16hi(u.x); a[2] = bf16lo(u.y); a[3] = bf16hi(u.y);
+            a[4] = bf16lo(u.z); a[5] = bf16hi(u.z); a[6] = bf16lo(u.w); a[7] = bf16hi(u.w);
+          }
+          if (F32) {
+            const uint4 u0 = rb[rd][0], u1 = rb[rd][F32 ? 1 : 0];
+            b[0] = __uint_as_float(u0.x); b[1] = __uint_as_float(u0.y); b[2] = __uint_as_float(u0.z); b[3] = __uint_as_float(u0.w);
+            b[4] = __uint_as_float(u1.x); b[5] = __uint_as_float(u1.y); b[6] = __uint_as_float(u1.z); b[7] = __uint_as_float(u1.w);
+          } else if (dth == DT_BF16) {
+            const uint4 u = rb[rd][0];
+            b[0] = bf16lo(u.x); b[1] = bf16hi(u.x); b[2] = bf16lo(u.y); b[3] = bf16hi(u.y);
+            b[4] = bf16lo(u.z); b[5] = bf16hi(u.z); b[6] = bf16lo(u.w); b[7] = bf16hi(u.w);
+          } else {
+            const uint4 u = rb[rd][0];
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); b[2 * j] = f.x; b[2 * j + 1] = f.y; }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             a[j] = fmaf(cse[j].x, a[j], cse[j].y);
@@ -547,7 +594,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
       const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + q * 4;
       // ReLU6 backward: pre-activation u = a2 h1 + b2 of the centre pixel
       float hc[4], d4[4] = {dv[p].x, dv[p].y, dv[p].z, dv[p].w};
-      if (dth == DT_F32) {
+      if (F32) {
         const float4 t4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h1) + o);
         hc[0] = t4.x; hc[1] = t4.y; hc[2] = t4.z; hc[3] = t4.w;
       } else if (dth == DT_BF16) {
@@ -563,7 +610,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
         const float u = fmaf(ab4[j].x, hc[j], ab4[j].y);
         d4[j] = (u > 0.f && u < 6.f) ? d4[j] : 0.f;
       }
-      if (dtg == DT_F32) {
+      if (F32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(du) + o) = make_float4(d4[0], d4[1], d4[2], d4[3]);
       } else {
         uint2 pk;
@@ -612,9 +659,15 @@ void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const voi
   bx = (total + per - 1) / per;
   const size_t smem = (size_t)2 * 10 * 18 * 32 * sizeof(float);
   // static (3.2 KB) + dynamic (45 KB) shared memory together exceed the 48 KB default: opt in explicitly
-  if (ensure_dyn_smem_fn(dwconv_bwd_kernel, 64 * 1024)) return;
-  dwconv_bwd_kernel<<<dim3((unsigned)bx, cblocks), 256, smem, st>>>(dq, dtg, coef_se, h1, dth, coef2, w, du, t12, dW, N, H, W, C,
-                                                              tilesX, tilesY, per);
+  if (dtg == DT_F32) {
+    if (ensure_dyn_smem_fn(dwconv_bwd_kernel<true>, 64 * 1024)) return;
+    dwconv_bwd_kernel<true><<<dim3((unsigned)bx, cblocks), 256, smem, st>>>(dq, dtg, coef_se, h1, dth, coef2, w, du, t12, dW, N, H, W, C,
+                                                                      tilesX, tilesY, per);
+  } else {
+    if (ensure_dyn_smem_fn(dwconv_bwd_kernel<false>, 64 * 1024)) return;
+    dwconv_bwd_kernel<false><<<dim3((unsigned)bx, cblocks), 256, smem, st>>>(dq, dtg, coef_se, h1, dth, coef2, w, du, t12, dW, N, H, W, C,
+                                                                       tilesX, tilesY, per);
+  }
 }
 
 // =================================================================================================
