@@ -78,6 +78,8 @@ bool launch_final_conv_h2(const void* in, const float2* coef, const float* w, co
 void launch_attn_kv(const void* qkv, double* state, int N, int P, int heads, int bf16act, cudaStream_t st);
 void launch_attn_apply(const void* qkv, const double* state, void* out, int N, int P, int heads, int bf16act,
                        cudaStream_t st);
+// StandardAttention core (efficient_unet.py:344-349): out = softmax(q k^T d^-0.5) v per head (d = 32), qkv as above
+void launch_attn_softmax(const void* qkv, void* out, int N, int P, int heads, int bf16act, cudaStream_t st);
 // y = a*u + b + x (to_out GroupNorm + residual), channel statistics of y.
 void launch_affine_residual(const void* u, const float2* coef, const void* x, void* y, double* stats, int N, int P,
                             int C, int bf16act, cudaStream_t st);

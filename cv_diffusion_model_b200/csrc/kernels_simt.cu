@@ -591,6 +591,92 @@ void launch_attn_apply(const void* qkv, const double* state, void* out, int N, i
 }
 
 // =================================================================================================
+// StandardAttention (efficient_unet.py:311-357, use_linear_attention=False): softmax(q k^T / sqrt(d)) v per head, d = 32.
+// One block = 64 queries of one (image, head); keys / values stream through shared memory in tiles of 64 with the
+// online-softmax recurrence (running max and sum per query), fp32 throughout.  A thread owns one query and 8 of the 32
+// output channels (4 threads per query).
+template <typename T>
+__global__ void __launch_bounds__(256) attn_softmax_kernel(const T* __restrict__ qkv, T* __restrict__ out, int P, int heads) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float ks[64][33], vs[64][33];
+  const int n = blockIdx.z, h = blockIdx.y, p0 = blockIdx.x * 64;
+  const int inner = heads * 32, ld = 3 * inner;
+  const int tid = threadIdx.x;
+  const int qi = tid >> 2, part = tid & 3;       // query, channel quarter
+  const int p = p0 + qi;
+  float q[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) q[d] = p < P ? to_f<T>(qkv[((size_t)n * P + p) * ld + h * 32 + d]) * 0.17677669529663687f : 0.f;   // 32^-0.5
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < P; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 32; i += 256) {
+      const int kk = i >> 5, d = i & 31, kp = k0 + kk;
+      float kv = 0.f, vv = 0.f;
+      if (kp < P) {
+        const T* row = qkv + ((size_t)n * P + kp) * ld;
+        kv = to_f<T>(row[inner + h * 32 + d]);
+        vv = to_f<T>(row[2 * inner + h * 32 + d]);
+      }
+      ks[kk][d] = kv;
+      vs[kk][d] = vv;
+    }
+    __syncthreads();
+    const int kend = min(64, P - k0);
+    // the 4 threads of a query each score 16 of the 64 keys, then exchange the tile maximum and rescale once per tile
+    float s[16];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int kk = part * 16 + j;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) a = fmaf(q[d], ks[kk][d], a);
+      s[j] = kk < kend ? a : -INFINITY;
+      tmax = fmaxf(tmax, s[j]);
+    }
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+    const float mn = fmaxf(m, tmax);
+    const float corr = __expf(m - mn);          // exp(-inf) = 0 on the first tile
+    float lsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s[j] = __expf(s[j] - mn); lsum += s[j]; }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+    l = l * corr + lsum;
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= corr;
+    // acc[e] += sum_k p[k] v[k][e] for this thread's 8 channels: the probabilities of the other three threads come by shuffle
+#pragma unroll
+    for (int src = 0; src < 4; ++src) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, s[j], (tid & 31 & ~3) | src);
+        const int kk = src * 16 + j;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vs[kk][part * 8 + e], acc[e]);
+      }
+    }
+  }
+  if (p < P) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[((size_t)n * P + p) * inner + h * 32 + part * 8 + e] = from_f<T>(acc[e] * inv);
+  }
+}
+
+void launch_attn_softmax(const void* qkv, void* out, int N, int P, int heads, int bf16act, cudaStream_t st) {
+  dim3 grid((P + 63) / 64, heads, N);
+  if (bf16act) launch_pdl(attn_softmax_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)qkv, (bf16*)out, P, heads);
+  else launch_pdl(attn_softmax_kernel<float>, grid, dim3(256), 0, st, (const float*)qkv, (float*)out, P, heads);
+}
+
+// =================================================================================================
 // y = a*u + b + x : the GroupNorm after to_out plus the attention residual (efficient_unet.py:266-269,
 // 306-308), with channel statistics of y for the next GroupNorm.  Block = 64 pixels of one image.
 template <typename T>

@@ -723,7 +723,39 @@ struct Builder {
   }
 
   // ---- LinearAttention (efficient_unet.py:273-308) ---------------------------------------------
+  // ---- StandardAttention (efficient_unet.py:311-357): norm -> to_qkv -> softmax(q k^T d^-0.5) v -> to_out -> + x -----------
+  // state_dict: norm.{weight,bias}, to_qkv.weight, to_out.weight (a plain conv, no GroupNorm after it); the residual is the
+  // identity K-segment of the to_out GEMM, like a block's project.
+  TensorP standard_attention(const std::string& name, const TensorP& x) {
+    const int C = x->C, heads = p->cfg.num_attention_heads, inner = heads * 32;
+    const int h = x->H, w = x->W, P = h * w;
+    const double es = (double)p->esz;
+    const GnInfo gnn = gn_coef(name + ".norm", View::of(x), name + ".norm", -1);
+    TensorP qkv = p->new_tensor(3 * inner, h, w, false, name + ".qkv");
+    GemmW wq = make_w(3 * inner, {C});
+    p->add_weight(name + ".to_qkv.weight", (int64_t)3 * inner * C, mat_job(wq, 0, PACK_MAT, 3 * inner, C, C, 0));
+    gemm(name + ".to_qkv", {{x, gnn.coef, C, 0, XF_AFFINE}}, wq, qkv, false,
+         (C + 3.0 * inner) * N * P * es + 3.0 * inner * C * es, 2.0 * N * P * C * 3 * inner);
+    TensorP o = p->new_tensor(inner, h, w, false, name + ".attn");
+    {
+      lcm_plan* pl = p; const int n = N;
+      push(name + ".softmax", "attn_softmax", 4.0 * inner * N * P * es, 4.0 * N * heads * (double)P * P * 32,
+           [=](const RunCtx& c, cudaStream_t st) { launch_attn_softmax(c.a + qkv->off, c.a + o->off, n, P, heads, pl->bf16, st); });
+    }
+    p->release(qkv);
+    TensorP y = p->new_tensor(C, h, w, true, name + ".out");
+    GemmW wo = make_w(C, {inner, C});
+    p->add_weight(name + ".to_out.weight", (int64_t)C * inner, mat_job(wo, 0, PACK_MAT, C, inner, inner, 0));
+    p->identity_jobs.push_back(mat_job(wo, 1, PACK_IDENTITY, C, C, C, 0));
+    gemm(name + ".to_out", {{o, 0, 0, 0, XF_NONE}, {x, 0, 0, 0, XF_NONE}}, wo, y, true,
+         (2.0 * C + inner) * N * P * es + (double)inner * C * es, 2.0 * N * P * C * inner);
+    p->release(o);
+    p->release(x);
+    return y;
+  }
+
   TensorP attention(const std::string& name, const TensorP& x) {
+    if (p->cfg.standard_attention) return standard_attention(name, x);
     const int C = x->C, heads = p->cfg.num_attention_heads, inner = heads * 32;
     const int h = x->H, w = x->W, P = h * w;
     const double es = (double)p->esz;
@@ -1288,6 +1320,8 @@ int lcm_plan_create(const lcm_unet_config* cfg, int batch, int height, int width
   p->tc = p->bf16 && !(flags & LCM_FLAG_SIMT_GEMM);
   p->taps = (flags & LCM_FLAG_TAPS) != 0;
   p->train = (flags & LCM_FLAG_TRAIN) != 0;
+  if (p->train && cfg->standard_attention)
+    return fail(LCM_ERR_INVALID, "training plans implement the presets' linear attention; StandardAttention is inference-only");
   if (p->train && p->bf16 && !p->tc) return fail(LCM_ERR_INVALID, "training plans are fp32 or bf16 (tensor-core); LCM_FLAG_SIMT_GEMM is inference-only");
   p->pool.reuse = !p->taps && !p->train;     // the backward pass reads every forward tensor
   p->gpool.reuse = !p->taps;

@@ -81,6 +81,17 @@ def _linear_attention(c: int, heads: int, strict: bool) -> _Named:
     return att
 
 
+def _standard_attention(c: int, heads: int, strict: bool) -> _Named:
+    """Weights of the softmax attention (reference :322-333): norm, to_qkv, to_out (a plain conv)."""
+    inner = heads * ATTN_DIM_HEAD
+    att = _Named()
+    att.add_module("norm", _gn(c, strict))
+    att.add_module("to_qkv", _conv(c, 3 * inner, 1, bias=False))
+    att.add_module("to_out", _conv(inner, c, 1, bias=False))
+    att.meta = ("attn", c, heads)
+    return att
+
+
 class EfficientUNet(nn.Module):
     """Drop-in for the reference ``EfficientUNet`` (efficient_unet.py:387-606).
 
@@ -94,9 +105,6 @@ class EfficientUNet(nn.Module):
         super().__init__()
         if groupnorm not in ("strict", "gcd"):
             raise ValueError(f"Unknown groupnorm mode: {groupnorm}")
-        if not config.use_linear_attention:
-            raise ValueError("only use_linear_attention=True is supported by the B200 path (SURVEY §2: "
-                             "StandardAttention is out of scope)")
         if not config.quantization_friendly or not config.use_se:
             raise ValueError("the B200 path implements the preset blocks only (ReLU6 + SE)")
         self.config = config
@@ -104,6 +112,7 @@ class EfficientUNet(nn.Module):
         strict = groupnorm == "strict"
         cfg = config
         widths = list(cfg.level_channels)
+        _attention = _linear_attention if cfg.use_linear_attention else _standard_attention   # reference :448-454
 
         self.time_mlp = _Named.indexed([
             (1, nn.Linear(cfg.base_channels, cfg.time_embed_dim)),
@@ -116,7 +125,7 @@ class EfficientUNet(nn.Module):
             for _ in range(n_blocks):
                 mods.append(_inverted_residual(ci, co, cfg, strict))
                 if res in cfg.attention_resolutions:
-                    mods.append(_linear_attention(co, cfg.num_attention_heads, strict))
+                    mods.append(_attention(co, cfg.num_attention_heads, strict))
                 ci = co
             return nn.ModuleList(mods)
 
@@ -134,7 +143,7 @@ class EfficientUNet(nn.Module):
         # the reference builds the two mid blocks with the constructor default se_ratio=0.25, not config.se_ratio
         # (efficient_unet.py:467-478)
         self.mid_block1 = _inverted_residual(mid, mid, cfg, strict, se_ratio=0.25)
-        self.mid_attn = _linear_attention(mid, cfg.num_attention_heads, strict)
+        self.mid_attn = _attention(mid, cfg.num_attention_heads, strict)
         self.mid_block2 = _inverted_residual(mid, mid, cfg, strict, se_ratio=0.25)
 
         self.decoder_blocks = nn.ModuleList()
@@ -145,7 +154,7 @@ class EfficientUNet(nn.Module):
                 mods.append(_inverted_residual(ci + co if first else co, co, cfg, strict))
                 first = False
                 if res in cfg.attention_resolutions:
-                    mods.append(_linear_attention(co, cfg.num_attention_heads, strict))
+                    mods.append(_attention(co, cfg.num_attention_heads, strict))
             self.decoder_blocks.append(nn.ModuleList(mods))
             ci = co
             if li < len(widths) - 1:

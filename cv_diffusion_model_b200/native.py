@@ -24,7 +24,7 @@ class UNetConfigC(C.Structure):
         ("num_attention_resolutions", C.c_int32), ("attention_resolutions", C.c_int32 * LCM_MAX_LEVELS),
         ("num_attention_heads", C.c_int32), ("num_res_blocks", C.c_int32), ("expansion_ratio", C.c_int32),
         ("se_ratio", C.c_float), ("time_embed_dim", C.c_int32), ("image_size", C.c_int32),
-        ("groupnorm_gcd", C.c_int32),
+        ("groupnorm_gcd", C.c_int32), ("standard_attention", C.c_int32),
     ]
 
 
@@ -142,4 +142,5 @@ def config_struct(cfg, groupnorm: str) -> UNetConfigC:
     c.expansion_ratio, c.se_ratio = cfg.expansion_ratio, cfg.se_ratio
     c.time_embed_dim, c.image_size = cfg.time_embed_dim, cfg.image_size
     c.groupnorm_gcd = 1 if groupnorm == "gcd" else 0
+    c.standard_attention = 0 if getattr(cfg, "use_linear_attention", True) else 1
     return c

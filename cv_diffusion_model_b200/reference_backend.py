@@ -28,7 +28,7 @@ class UNetConfigC(C.Structure):
                 ("num_attention_resolutions", C.c_int32), ("attention_resolutions", C.c_int32 * 8),
                 ("num_attention_heads", C.c_int32), ("num_res_blocks", C.c_int32), ("expansion_ratio", C.c_int32),
                 ("se_ratio", C.c_float), ("time_embed_dim", C.c_int32), ("image_size", C.c_int32),
-                ("groupnorm_gcd", C.c_int32)]
+                ("groupnorm_gcd", C.c_int32), ("standard_attention", C.c_int32)]
 
 
 _lib = None
@@ -67,9 +67,8 @@ def _check(rc):
 
 def config_struct(cfg) -> UNetConfigC:
     """Copy the reference dataclass field by field; refuses what the native path does not implement."""
-    if not getattr(cfg, "use_linear_attention", True) or not getattr(cfg, "use_se", True) \
-            or not getattr(cfg, "quantization_friendly", True) or getattr(cfg, "dropout", 0.0) != 0.0:
-        raise ValueError("the B200 path implements the preset blocks (linear attention, SE, ReLU6, dropout 0)")
+    if not getattr(cfg, "use_se", True) or not getattr(cfg, "quantization_friendly", True) or getattr(cfg, "dropout", 0.0) != 0.0:
+        raise ValueError("the B200 path implements the preset blocks (SE, ReLU6, dropout 0)")
     c = UNetConfigC()
     c.in_channels, c.out_channels, c.base_channels = cfg.in_channels, cfg.out_channels, cfg.base_channels
     mult, att = tuple(cfg.channel_multipliers), tuple(cfg.attention_resolutions)
@@ -88,6 +87,7 @@ def config_struct(cfg) -> UNetConfigC:
     # GroupNorm(gcd(32, C), C) patched in.  gcd == min(32, C) whenever the latter divides C, so one flag
     # value serves every model instance that can be passed in.
     c.groupnorm_gcd = 1
+    c.standard_attention = 0 if getattr(cfg, "use_linear_attention", True) else 1
     return c
 
 

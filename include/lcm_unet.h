@@ -66,6 +66,8 @@ typedef struct {
   int32_t time_embed_dim;
   int32_t image_size;       /* config.image_size: decides where attention modules exist (:426,447) */
   int32_t groupnorm_gcd;    /* 0: min(32,C) groups like the reference; 1: gcd(32,C) (tiny/base patch) */
+  int32_t standard_attention; /* 0: LinearAttention (every preset); 1: StandardAttention, use_linear_attention=False
+                                 (efficient_unet.py:311-357, 448-454, 473-474); inference plans only */
 } lcm_unet_config;
 
 typedef struct lcm_plan lcm_plan;

@@ -109,12 +109,36 @@ def linear_attention(sd, p: str, x: torch.Tensor, heads: int, strict: bool,
     return out
 
 
+def standard_attention(sd, p: str, x: torch.Tensor, heads: int, strict: bool, tap: Optional[Callable] = None) -> torch.Tensor:
+    """efficient_unet.py:335-357 (use_linear_attention=False): softmax(q k^T * dim_head^-0.5) v, plain to_out conv, + x."""
+    b, c, hh, ww = x.shape
+    h = F.group_norm(x, _groups(c, strict), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    qkv = F.conv2d(h, sd[p + "to_qkv.weight"])
+    if tap: tap(p + "qkv", qkv)
+    q, k, v = qkv.chunk(3, dim=1)
+    d = q.shape[1] // heads
+
+    def split(z):
+        return z.reshape(b, heads, d, hh * ww).transpose(2, 3)
+
+    q, k, v = split(q), split(k), split(v)
+    attn = torch.einsum("bhid,bhjd->bhij", q, k) * (d ** -0.5)
+    attn = F.softmax(attn, dim=-1)
+    out = torch.einsum("bhij,bhjd->bhid", attn, v)
+    out = out.transpose(2, 3).reshape(b, heads * d, hh, ww)
+    if tap: tap(p + "attn", out)
+    out = F.conv2d(out, sd[p + "to_out.weight"]) + x
+    if tap: tap(p + "out", out)
+    return out
+
+
 def unet_forward(sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, timestep: torch.Tensor,
                  strict_groupnorm: bool = True, tap: Optional[Callable] = None) -> torch.Tensor:
     """efficient_unet.py:532-606.  `cfg` needs: base_channels, channel_multipliers,
     num_res_blocks, num_attention_heads, attention_resolutions, image_size."""
     st = strict_groupnorm
     widths = [cfg.base_channels * m for m in cfg.channel_multipliers]
+    attention = linear_attention if getattr(cfg, "use_linear_attention", True) else standard_attention   # :448-454,473-474
     t_emb = time_embedding(sd, timestep, cfg.base_channels)
     if tap: tap("t_emb", t_emb)
     h = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=1)
@@ -126,7 +150,7 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, timestep: to
             h = inverted_residual(sd, f"{prefix}.{idx}.", h, t_emb, st, tap)
             idx += 1
             if res in cfg.attention_resolutions:       # :447, absolute resolution from config.image_size
-                h = linear_attention(sd, f"{prefix}.{idx}.", h, cfg.num_attention_heads, st, tap)
+                h = attention(sd, f"{prefix}.{idx}.", h, cfg.num_attention_heads, st, tap)
                 idx += 1
         return h
 
@@ -140,7 +164,7 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, timestep: to
             if tap: tap(f"downsamplers.{li}", h)
             res //= 2
     h = inverted_residual(sd, "mid_block1.", h, t_emb, st, tap)
-    h = linear_attention(sd, "mid_attn.", h, cfg.num_attention_heads, st, tap)
+    h = attention(sd, "mid_attn.", h, cfg.num_attention_heads, st, tap)
     h = inverted_residual(sd, "mid_block2.", h, t_emb, st, tap)
     for li in range(len(widths)):
         if li > 0:

@@ -123,16 +123,20 @@ def main():
         ("large256_in32", "large", 256, 32, 1, False, False),
         ("tiny256_in64_patched", "tiny", 256, 64, 2, True, True),
         ("base256_in32_patched", "base", 256, 32, 1, True, True),
+        # use_linear_attention=False: StandardAttention (softmax) at the bottleneck (efficient_unet.py:311-357,473-474)
+        ("small256_in64_stdattn", "small", 256, 64, 2, False, True),
+        ("small64_in32_stdattn", "small", 64, 32, 2, False, True),      # softmax attention at four places, n = 64 / 16
     ]
     for tag, variant, cfg_size, in_size, b, patched, affine in cases:
+        kw = {"use_linear_attention": False} if tag.endswith("stdattn") else {}
         torch.manual_seed(0)
         if patched:
             with gcd_groupnorm():
-                ref = ref_create(variant, image_size=cfg_size, in_channels=6).eval()
+                ref = ref_create(variant, image_size=cfg_size, in_channels=6, **kw).eval()
         else:
-            ref = ref_create(variant, image_size=cfg_size, in_channels=6).eval()
+            ref = ref_create(variant, image_size=cfg_size, in_channels=6, **kw).eval()
         torch.manual_seed(0)
-        mine = my_create(variant, image_size=cfg_size, in_channels=6, groupnorm="gcd" if patched else "strict")
+        mine = my_create(variant, image_size=cfg_size, in_channels=6, groupnorm="gcd" if patched else "strict", **kw)
         if affine:
             randomise_affine(ref)
             randomise_affine(mine)

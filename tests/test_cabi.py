@@ -31,7 +31,8 @@ def test_config_struct_layout():
     from cv_diffusion_model_b200 import native
     from cv_diffusion_model_b200.config import variant_config
     c = native.config_struct(variant_config("small", 256, in_channels=6), "strict")
-    assert C.sizeof(c) == 4 * (4 + 8 + 1 + 8 + 3 + 1 + 3)
+    assert C.sizeof(c) == 4 * (4 + 8 + 1 + 8 + 3 + 1 + 3 + 1)
+    assert c.standard_attention == 0 and native.config_struct(variant_config("small", 256, use_linear_attention=False), "strict").standard_attention == 1
     assert (c.base_channels, c.num_levels, list(c.channel_multipliers)[:4]) == (32, 4, [1, 2, 4, 8])
     assert list(c.attention_resolutions)[:2] == [16, 8] and c.time_embed_dim == 128 and c.image_size == 256
 

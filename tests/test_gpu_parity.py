@@ -26,6 +26,8 @@ UNET_CASES = [  # tag, variant, cfg image_size, input size, batch, patched, affi
     ("large256_in32", "large", 256, 32, 1, False, False),
     ("tiny256_in64_patched", "tiny", 256, 64, 2, True, True),
     ("base256_in32_patched", "base", 256, 32, 1, True, True),
+    ("small256_in64_stdattn", "small", 256, 64, 2, False, True),     # use_linear_attention=False (softmax attention)
+    ("small64_in32_stdattn", "small", 64, 32, 2, False, True),
 ]
 MODES = [("fp32", False), ("bf16", True), ("bf16", False)]   # (precision, simt_gemm)
 if os.environ.get("LCM_SKIP_TC"):
@@ -43,7 +45,7 @@ def _run_unet(m, x, t, precision, simt):
 @pytest.mark.parametrize("precision,simt", MODES)
 @pytest.mark.parametrize("tag,variant,cfg_size,in_size,b,patched,affine", UNET_CASES)
 def test_unet_forward_vs_golden(golden, weight_digests, tag, variant, cfg_size, in_size, b, patched, affine, precision, simt):
-    m = seeded_unet(variant, cfg_size, patched, affine)
+    m = seeded_unet(variant, cfg_size, patched, affine, use_linear_attention=not tag.endswith("stdattn"))
     assert sd_digest(m.state_dict()) == weight_digests[tag]
     torch.manual_seed(1)
     x = torch.randn(b, 6, in_size, in_size)

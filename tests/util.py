@@ -19,9 +19,9 @@ def randomise_affine(model, seed=1):
                     p.copy_(torch.randn(p.shape, generator=g) * 0.1)
 
 
-def seeded_unet(variant, image_size, patched=False, affine=False, seed=0):
+def seeded_unet(variant, image_size, patched=False, affine=False, seed=0, **overrides):
     torch.manual_seed(seed)
-    m = create_efficient_unet(variant, image_size=image_size, in_channels=6, groupnorm="gcd" if patched else "strict")
+    m = create_efficient_unet(variant, image_size=image_size, in_channels=6, groupnorm="gcd" if patched else "strict", **overrides)
     if affine:
         randomise_affine(m)
     return m
