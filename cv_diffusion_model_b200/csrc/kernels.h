@@ -91,6 +91,8 @@ void launch_lcm_step(const float* eps, const float* sample, const float* noise, 
 void launch_image_pre_u8(const uint8_t* hwc, float* nchw, int N, int H, int W, cudaStream_t st);
 void launch_image_post_u8(const float* nchw, uint8_t* hwc, int N, int H, int W, cudaStream_t st);
 void launch_image_resize_u8(const uint8_t* src, int N, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st);
+void launch_add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+void launch_fill_float2(float2* p, float2 v, long long n, cudaStream_t st);
 void launch_ddim_step(const float* x_t, const float* eps, const long long* t, const long long* t_next, const float* abar,
                       float* x_next, int batch, long long per_sample, cudaStream_t st);
 void launch_consistency_loss(const float* x_t, const float* eps_s, const long long* t, const float* x_next, const float* eps_tgt,

@@ -377,6 +377,23 @@ void launch_lcm_mix(const float* a, const float* b, const long long* t, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// condition_mode="add" (low_light_diffusion.py:108-113,158-160,223-225): model_input = latents + condition_encoder(low_light)
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+void launch_add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_f32_kernel<<<(int)blocks, 256, 0, st>>>(a, b, out, n);
+}
+__global__ void fill_float2_kernel(float2* __restrict__ p, float2 v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_float2(float2* p, float2 v, long long n, cudaStream_t st) {
+  fill_float2_kernel<<<(int)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256), 256, 0, st>>>(p, v, n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Consistency distillation (low_light_diffusion.py:325-408), the element-wise parts around the three UNet forwards.
 // DDIM step of the teacher (:372-381): x0 = (x_t - sqrt(1 - a_t) eps) / sqrt(a_t) ; x_next = sqrt(a_n) x0 + sqrt(1 - a_n) eps,
 // per-sample timesteps t, t_next.

@@ -194,6 +194,7 @@ struct lcm_plan {
 
   int film_rows = 0;
   size_t film_f_off = 0, silu_f_off = 0;
+  size_t addtmp_f_off = 0;   // condition_mode="add" (in_channels == out_channels): latents + condition features, fp32 NCHW
 
   std::vector<Op> ops;
   // ---- training (LCM_FLAG_TRAIN) -------------------------------------------------------------------
@@ -1030,6 +1031,7 @@ int build_plan(lcm_plan* p) {
   };
   const int ted = c.time_embed_dim, base = c.base_channels;
 
+  if (c.in_channels == c.out_channels) p->addtmp_f_off = p->falloc((size_t)N * c.in_channels * H * W * sizeof(float));
   // a2: time embedding (efficient_unet.py:550)
   {
     const size_t w1 = p->add_copy("time_mlp.1.weight", (int64_t)ted * base), b1 = p->add_copy("time_mlp.1.bias", ted);
@@ -1469,6 +1471,70 @@ int lcm_enhance(lcm_plan* plan, const float* cond_dev, float* latents_dev, const
     rc = run_forward(plan, c, (cudaStream_t)stream, nullptr, 0);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int lcm_enhance_add(lcm_plan* plan, const float* cond_feat_dev, float* latents_dev, const float* noises_dev, int steps,
+                    const int64_t* timesteps, const float* coef, float* out_dev, float* trace_dev, void* workspace, void* stream) {
+  if (!plan || !cond_feat_dev || !latents_dev || !timesteps || !coef || !out_dev || !workspace)
+    return fail(LCM_ERR_INVALID, "null argument");
+  if (steps < 1) return fail(LCM_ERR_INVALID, "steps must be >= 1");
+  if (steps > 1 && !noises_dev) return fail(LCM_ERR_INVALID, "noises_dev is required for steps > 1");
+  if (plan->cfg.in_channels != plan->cfg.out_channels)
+    return fail(LCM_ERR_INVALID, "enhance_add needs add conditioning: in_channels == out_channels");
+  int rc = check_ready(plan);
+  if (rc) return rc;
+  const int C = plan->cfg.out_channels;
+  const long long per = (long long)C * plan->H * plan->W, all = per * plan->N;
+  RunCtx c = make_ctx(plan, workspace);
+  float* tmp = (float*)(c.f + plan->addtmp_f_off);
+  rc = fill_inputs(plan, c, tmp, C, per, nullptr, 0, 0);
+  if (rc) return rc;
+  for (int i = 0; i < steps; ++i) {
+    const bool last = i == steps - 1;
+    launch_add_f32(latents_dev, cond_feat_dev, tmp, all, (cudaStream_t)stream);   // model_input = latents + condition_feat (:223-225)
+    c.t_dev = nullptr;
+    c.t_scalar = timesteps[i];
+    c.eps = nullptr;
+    c.step.enabled = 1;
+    c.step.noise = last ? nullptr : noises_dev + (long long)i * all;
+    c.step.latents = latents_dev;
+    c.step.clamped = last ? out_dev : nullptr;
+    c.step.trace = trace_dev ? trace_dev + (long long)i * all : nullptr;
+    c.step.sb_t = coef[4 * i + 0]; c.step.sa_t = coef[4 * i + 1]; c.step.sa_p = coef[4 * i + 2]; c.step.sb_p = coef[4 * i + 3];
+    rc = run_forward(plan, c, (cudaStream_t)stream, nullptr, 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+size_t lcm_condition_encode_scratch_bytes(int batch, int height, int width, int hidden) {
+  const size_t px = (size_t)batch * height * width;
+  return align_up(px * hidden * sizeof(float), 1024) + align_up((size_t)batch * hidden * (2 * sizeof(double) + sizeof(float2)), 1024) +
+         align_up((size_t)9 * 3 * hidden * sizeof(float) * 2, 1024) + 4096;
+}
+
+int lcm_condition_encode(const float* low_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                         float* out_dev, int batch, int height, int width, int hidden, void* scratch_dev, void* stream) {
+  if (!low_dev || !w1_dev || !b1_dev || !w2_dev || !b2_dev || !out_dev || !scratch_dev) return fail(LCM_ERR_INVALID, "null argument");
+  if (hidden % 8 || hidden < 8 || hidden > 64 || batch < 1 || height < 1 || width < 1) return fail(LCM_ERR_INVALID, "bad condition encoder shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* s = (char*)scratch_dev;
+  const size_t px = (size_t)batch * height * width;
+  float* hid = (float*)s; s += align_up(px * hidden * sizeof(float), 1024);
+  double* stats = (double*)s; s += (size_t)batch * hidden * 2 * sizeof(double);
+  float2* coef = (float2*)s; s = (char*)scratch_dev + align_up(px * hidden * sizeof(float), 1024) + align_up((size_t)batch * hidden * (2 * sizeof(double) + sizeof(float2)), 1024);
+  float* w1 = (float*)s; s += (size_t)9 * 3 * hidden * sizeof(float);
+  float* w2 = (float*)s;
+  { PackJob j{}; j.kind = PACK_CONV3_KN; j.dst = w1; j.R = hidden; j.Ci = 3; launch_pack(j, w1_dev, st); }
+  { PackJob j{}; j.kind = PACK_CONV3_KN; j.dst = w2; j.R = 3; j.Ci = hidden; launch_pack(j, w2_dev, st); }
+  CUDA_TRY(cudaMemsetAsync(stats, 0, (size_t)batch * hidden * 2 * sizeof(double), st));
+  launch_fill_float2(coef, make_float2(1.f, 0.f), (long long)batch * hidden, st);
+  // Conv2d(3, hidden, 3, padding=1) -> SiLU -> Conv2d(hidden, 3, 3, padding=1)   (low_light_diffusion.py:108-113), fp32
+  launch_init_conv(low_dev, 3, (long long)3 * height * width, nullptr, 0, 0, w1, b1_dev, hid, stats, batch, height, width, hidden, 0, st);
+  FinalStep none{};
+  launch_final_conv(hid, coef, w2, b2_dev, out_dev, none, batch, height, width, hidden, 3, 0, st);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -115,8 +115,10 @@ class Engine:
 
     # ---- LowLightDiffusion.enhance loop -------------------------------------------------------------
     def enhance(self, cond: torch.Tensor, latents: torch.Tensor, noises: Optional[torch.Tensor],
-                timesteps: Sequence[int], coefs: Sequence[Sequence[float]], trace: bool = False):
-        """`latents` is updated in place and holds the pre-clamp result afterwards."""
+                timesteps: Sequence[int], coefs: Sequence[Sequence[float]], trace: bool = False, add_mode: bool = False):
+        """`latents` is updated in place and holds the pre-clamp result afterwards.  add_mode: `cond` holds the condition
+        encoder's features and the UNet input of every step is latents + cond (condition_mode="add")."""
+        entry = self.lib.lcm_enhance_add if add_mode else self.lib.lcm_enhance
         b, h, w = self.shape
         for t_, nm in ((cond, "low_light"), (latents, "latents")):
             _require_cuda(t_, nm)
@@ -134,7 +136,7 @@ class Engine:
 
         def call(cond_, lat_, noises_, out_, tr_):
             with torch.cuda.device(self.device):
-                native.check(self.lib.lcm_enhance(self.handle, C.c_void_p(cond_.data_ptr()), C.c_void_p(lat_.data_ptr()),
+                native.check(entry(self.handle, C.c_void_p(cond_.data_ptr()), C.c_void_p(lat_.data_ptr()),
                                                   C.c_void_p(noises_.data_ptr()) if steps > 1 else None, steps, ts, cf,
                                                   C.c_void_p(out_.data_ptr()), C.c_void_p(tr_.data_ptr()) if trace else None,
                                                   C.c_void_p(self.workspace.data_ptr()), _stream_ptr()))
@@ -143,7 +145,7 @@ class Engine:
         # the third call on it is replayed as ONE CUDA graph over static buffers (-2.4 % at Small@256 B=64: the gaps
         # between dependent kernels shrink; packed weights live at fixed addresses, so weight updates need no re-capture).
         # LCM_NO_GRAPH=1 disables it.
-        key = (steps, tuple(int(t) for t in timesteps), tuple(flat), bool(trace))
+        key = (steps, tuple(int(t) for t in timesteps), tuple(flat), bool(trace), bool(add_mode))
         ent = self._graphs.get(key) if self._use_graph and not torch.cuda.is_current_stream_capturing() else None
         if self._use_graph and ent is None and not torch.cuda.is_current_stream_capturing():
             ent = self._graphs[key] = {"calls": 0, "graph": None}
@@ -274,6 +276,27 @@ def unet_forward(unet, x: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
     if x.dim() != 4:
         raise ValueError("x must be [B, C, H, W]")
     return get_engine(unet, x.shape[0], x.shape[2], x.shape[3], x.device).forward(x, timestep)
+
+
+def condition_encode(low_light: torch.Tensor, encoder) -> torch.Tensor:
+    """``condition_encoder(low_light)`` of condition_mode="add" (low_light_diffusion.py:108-113): Conv3x3 -> SiLU -> Conv3x3 on
+    the native fp32 conv kernels.  ``encoder``: the nn.Sequential holding the two convolutions (indices 0 and 2)."""
+    _require_cuda(low_light, "low_light")
+    b, c, h, w = low_light.shape
+    if c != 3:
+        raise ValueError("low_light must have 3 channels")
+    conv1, conv2 = encoder[0], encoder[2]
+    hidden = conv1.out_channels
+    lib = native.lib()
+    low = low_light.contiguous()
+    out = torch.empty_like(low)
+    scratch = torch.empty(lib.lcm_condition_encode_scratch_bytes(b, h, w, hidden), dtype=torch.uint8, device=low.device)
+    ws = [t.detach().to(device=low.device, dtype=torch.float32).contiguous() for t in (conv1.weight, conv1.bias, conv2.weight, conv2.bias)]
+    with torch.cuda.device(low.device):
+        native.check(lib.lcm_condition_encode(C.c_void_p(low.data_ptr()), *[C.c_void_p(t.data_ptr()) for t in ws],
+                                              C.c_void_p(out.data_ptr()), b, h, w, hidden, C.c_void_p(scratch.data_ptr()),
+                                              _stream_ptr()))
+    return out
 
 
 def lcm_step(model_output: torch.Tensor, sample: torch.Tensor, noise: Optional[torch.Tensor], prediction_type: str,

@@ -183,7 +183,8 @@ class EfficientUNet(nn.Module):
                         last[int(name.split(".")[1])] = name          # the level's last block / attention output
                 feats = [eng.read_tap(last[k]) for k in sorted(last)]
             return out, feats
-        if self.training and torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and x.is_cuda and x.shape[1] > self.config.out_channels \
+                and any(p.requires_grad for p in self.parameters()):
             from .training import native_unet_forward   # training: activations are kept, eps carries autograd
             return native_unet_forward(self, x, timestep)
         from .engine import unet_forward  # late import: needs the CUDA library

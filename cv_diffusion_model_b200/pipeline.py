@@ -29,19 +29,21 @@ class LowLightDiffusion(nn.Module):
                  unet_variant: str = "small", image_size: int = 256, num_inference_steps: int = 4,
                  condition_mode: str = "concat", groupnorm: str = "strict", precision: Optional[str] = None):
         super().__init__()
-        if condition_mode != "concat":
-            raise ValueError('only condition_mode="concat" is supported by the B200 path '
-                             '("add" is a non-default mode outside the hot path, SURVEY §2)')
+        if condition_mode not in ("concat", "add"):
+            raise ValueError(f"Unknown condition mode: {condition_mode}")
         self.image_size = image_size
         self.num_inference_steps = num_inference_steps
         self.condition_mode = condition_mode
+        in_channels = 6 if condition_mode == "concat" else 3          # reference :77
         self.unet = unet if unet is not None else create_efficient_unet(
-            variant=unet_variant, image_size=image_size, groupnorm=groupnorm, in_channels=6)
+            variant=unet_variant, image_size=image_size, groupnorm=groupnorm, in_channels=in_channels)
         if precision is not None:          # an explicitly passed unet keeps its own precision unless told otherwise
             self.unet.precision = precision
         self.scheduler = scheduler if scheduler is not None else LCMScheduler(
             num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
             num_inference_steps=num_inference_steps, rescale_betas_zero_snr=True)
+        if condition_mode == "add":   # created after the UNet and the scheduler, like the reference (:108-113): same random init
+            self.condition_encoder = nn.Sequential(nn.Conv2d(3, 32, 3, padding=1), nn.SiLU(), nn.Conv2d(32, 3, 3, padding=1))
 
     # ---- inference -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -82,7 +84,11 @@ class LowLightDiffusion(nn.Module):
                     noises[i].zero_()
         eng = get_engine(self.unet, b, s, s, device)
         low = low_light.to(torch.float32).contiguous()
-        res = eng.enhance(low, latents.contiguous(), noises, ts, coefs, trace=return_intermediate)
+        add = self.condition_mode == "add"
+        if add:     # model_input = latents + condition_encoder(low_light) in every step (:223-225); the features are constant
+            from .engine import condition_encode
+            low = condition_encode(low, self.condition_encoder)
+        res = eng.enhance(low, latents.contiguous(), noises, ts, coefs, trace=return_intermediate, add_mode=add)
         self.scheduler._step_index = steps
         if return_intermediate:
             out, tr = res
@@ -117,7 +123,14 @@ class LowLightDiffusion(nn.Module):
         if noise is None:
             noise = torch.randn_like(normal_light)
         noisy = self.scheduler.add_noise(normal_light, noise, timesteps)
-        noise_pred = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
+        if self.condition_mode == "concat":
+            noise_pred = self.unet(torch.cat([noisy, low_light], dim=1), timesteps)
+        else:   # :158-160 — inference-style evaluation only: the native backward covers the concat pipeline
+            if torch.is_grad_enabled() and self.training:
+                raise NotImplementedError('training with condition_mode="add" is not implemented natively (the condition '
+                                          'encoder and the UNet input would need gradients); use condition_mode="concat"')
+            from .engine import condition_encode
+            noise_pred = self.unet(noisy + condition_encode(low_light.to(torch.float32), self.condition_encoder), timesteps)
         if return_dict:
             return {"noise_pred": noise_pred, "noise": noise, "timesteps": timesteps}
         return noise_pred
@@ -138,6 +151,10 @@ class LowLightDiffusion(nn.Module):
             timesteps = torch.randint(0, self.scheduler.config.num_train_timesteps, (b,), device=device)
         if noise is None:
             noise = torch.randn_like(normal_light)
+        if self.condition_mode != "concat":
+            import torch.nn.functional as F
+            out = self.forward(low_light, normal_light, timesteps=timesteps, noise=noise)
+            return {"mse": F.mse_loss, "huber": F.huber_loss, "l1": F.l1_loss}[loss_type](out["noise_pred"], out["noise"])
         noisy = self.scheduler.add_noise(normal_light.contiguous(), noise.contiguous(), timesteps)
         if not torch.is_grad_enabled():
             import torch.nn.functional as F
@@ -148,6 +165,36 @@ class LowLightDiffusion(nn.Module):
 
     def get_model_size(self) -> Dict[str, float]:
         return self.unet.get_memory_footprint()
+
+    # ---- checkpoints in the reference trainer's format (trainer.py:415-456, scripts/inference.py:78-79) ------------------
+    def load_reference_checkpoint(self, checkpoint, use_ema: bool = False, strict: bool = True):
+        """Load what the reference writes: a path / dict with ``model_state_dict`` (``save_checkpoint``), a bare
+        ``state_dict`` (``scripts/benchmark.py:56``), optionally replacing the weights by the ``ema_shadow`` the trainer
+        stores next to them (keys are the parameter names, values the EMA weights — ``EMAModel.shadow``, trainer.py:86-96)."""
+        ckpt = torch.load(checkpoint, map_location="cpu", weights_only=False) if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") else checkpoint
+        sd = ckpt.get("model_state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
+        sd = dict(sd)
+        if use_ema:
+            shadow = ckpt.get("ema_shadow") if isinstance(ckpt, dict) else None
+            if not shadow:
+                raise ValueError("the checkpoint has no ema_shadow")
+            for k, v in shadow.items():
+                if k not in sd:
+                    raise ValueError(f"ema_shadow entry '{k}' is not a parameter of the checkpoint")
+                sd[k] = v
+        result = self.load_state_dict(sd, strict=strict)
+        self.unet.invalidate_engines()
+        meta = {k: ckpt[k] for k in ("epoch", "global_step", "best_val_loss", "config") if isinstance(ckpt, dict) and k in ckpt}
+        return result, meta
+
+    def reference_checkpoint(self, ema_shadow: Optional[Dict[str, torch.Tensor]] = None, **meta) -> Dict:
+        """The dict ``LowLightTrainer.save_checkpoint`` writes for this model (weights part): loadable by the reference's
+        ``load_checkpoint`` / ``scripts/inference.py`` unchanged."""
+        out = {"model_state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}}
+        if ema_shadow is not None:
+            out["ema_shadow"] = {k: v.detach().cpu().clone() for k, v in ema_shadow.items()}
+        out.update(meta)
+        return out
 
 
 def normalize_image(image: torch.Tensor) -> torch.Tensor:

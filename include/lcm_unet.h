@@ -108,6 +108,15 @@ int lcm_enhance(lcm_plan* plan, const float* cond_dev, float* latents_dev, const
                 int steps, const int64_t* timesteps, const float* coef, float* out_dev, float* trace_dev,
                 void* workspace, void* stream);
 
+/* ---- condition_mode="add" (low_light_diffusion.py:108-113,158-160,223-225): the UNet has in_channels == out_channels, its
+ * input is latents + condition_encoder(low_light).  lcm_condition_encode runs the encoder (Conv3x3(3->hidden) -> SiLU ->
+ * Conv3x3(hidden->3), weights in the reference's layouts, fp32) once; lcm_enhance_add is lcm_enhance with the per-step add. */
+size_t lcm_condition_encode_scratch_bytes(int batch, int height, int width, int hidden);
+int lcm_condition_encode(const float* low_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                         float* out_dev, int batch, int height, int width, int hidden, void* scratch_dev, void* stream);
+int lcm_enhance_add(lcm_plan* plan, const float* cond_feat_dev, float* latents_dev, const float* noises_dev, int steps,
+                    const int64_t* timesteps, const float* coef, float* out_dev, float* trace_dev, void* workspace, void* stream);
+
 /* ---- LCMScheduler.step (lcm_scheduler.py:204-242), stand-alone.  prediction: 0 epsilon, 1 v_prediction.
  * noise_dev == NULL means last step (prev = x0). */
 int lcm_scheduler_step(const float* model_out_dev, const float* sample_dev, const float* noise_dev,

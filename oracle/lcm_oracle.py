@@ -57,18 +57,29 @@ def step(eps: torch.Tensor, t: int, sample: torch.Tensor, schedule: Sequence[int
     return a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * noise, x0
 
 
+def condition_encoder(enc_sd: Dict[str, torch.Tensor], low_light: torch.Tensor) -> torch.Tensor:
+    """condition_mode="add" (low_light_diffusion.py:108-113): Conv2d(3,32,3,p=1) -> SiLU -> Conv2d(32,3,3,p=1); keys
+    `0.weight`, `0.bias`, `2.weight`, `2.bias` (the nn.Sequential's)."""
+    import torch.nn.functional as F
+    h = F.silu(F.conv2d(low_light, enc_sd["0.weight"], enc_sd["0.bias"], padding=1))
+    return F.conv2d(h, enc_sd["2.weight"], enc_sd["2.bias"], padding=1)
+
+
 @torch.no_grad()
 def enhance(sd: Dict[str, torch.Tensor], cfg, low_light: torch.Tensor, latents0: torch.Tensor,
             noises: Sequence[torch.Tensor], num_inference_steps: int = 4, strict_groupnorm: bool = True,
-            return_all: bool = False):
-    """low_light_diffusion.py:204-240 with injected randomness.  `noises` has steps-1 entries."""
+            return_all: bool = False, condition_encoder_sd: Optional[Dict[str, torch.Tensor]] = None):
+    """low_light_diffusion.py:204-240 with injected randomness.  `noises` has steps-1 entries.  With
+    `condition_encoder_sd` the conditioning is "add" (:223-225): model_input = latents + condition_encoder(low_light)."""
     abar = alphas_cumprod()
     sched = timesteps(num_inference_steps)
     latents = latents0
     trace = []
+    feat = condition_encoder(condition_encoder_sd, low_light) if condition_encoder_sd is not None else None
     for i, t in enumerate(sched):
         tt = torch.full((low_light.shape[0],), t, dtype=torch.long, device=low_light.device)
-        eps = unet_oracle.unet_forward(sd, cfg, torch.cat([latents, low_light], dim=1), tt, strict_groupnorm)
+        x = torch.cat([latents, low_light], dim=1) if feat is None else latents + feat
+        eps = unet_oracle.unet_forward(sd, cfg, x, tt, strict_groupnorm)
         nz = noises[i] if i < len(sched) - 1 else None
         latents, _ = step(eps, t, latents, sched, abar, nz)
         trace.append((eps, latents))

@@ -158,9 +158,12 @@ def main():
         out[f"unet_{tag}_t"] = t.numpy()
 
     # ---- 4. whole enhance loop, reference RNG protocol ----------------------------------------
-    for tag, variant, size, b, steps in [("small64", "small", 64, 2, 4), ("small32_8step", "small", 32, 1, 8)]:
+    for tag, variant, size, b, steps in [("small64", "small", 64, 2, 4), ("small32_8step", "small", 32, 1, 8),
+                                         ("add64", "small", 64, 2, 4)]:
+        add = tag.startswith("add")      # condition_mode="add": latents + condition_encoder(low_light), 3-channel UNet
         torch.manual_seed(0)
-        pipe = RefPipeline(unet_variant=variant, image_size=size, num_inference_steps=steps).eval()
+        pipe = RefPipeline(unet_variant=variant, image_size=size, num_inference_steps=steps,
+                           condition_mode="add" if add else "concat").eval()
         randomise_affine(pipe.unet)
         low = torch.rand(b, 3, size, size, generator=torch.Generator().manual_seed(1234)) * 0.2 * 2 - 1
         gen = torch.Generator().manual_seed(9)
@@ -170,12 +173,20 @@ def main():
         lat0 = torch.randn(b, 3, size, size, generator=torch.Generator().manual_seed(9))
         torch.manual_seed(5)
         noises = [torch.randn(b, 3, size, size) for _ in range(steps - 1)]
-        sd = unet_oracle.strip_unet_prefix(pipe.state_dict())
-        o, trace = lcm_oracle.enhance(sd, pipe.unet.config, low, lat0, noises, steps, return_all=True)
+        full = pipe.state_dict()
+        sd = {k[5:]: v for k, v in full.items() if k.startswith("unet.")}
+        enc = {k[len("condition_encoder."):]: v for k, v in full.items() if k.startswith("condition_encoder.")} if add else None
+        if add:   # the package's pipeline creates the same parameters in the same order
+            from cv_diffusion_model_b200 import LowLightDiffusion as MyPipeline
+            torch.manual_seed(0)
+            mine = MyPipeline(unet_variant=variant, image_size=size, num_inference_steps=steps, condition_mode="add")
+            randomise_affine(mine.unet)
+            assert list(mine.state_dict()) == list(full) and all(torch.equal(mine.state_dict()[k], full[k]) for k in full)
+        o, trace = lcm_oracle.enhance(sd, pipe.unet.config, low, lat0, noises, steps, return_all=True, condition_encoder_sd=enc)
         err = (o - res.enhanced).abs().max().item()
         print(f"enhance {tag}: oracle max|diff|={err:.3e}  saturated={(res.enhanced.abs() == 1).float().mean():.3f}")
         assert err <= 1e-5
-        digests[f"enhance_{tag}"] = sd_digest(sd)
+        digests[f"enhance_{tag}"] = sd_digest(full if add else sd)
         out[f"enh_{tag}_low"] = low.numpy()
         out[f"enh_{tag}_lat0"] = lat0.numpy()
         out[f"enh_{tag}_noises"] = torch.stack(noises).numpy() if noises else np.zeros((0,))

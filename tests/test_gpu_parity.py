@@ -409,3 +409,41 @@ def test_engines_on_two_devices_in_one_process():
         outs.append(eng.forward(x.to(f"cuda:{d}"), t.to(f"cuda:{d}")).cpu())
         eng.close()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_enhance_add_conditioning_vs_reference_golden(golden, weight_digests, precision):
+    """condition_mode="add" (low_light_diffusion.py:108-113,223-225): 3-channel UNet on latents + condition_encoder(low_light),
+    free-running 4-step loop against the unmodified reference's output."""
+    from cv_diffusion_model_b200 import LowLightDiffusion
+    from tests.util import randomise_affine
+    torch.manual_seed(0)
+    pipe = LowLightDiffusion(unet_variant="small", image_size=64, num_inference_steps=4, condition_mode="add", precision=precision)
+    randomise_affine(pipe.unet)
+    assert sd_digest(pipe.state_dict()) == weight_digests["enhance_add64"]
+    assert pipe.unet.config.in_channels == 3 and "condition_encoder.2.bias" in pipe.state_dict()
+    low, lat0 = torch.from_numpy(golden["enh_add64_low"]), torch.from_numpy(golden["enh_add64_lat0"])
+    noises = torch.from_numpy(golden["enh_add64_noises"])
+    pipe = pipe.cuda().eval()
+    res = pipe.enhance(low.cuda(), latents=lat0.cuda(), noises=noises.cuda(), return_intermediate=True)
+    pre, want_pre = res.intermediate[-1].cpu(), torch.from_numpy(golden["enh_add64_preclamp"])
+    assert torch.equal(res.enhanced.cpu(), pre.clamp(-1, 1))
+    if precision == "fp32":
+        assert (pre - want_pre).abs().max().item() <= 5e-3
+        assert (res.enhanced.cpu() - torch.from_numpy(golden["enh_add64_out"])).abs().max().item() <= 5e-3
+    else:
+        sd = {k[5:]: v.cpu() for k, v in pipe.state_dict().items() if k.startswith("unet.")}
+        enc = {k[len("condition_encoder."):]: v.cpu() for k, v in pipe.state_dict().items() if k.startswith("condition_encoder.")}
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            _, tr = lcm_oracle.enhance(sd, pipe.unet.config, low, lat0, list(noises), 4, return_all=True, condition_encoder_sd=enc)
+        ref_bf16 = psnr(tr[-1][1].float(), want_pre, 2.0)
+        got = psnr(pre, want_pre, 2.0)
+        print(f"add conditioning bf16: PSNR {got:.1f} dB (reference under torch bf16 autocast: {ref_bf16:.1f} dB)")
+        assert got >= min(33.0, ref_bf16 - 1.0)
+    # training-style forward without autograd works; with autograd it states what is missing
+    pipe.train()
+    with torch.no_grad():
+        out = pipe(low.cuda(), lat0.cuda().clamp(-1, 1), timesteps=torch.tensor([10, 700]).cuda())
+    assert out["noise_pred"].shape == (2, 3, 64, 64)
+    with pytest.raises(NotImplementedError):
+        pipe.compute_loss(low.cuda(), lat0.cuda().clamp(-1, 1))

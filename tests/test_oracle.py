@@ -158,3 +158,29 @@ def test_image_io_oracle_matches_reference_golden():
     assert x.min() == -1.0 and x.max() == 1.0
     back = image_io_oracle.postprocess_u8(x).astype(np.int32)
     assert ((u.astype(np.int32) - back) >= 0).all() and ((u.astype(np.int32) - back) <= 1).all()
+
+
+def test_reference_checkpoint_format_roundtrip(tmp_path):
+    """Checkpoints in the reference trainer's format (trainer.py:415-456): `model_state_dict` with the 321 `unet.*` keys,
+    optional `ema_shadow` keyed by parameter name; a bare state_dict (scripts/benchmark.py:56) loads too."""
+    from cv_diffusion_model_b200 import LowLightDiffusion
+    torch.manual_seed(0)
+    a = LowLightDiffusion(unet_variant="small", image_size=64)
+    shadow = {k: v.detach() * 0.5 for k, v in a.named_parameters()}
+    ckpt = a.reference_checkpoint(ema_shadow=shadow, epoch=3, global_step=120, best_val_loss=0.25)
+    assert len(ckpt["model_state_dict"]) == 381 and all(k.startswith("unet.") for k in ckpt["model_state_dict"])
+    path = tmp_path / "checkpoint_epoch_3.pt"
+    torch.save(ckpt, path)
+    torch.manual_seed(1)
+    b = LowLightDiffusion(unet_variant="small", image_size=64)
+    _, meta = b.load_reference_checkpoint(str(path))
+    assert meta == {"epoch": 3, "global_step": 120, "best_val_loss": 0.25}
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+    b.load_reference_checkpoint(ckpt, use_ema=True)
+    assert all(torch.equal(p * 0.5, q) for p, q in zip(a.parameters(), b.parameters()))
+    b.load_reference_checkpoint(a.state_dict())            # bare state_dict
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+    with pytest.raises(ValueError):
+        b.load_reference_checkpoint({"model_state_dict": a.state_dict()}, use_ema=True)
+    with pytest.raises(RuntimeError):                        # torch's own strict-key error, like the reference
+        b.load_reference_checkpoint({"model_state_dict": {k: v for k, v in list(a.state_dict().items())[:-1]}})
