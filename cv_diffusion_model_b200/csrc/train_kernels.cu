@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
   float* tv = dsm + HSY * HS * CB;      // [HSY*HS][CB] v halo tile
   __shared__ __align__(16) float s_w[9 * CB];
   __shared__ float s_red[8][2 * CB];
+  __shared__ __align__(16) float2 s_cse[CB], s_c2[CB];   // this image's prologue coefficients (reloaded when the image changes)
   const int tid = threadIdx.x;
   const int c0 = blockIdx.y * CB;
   const int cg = tid & 3;               // fill phase: 8-channel group
@@ -434,6 +435,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
   int cur_n = -1;
 
   auto flush = [&](int n) {
+    // s2 holds sum du * v (v = a2 h1 + b2 wherever du != 0): sum du * h1 = (s2 - b2 s1) / a2
+    {
+      const float s1v[4] = {s1.x, s1.y, s1.z, s1.w};
+      float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 ab = s_c2[q * 4 + j];
+        s2v[j] = fabsf(ab.x) > 1e-30f ? (s2v[j] - ab.y * s1v[j]) / ab.x : 0.f;
+      }
+      s2 = make_float4(s2v[0], s2v[1], s2v[2], s2v[3]);
+    }
     // lanes with equal q (l, l^8, l^16) hold the same channels: reduce them, then the 8 warps through shared memory
     float a[4] = {s1.x, s1.y, s1.z, s1.w}, b[4] = {s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
@@ -457,17 +469,19 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
   for (long long it = i0; it < i1; ++it) {
     const int n = (int)(it / tiles), tile = (int)(it % tiles);
     if (n != cur_n) {
-      if (cur_n >= 0) flush(cur_n);
+      if (cur_n >= 0) flush(cur_n);     // (ends with a block-wide barrier: nobody still reads the old coefficients)
       cur_n = n;
+      if (tid < CB) s_cse[tid] = coef_se[(size_t)n * C + c0 + tid];
+      else if (tid < 2 * CB) s_c2[tid - CB] = coef2[(size_t)n * C + c0 + tid - CB];
     }
     const int ty0 = (tile / tilesX) * TSY, tx0 = (tile % tilesX) * TSX;
-    __syncthreads();   // previous tile fully consumed
+    __syncthreads();   // previous tile fully consumed; coefficients visible
     {
       float2 cse[8], c2[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        cse[j] = coef_se[(size_t)n * C + c0 + cg * 8 + j];
-        c2[j] = coef2[(size_t)n * C + c0 + cg * 8 + j];
+        cse[j] = s_cse[cg * 8 + j];
+        c2[j] = s_c2[cg * 8 + j];
       }
       // 720 (pixel, channel-group) items over 256 threads: three fully unrolled rounds, every global load issued before the
       // first use (the fill is latency-bound otherwise: one DRAM round trip per round)
@@ -584,32 +598,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
     }
     // note: pixels of the tile that lie outside the image have dh2 = 0 in the halo tile, so their gc is 0 and they add
     // nothing to dW; their dv is simply not stored
-    float2 ab4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ab4[j] = coef2[(size_t)n * C + c0 + q * 4 + j];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int gx = tx0 + xs + p;
       if (gy >= H || gx >= W) continue;
       const size_t o = (((size_t)n * H + gy) * W + gx) * C + c0 + q * 4;
-      // ReLU6 backward: pre-activation u = a2 h1 + b2 of the centre pixel
-      float hc[4], d4[4] = {dv[p].x, dv[p].y, dv[p].z, dv[p].w};
-      if (F32) {
-        const float4 t4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(h1) + o);
-        hc[0] = t4.x; hc[1] = t4.y; hc[2] = t4.z; hc[3] = t4.w;
-      } else if (dth == DT_BF16) {
-        const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(h1) + o);
-        hc[0] = bf16lo(t2.x); hc[1] = bf16hi(t2.x); hc[2] = bf16lo(t2.y); hc[3] = bf16hi(t2.y);
-      } else {
-        const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(h1) + o);
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t2.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t2.y));
-        hc[0] = f0.x; hc[1] = f0.y; hc[2] = f1.x; hc[3] = f1.y;
-      }
+      // ReLU6 backward from the activation itself: v = clamp(u, 0, 6), so 0 < u < 6  <=>  0 < v < 6 (and then v == u)
+      const float4 vc = *reinterpret_cast<const float4*>(tv + ((row + 1) * HS + xs + 1 + p) * CB + q * 4);
+      const float vv[4] = {vc.x, vc.y, vc.z, vc.w};
+      float d4[4] = {dv[p].x, dv[p].y, dv[p].z, dv[p].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float u = fmaf(ab4[j].x, hc[j], ab4[j].y);
-        d4[j] = (u > 0.f && u < 6.f) ? d4[j] : 0.f;
-      }
+      for (int j = 0; j < 4; ++j) d4[j] = (vv[j] > 0.f && vv[j] < 6.f) ? d4[j] : 0.f;
       if (F32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(du) + o) = make_float4(d4[0], d4[1], d4[2], d4[3]);
       } else {
@@ -620,7 +619,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
         d4[0] = bf16lo(pk.x); d4[1] = bf16hi(pk.x); d4[2] = bf16lo(pk.y); d4[3] = bf16hi(pk.y);
       }
       s1.x += d4[0]; s1.y += d4[1]; s1.z += d4[2]; s1.w += d4[3];
-      s2.x = fmaf(d4[0], hc[0], s2.x); s2.y = fmaf(d4[1], hc[1], s2.y); s2.z = fmaf(d4[2], hc[2], s2.z); s2.w = fmaf(d4[3], hc[3], s2.w);
+      s2.x = fmaf(d4[0], vv[0], s2.x); s2.y = fmaf(d4[1], vv[1], s2.y); s2.z = fmaf(d4[2], vv[2], s2.z); s2.w = fmaf(d4[3], vv[3], s2.w);
     }
   }
   if (cur_n >= 0) flush(cur_n);
