@@ -10,13 +10,13 @@
 // MN-major operand (the same trick as the Gram MMA of gemm_expand.cu): D[k][n] (TMEM, lane = k, column = n) accumulates
 // A_chunk^T . dY_chunk, 16 pixels per instruction, over ALL pixel tiles a CTA owns — one epilogue per CTA.
 //
-//   warps 0-3   XF    in-place prologue on the landed A chunks (ReLU6(a x + b) for the expand, gate * h2 for the project,
-//                     a x + b for to_qkv) — then, at the very end, the epilogue: TMEM -> fp32 atomics into the flat
-//                     gradient buffer (reference state_dict layout)
-//   warp  4     TMA   A chunks (1-2) + dY chunks (1-4) per 128-pixel tile into a ring of stages
-//   warp  5     MMA   8 instructions (M = 128, N = 64..256, K = 16 pixels) per tile; owns the TMEM allocation
+//   warps 0-7   XF    in-place prologue on the landed A chunks (ReLU6(a x + b) for the expand, gate * h2 for the project,
+//                     a x + b for to_qkv; fp16 chunks are re-packed as bf16) — warps 0-3 then run the epilogue at the very
+//                     end: TMEM -> fp32 atomics into the flat gradient buffer (reference state_dict layout)
+//   warp  8     TMA   A chunks (1-2) + dY chunks (1-2) per 128-pixel tile into a ring of 3-4 stages
+//   warp  9     MMA   8 instructions (M = 128, N = 64 / 128, K = 16 pixels) per tile; owns the TMEM allocation
 //
-// Work split: output tiles (128 A-channels x up to 256 dY-channels) x pixel splits, all CTAs co-resident.  At the two
+// Work split: output tiles (128 A-channels x 128 dY-channels) x pixel splits, all CTAs co-resident.  At the two
 // high-resolution levels (K <= 192) the op streams (K + N) * 2 bytes per pixel once: HBM-bound.
 #include <cstdlib>
 #include <cstring>
@@ -31,9 +31,10 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreadsWT = 192;
-constexpr int kXfThreadsWT = 128;
-constexpr int kTmaWarpWT = 4, kMmaWarpWT = 5;
+constexpr int kThreadsWT = 320;
+constexpr int kXfThreadsWT = 256;            // 8 prologue warps (the first four also run the epilogue: TMEM lane quadrants)
+constexpr int kTmaWarpWT = 8, kMmaWarpWT = 9;
+constexpr int kNChunksWT = 2;                // dY chunks per output tile (N = 128): stages of 48-64 KB, 3-4 of them in flight
 constexpr uint32_t kChunkWT = 16384;         // 128 pixels x 64 16-bit channels
 constexpr uint32_t kSmemLimitWT = 232448;
 constexpr int kMaxAChunksWT = 96;            // K up to 6144 channels
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   const int ot = blockIdx.x / p.splits, split = blockIdx.x - ot * p.splits;
   const int mb = ot / p.n_nblocks, nb = ot - mb * p.n_nblocks;
   const int nA = p.mb_count[mb], a0 = p.mb_first[mb];
-  const int y0 = nb * 4;
-  const int nY = min(4, p.nychunks - y0);
+  const int y0 = nb * kNChunksWT;
+  const int nY = min(kNChunksWT, p.nychunks - y0);
   const int t_begin = (int)((long long)p.m_tiles * split / p.splits);
   const int t_end = (int)((long long)p.m_tiles * (split + 1) / p.splits);
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ================================ XF: prologue of the A chunks, in place ====================================
     const int xt = tid;
     const int cu = (xt & 7) ^ ((xt >> 3) & 7);     // the 8-channel unit this thread owns in every row it touches
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
             for (int j = 0; j < 4; ++j) { const float4 c = c4[j]; ab[2 * j] = make_float2(c.x, c.y); ab[2 * j + 1] = make_float2(c.z, c.w); }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 1024 / kXfThreadsWT; ++i) {
             const uint32_t addr = a_smem + (uint32_t)(xt + i * kXfThreadsWT) * 16u;
             const uint4 v = lds128(addr);
             float f[8];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
       if (++tin == tiles_per_img) { tin = 0; ++img; }
     }
     // ================================ epilogue: TMEM -> fp32 atomics =============================================
-    if (t_end > t_begin) {
+    if (t_end > t_begin && warp < 4) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const int m = warp * 32 + lane;                 // TMEM lane = A channel within the M-block
@@ -300,19 +301,19 @@ int launch_wgrad_tc(const GemmParams& g, const int* seg_dt, const void* dY, int 
     if (!tmap_rows128(g.seg[s].A, g.M, g.seg[s].K, g.seg[s].ld, f16 ? TMAP_F16 : TMAP_BF16, &p.tmap_a[s])) return -3;
     p.coef[s] = g.seg[s].coef; p.coef_ld[s] = g.seg[s].coef_ld; p.coef_off[s] = g.seg[s].coef_off;
     p.dst[s] = dst[s]; p.dst_ld[s] = dst_ld[s];
-    const int first = nch;
     for (int c0 = 0; c0 < g.seg[s].K; c0 += 64) {
       if (nch >= kMaxAChunksWT) return -1;
       const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;
       p.achunk_c0[nch] = (uint16_t)c0;
       p.achunk[nch++] = (uint32_t)s | ((uint32_t)kv << 8) | ((uint32_t)g.seg[s].mode << 24) | ((f16 ? 1u : 0u) << 28);
     }
-    // M-blocks never span segments (operand format and destination are per segment): pairs of chunks, a single one at the end
-    for (int c = first; c < nch; c += 2) {
-      p.mb_first[nmb] = (uint8_t)c;
-      p.mb_count[nmb] = (uint8_t)(c + 1 < nch ? 2 : 1);
-      ++nmb;
-    }
+  }
+  // M-blocks = consecutive pairs of chunks (they may span segments: mode, destination and source map are per chunk, and the
+  // prologue hands every chunk to the tensor core as bf16)
+  for (int c = 0; c < nch; c += 2) {
+    p.mb_first[nmb] = (uint8_t)c;
+    p.mb_count[nmb] = (uint8_t)(c + 1 < nch ? 2 : 1);
+    ++nmb;
   }
   if (!tmap_rows128(dY, g.M, g.Nc, g.Nc, TMAP_BF16, &p.tmap_y)) return -3;
   p.n_mblocks = nmb;
@@ -325,10 +326,10 @@ namespace {
 int launch_common(WTParams& p, int num_sms, cudaStream_t st) {
   const int nmb = p.n_mblocks;
   p.nychunks = (p.Nc + 63) / 64;
-  p.n_nblocks = (p.nychunks + 3) / 4;
+  p.n_nblocks = (p.nychunks + kNChunksWT - 1) / kNChunksWT;
   int maxA = 1;
   for (int i = 0; i < nmb; ++i) if (p.mb_count[i] > maxA) maxA = p.mb_count[i];
-  const int maxY = p.nychunks < 4 ? p.nychunks : 4;
+  const int maxY = p.nychunks < kNChunksWT ? p.nychunks : kNChunksWT;
   p.stage_bytes = (uint32_t)(maxA + maxY) * kChunkWT;
   p.y_off = (uint32_t)maxA * kChunkWT;
   const uint32_t fixed = 1024 /* coef */ + 1024 /* misc */ + 1024 /* align */;
