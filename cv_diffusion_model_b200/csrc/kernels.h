@@ -196,8 +196,10 @@ void launch_wgrad_1x1(const GemmParams& p, const int* seg_dt, const void* dY, in
 // the same on the tensor cores (wgrad_tc.cu, bf16 plan); non-zero = shape not covered, use the CUDA-core kernel
 int launch_wgrad_tc(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
                     int num_sms, cudaStream_t st);
-int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int num_sms,
-                          cudaStream_t st);   // stride-1 conv on the tensor cores (bf16); bias via launch_colsum
+// dense 3x3 conv (pad 1, stride 1 or 2) on the tensor cores (bf16); H, W = INPUT size; bias via launch_colsum
+int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int stride, int num_sms,
+                          cudaStream_t st);
+void launch_zero_insert2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t st);   // 16-bit, C % 8 == 0
 void launch_colsum(const void* g, int dt, long long rows, int C, float* out, cudaStream_t st);
 void launch_wgrad_conv3(const void* in, int dti, const void* dY, int dty, float* dW, float* dbias, int N, int Hin, int Win, int Ci,
                         int Co, int mode, int num_sms, cudaStream_t st);

@@ -947,7 +947,11 @@ struct Builder {
       // transposed-conv weights: W'[ci][(8 - tap) * stride + co] (flipped taps, swapped channel roles)
       PackJob jt{};
       jt.kind = PACK_CONV3_T; jt.bf16 = p->bf16 ? 1 : 0; jt.R = C; jt.Cc = C; jt.Ci = C;
-      const bool tc_dgrad = p->tc && mode_in == CONV_UP2;   // stride-1 transposed conv = conv over dY: tcgen05 kernel
+      // stride-1 transposed conv = conv over dY: tcgen05 kernel.  A stride-2 conv's input gradient is the same stride-1
+      // transposed conv over the zero-inserted dY (Z[2y][2x] = dY[y][x]): 4x the MMA work of a phase decomposition, but
+      // the tensor core is idle otherwise and the op stays one halo-mode conv (was 10.8 ms of CUDA-core time per step)
+      const bool s2_tc = p->tc && mode_in == CONV_S2 && x->H % 2 == 0 && x->W % 2 == 0;
+      const bool tc_dgrad = p->tc && (mode_in == CONV_UP2 || s2_tc);
       size_t wt_off;
       int bn_t = 0;
       if (tc_dgrad) {
@@ -967,8 +971,8 @@ struct Builder {
         const size_t g_w = wg(wname + ".weight"), g_b = wg(wname + ".bias");
         // weight + bias gradient; the fp32 plan recomputes the bilinear blend inside the loader (mode UP2 on the low-res input)
         pushb(name + ".wgrad", "wgrad_simt", {wname + ".weight", wname + ".bias"}, [=](const RunCtx& c, cudaStream_t st) {
-          if (pl->tc && mode == CONV_S1 &&
-              launch_wgrad_conv3_tc(c.a + x->off, c.g + dY, c.wg + g_w, n, Hin, Win, C, C, pl->num_sms, st) == 0) {
+          if (pl->tc && (mode == CONV_S1 || s2_tc) &&
+              launch_wgrad_conv3_tc(c.a + x->off, c.g + dY, c.wg + g_w, n, Hin, Win, C, C, mode == CONV_S2 ? 2 : 1, pl->num_sms, st) == 0) {
             launch_colsum(c.g + dY, dtg, (long long)n * Ho * Wo, C, c.wg + g_b, st);
             return;
           }
@@ -978,6 +982,21 @@ struct Builder {
           const GradW gx = grad_w(x);
           const size_t bytes = (size_t)n * Hin * Win * C * gsz;
           const size_t tmp = gx.accumulate ? galloc(bytes) : 0;
+          if (s2_tc) {
+            const size_t Z = galloc(bytes);
+            pushb(name + ".dgrad.zero_insert", "zero_insert2x", {}, [=](const RunCtx& c, cudaStream_t st) {
+              launch_zero_insert2x(c.g + dY, c.g + Z, n, Ho, Wo, C, st);
+            });
+            pushb(name + ".dgrad", "conv3x3_tc", {}, [=](const RunCtx& c, cudaStream_t st) {
+              GemmParams gp{};
+              gp.nseg = 1; gp.seg[0].A = c.g + Z; gp.seg[0].K = 9 * C; gp.seg[0].ld = C; gp.seg[0].mode = XF_NONE;
+              gp.Ktot = 9 * C; gp.W = pl->wbase + wt_off; gp.out = c.g + (gx.accumulate ? tmp : gx.off); gp.stats = nullptr;
+              gp.P = Hin * Win; gp.M = (long long)n * Hin * Win; gp.Nc = C;
+              ConvGeom cg{CONV_S1, Hin, Win, Hin, Win, C, nullptr};
+              if (launch_gemm_tc(gp, cg, bn_t, pl->num_sms, st)) *c.launch_err = 1;
+            });
+            gfree(Z, bytes);
+          } else
           pushb(name + ".dgrad", "conv3x3_dgrad_simt", {}, [=](const RunCtx& c, cudaStream_t st) {
             launch_conv3x3_dgrad_simt(c.g + dY, pl->wbase + wt_off, c.g + (gx.accumulate ? tmp : gx.off), n, Hin, Win, C, C, CONV_S2,
                                       pl->bf16, st);

@@ -334,6 +334,115 @@ __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restric
     v_ds2[(size_t)n * C + c] = ds2[c];
   }
   __syncthreads();
+  // The three FC products are latency problems (64 blocks, weights of up to 2 x 1 MB out of L2): every stage keeps
+  // several independent 16-byte loads in flight per thread and spreads its reduction dimension over the whole block.
+  const bool vec = (C % 128 == 0) && (SQ % 4 == 0) && SQ <= 1024;
+  float* scr = dz1 + SQ;     // [1024] partial sums of stages 2 and 3
+  if (vec) {
+    for (int j = warp; j < SQ; j += 8) {          // z_pre[j] = b1[j] + w1[j][:] . pm
+      const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * C);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 w = wr[c4];
+        const float4 m = *reinterpret_cast<const float4*>(pm + c4 * 4);
+        a0 = fmaf(w.x, m.x, a0); a1 = fmaf(w.y, m.y, a1); a2 = fmaf(w.z, m.z, a2); a3 = fmaf(w.w, m.w, a3);
+      }
+      float acc = (a0 + a1) + (a2 + a3);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const float zp = acc + b1[j];
+        z[j] = fminf(fmaxf(zp, 0.f), 6.f);
+        dz1[j] = (zp > 0.f && zp < 6.f) ? 1.f : 0.f;   // mask for now
+      }
+    }
+    __syncthreads();
+    {                                             // dz[j] = sum_c ds2[c] w2[c][j]: thread = (4 columns j, slice of c)
+      const int nj = SQ / 4;                      // threads across j
+      const int parts = nj >= 256 ? 1 : 256 / nj; // slices of c (nj is a power of two or a divisor of 256 for the presets)
+      for (int j4 = tid % nj; j4 < nj; j4 += (nj >= 256 ? 256 : nj)) {
+        const int part = nj >= 256 ? 0 : tid / nj;
+        if (part < parts) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          int c = part;
+          for (; c + parts < C; c += 2 * parts) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w2 + (size_t)c * SQ + j4 * 4);
+            const float4 w1v = *reinterpret_cast<const float4*>(w2 + (size_t)(c + parts) * SQ + j4 * 4);
+            const float d0 = ds2[c], d1 = ds2[c + parts];
+            a.x = fmaf(d0, w0.x, a.x); a.y = fmaf(d0, w0.y, a.y); a.z = fmaf(d0, w0.z, a.z); a.w = fmaf(d0, w0.w, a.w);
+            b.x = fmaf(d1, w1v.x, b.x); b.y = fmaf(d1, w1v.y, b.y); b.z = fmaf(d1, w1v.z, b.z); b.w = fmaf(d1, w1v.w, b.w);
+          }
+          for (; c < C; c += parts) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w2 + (size_t)c * SQ + j4 * 4);
+            const float d0 = ds2[c];
+            a.x = fmaf(d0, w0.x, a.x); a.y = fmaf(d0, w0.y, a.y); a.z = fmaf(d0, w0.z, a.z); a.w = fmaf(d0, w0.w, a.w);
+          }
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          if (parts == 1) {
+            dz1[j4 * 4 + 0] *= a.x; dz1[j4 * 4 + 1] *= a.y; dz1[j4 * 4 + 2] *= a.z; dz1[j4 * 4 + 3] *= a.w;
+          } else {
+            *reinterpret_cast<float4*>(scr + (part * nj + j4) * 4) = a;   // parts * SQ <= 1024 floats
+          }
+        }
+        if (nj < 256) break;
+      }
+      if (parts > 1) {
+        __syncthreads();
+        for (int j = tid; j < SQ; j += 256) {
+          float acc = 0.f;
+          for (int q = 0; q < parts; ++q) acc += scr[q * SQ + j];
+          dz1[j] *= acc;
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < SQ; j += 256) {
+        v_z[(size_t)n * SQ + j] = z[j];
+        v_dz1[(size_t)n * SQ + j] = dz1[j];
+      }
+    }
+    {                                             // dpm[c] = sum_j dz1[j] w1[j][c]: thread = (4 channels c, slice of j)
+      const int nc = C / 4;
+      if (nc >= 256) {
+        for (int c4 = tid; c4 < nc; c4 += 256) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          int j = 0;
+          for (; j + 1 < SQ; j += 2) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w1 + (size_t)j * C + c4 * 4);
+            const float4 w1v = *reinterpret_cast<const float4*>(w1 + (size_t)(j + 1) * C + c4 * 4);
+            const float d0 = dz1[j], d1 = dz1[j + 1];
+            a.x = fmaf(d0, w0.x, a.x); a.y = fmaf(d0, w0.y, a.y); a.z = fmaf(d0, w0.z, a.z); a.w = fmaf(d0, w0.w, a.w);
+            b.x = fmaf(d1, w1v.x, b.x); b.y = fmaf(d1, w1v.y, b.y); b.z = fmaf(d1, w1v.z, b.z); b.w = fmaf(d1, w1v.w, b.w);
+          }
+          for (; j < SQ; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w1 + (size_t)j * C + c4 * 4);
+            const float d0 = dz1[j];
+            a.x = fmaf(d0, w0.x, a.x); a.y = fmaf(d0, w0.y, a.y); a.z = fmaf(d0, w0.z, a.z); a.w = fmaf(d0, w0.w, a.w);
+          }
+          const float r[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            coef_se[(size_t)n * C + c4 * 4 + e] = make_float2(gate[(size_t)n * C + c4 * 4 + e].x, r[e] * inv_count);
+        }
+      } else {
+        const int parts = 256 / nc, c4 = tid % nc, part = tid / nc;   // nc in {32, 64, 96 -> parts 2 (64 threads idle), 128, 192}
+        if (part < parts) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = part; j < SQ; j += parts) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w1 + (size_t)j * C + c4 * 4);
+            const float d0 = dz1[j];
+            a.x = fmaf(d0, w0.x, a.x); a.y = fmaf(d0, w0.y, a.y); a.z = fmaf(d0, w0.z, a.z); a.w = fmaf(d0, w0.w, a.w);
+          }
+          *reinterpret_cast<float4*>(scr + (part * nc + c4) * 4) = a;   // parts * C <= 1024 floats
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += 256) {
+          float acc = 0.f;
+          for (int q = 0; q < parts; ++q) acc += scr[q * C + c];
+          coef_se[(size_t)n * C + c] = make_float2(gate[(size_t)n * C + c].x, acc * inv_count);
+        }
+      }
+    }
+    return;
+  }
   for (int j = warp; j < SQ; j += 8) {          // z_pre[j] = b1[j] + w1[j][:] . pm
     float acc = 0.f;
     for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], pm[c], acc);
@@ -363,7 +472,7 @@ __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restric
 int launch_se_bwd_vec(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2, const float2* gate,
                       const double* t12, float2* coef_se, float* v_pm, float* v_z, float* v_ds2, float* v_dz1, int N, int C,
                       int SQ, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * C + 2 * SQ) * sizeof(float);
+  const size_t smem = (size_t)(2 * C + 2 * SQ + 1024) * sizeof(float);
   if (ensure_dyn_smem_fn(se_bwd_vec_kernel, smem)) return 1;
   se_bwd_vec_kernel<<<N, 256, smem, st>>>(pool, inv_count, w1, b1, w2, gate, t12, coef_se, v_pm, v_z, v_ds2, v_dz1, C, SQ);
   return 0;
@@ -921,6 +1030,29 @@ void launch_upsample2x_any(const void* in, void* out, int dt, int N, int H, int 
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   upsample2x_any_kernel<<<(int)blocks, 256, 0, st>>>(in, out, dt, H, W, C, total);
+}
+
+// zero insertion: out[n][2y][2x][:] = in[n][y][x][:], every other element 0 (16-bit tensors).  The input gradient of a
+// stride-2 3x3 conv is the STRIDE-1 transposed conv of this tensor, which runs on the tensor cores (conv3x3_tc, halo mode).
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int cvecs,
+                                                            long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int cv = (int)(i % cvecs);
+    long long q = i / cvecs;
+    const int X = (int)(q % (2 * W));
+    q /= 2 * W;
+    const int Y = (int)(q % (2 * H));
+    const long long n = q / (2 * H);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (!((X | Y) & 1)) v = in[(((size_t)n * H + (Y >> 1)) * W + (X >> 1)) * cvecs + cv];
+    out[i] = v;
+  }
+}
+void launch_zero_insert2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t st) {
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  zero_insert2x_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), H, W, C / 8, total);
 }
 
 // transpose: d in[y][x] = sum_{i,j} wy[i] wx[j] d out[Y_i][X_j],  Y_i in {2y-1, 2y, 2y+1, 2y+2}:

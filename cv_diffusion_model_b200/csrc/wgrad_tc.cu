@@ -53,9 +53,10 @@ struct WTParams {
   int n_mblocks, n_nblocks, nychunks, Nc;
   int m_tiles, P, splits, stages;
   uint32_t stage_bytes, y_off, coef_smem_off, misc_off;
-  // dense 3x3 conv (stride 1): achunk's segment field is the TAP, the A chunk of tap (ky, kx) is the image box shifted by
-  // (kx - 1, ky - 1) (out-of-image elements zero-filled by TMA = the conv's padding); dW layout [Co][Ci][3][3]
-  int conv, Wimg, box_w, box_h, Ci;
+  // dense 3x3 conv (stride 1 or 2): achunk's segment field is the TAP, the A chunk of tap (ky, kx) is the image box shifted
+  // by (kx - 1, ky - 1) (out-of-image elements zero-filled by TMA = the conv's padding; stride 2: tensor map with element
+  // strides 2, every second pixel / row of a twice as large window); dW layout [Co][Ci][3][3].  Wimg = OUTPUT width.
+  int conv, Wimg, box_w, box_h, Ci, cstride;
   CUtensorMap tmap_img;
   float* conv_dst;
 };
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
           for (int ci = 0; ci < nA; ++ci) {
             const uint32_t cd = p.achunk[a0 + ci];
             const int tap = cd & 0xff, ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d_wt(sb + (uint32_t)ci * kChunkWT, &p.tmap_img, (int)p.achunk_c0[a0 + ci], x0 + kx - 1, y0 + ky - 1, n, raw_bar(stage));
+            tma_load_4d_wt(sb + (uint32_t)ci * kChunkWT, &p.tmap_img, (int)p.achunk_c0[a0 + ci], p.cstride * x0 + kx - 1, p.cstride * y0 + ky - 1, n,
+                           raw_bar(stage));
           }
         } else {
           for (int ci = 0; ci < nA; ++ci) {
@@ -351,25 +353,29 @@ int launch_common(WTParams& p, int num_sms, cudaStream_t st) {
 }
 }  // namespace
 
-// dense 3x3, stride 1, pad 1 (the up-convolutions on the materialised bilinear output): in [N][H][W][Ci] bf16,
-// dY [N][H][W][Co] bf16 -> dW [Co][Ci][3][3] (+=).  Tiles of 128 output pixels must be image boxes (128 | W, or W | 128
-// with whole rows).  Returns non-zero when the shape is not covered.
-int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int num_sms,
+// dense 3x3, pad 1, stride 1 (the up-convolutions on the materialised bilinear output) or 2 (the downsamplers):
+// in [N][H][W][Ci] bf16, dY [N][H/stride][W/stride][Co] bf16 -> dW [Co][Ci][3][3] (+=).  Tiles of 128 output pixels must be
+// image boxes (128 | Wout, or Wout | 128 with whole rows).  Returns non-zero when the shape is not covered.
+int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int stride, int num_sms,
                           cudaStream_t st) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("LCM_NO_WGRAD_TC"); off = (e && atoi(e)) ? 1 : 0; }
-  const long long P = (long long)H * W, M = P * N;
-  const bool boxable = (W >= 128 ? W % 128 == 0 : 128 % W == 0) && P % 128 == 0;
+  if (stride != 1 && stride != 2) return -1;
+  if (H % stride || W % stride) return -1;
+  const int Ho = H / stride, Wo = W / stride;
+  const long long P = (long long)Ho * Wo, M = P * N;
+  const bool boxable = (Wo >= 128 ? Wo % 128 == 0 : 128 % Wo == 0) && P % 128 == 0;
   if (off || !boxable || Ci % 16 || Co % 16 || M > 0x7fffff00LL || 9 * ((Ci + 63) / 64) > kMaxAChunksWT) return -1;
   WTParams p;
   memset(&p, 0, sizeof(p));
-  p.conv = 1; p.Wimg = W; p.Ci = Ci; p.conv_dst = dW;
-  p.box_w = W >= 128 ? 128 : W; p.box_h = 128 / p.box_w;
+  p.conv = 1; p.Wimg = Wo; p.Ci = Ci; p.conv_dst = dW; p.cstride = stride;
+  p.box_w = Wo >= 128 ? 128 : Wo; p.box_h = 128 / p.box_w;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstride[3] = {(cuuint64_t)Ci * 2, (cuuint64_t)W * Ci * 2, (cuuint64_t)H * W * Ci * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.box_w, (cuuint32_t)p.box_h, 1};
-    if (!encode_tmap(&p.tmap_img, TMAP_BF16, 4, in, gdim, gstride, box, true)) return -3;
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.box_w * stride), (cuuint32_t)(p.box_h * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (!encode_tmap(&p.tmap_img, TMAP_BF16, 4, in, gdim, gstride, box, true, estr)) return -3;
   }
   int nch = 0, nmb = 0;
   for (int tap = 0; tap < 9; ++tap)

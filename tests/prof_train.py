@@ -73,6 +73,30 @@ def main():
     print("slowest ops:")
     for dt, name, kern in sorted(rows, reverse=True)[:25]:
         print(f"  {dt:8.3f} ms  {kern:20s} {name}")
+    if os.environ.get("PROF_ALL"):
+        print("all backward ops (execution order):")
+        for dt, name, kern in rows:
+            print(f"  {dt:8.3f} ms  {kern:20s} {name}")
+        # per-op forward profile of the TRAINING plan (same C call as the inference profiler)
+        import ctypes as C
+        from cv_diffusion_model_b200 import native
+        cap = eng.lib.lcm_plan_launches_per_forward(eng.handle)
+        recs = (native.OpProfileC * cap)()
+        tt = t.to(torch.long).contiguous()
+        epsb = torch.empty_like(eps)
+        for _ in range(2):
+            n = native.check(eng.lib.lcm_plan_profile_forward(
+                eng.handle, C.c_void_p(noisy.data_ptr()), noisy.shape[1], noisy.stride(0), C.c_void_p(low.data_ptr()), low.shape[1],
+                low.stride(0), C.c_void_p(tt.data_ptr()), C.c_void_p(epsb.data_ptr()), C.c_void_p(eng.workspace.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream().cuda_stream), recs, cap))
+        print("forward ops of the training plan:")
+        fby = defaultdict(lambda: [0.0, 0])
+        for i in range(min(n, cap)):
+            r = recs[i]
+            fby[r.kernel.decode()][0] += r.ms; fby[r.kernel.decode()][1] += 1
+            print(f"  {r.ms:8.3f} ms  {r.kernel.decode():16s} {r.name.decode():44s} {r.bytes / max(r.ms, 1e-9) / 1e6:8.0f} GB/s")
+        for k, (msk, nn) in sorted(fby.items(), key=lambda kv: -kv[1][0]):
+            print(f"  fwd {k:18s} {msk:8.3f} ms {nn:4d} ops")
 
 
 if __name__ == "__main__":
