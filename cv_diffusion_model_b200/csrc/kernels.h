@@ -183,14 +183,18 @@ void launch_bwd_add(const void* src, int dts, int lds, int soff, void* dst, int 
 // GroupNorm (+FiLM) backward finalise: (T1, T2) + forward statistics -> (A, B, C), d gamma, d beta, d FiLM rows
 void launch_gn_bwd_coef(const double* t12, const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
                         const float* gamma, const float* beta, const float* film, float* dfilm, int film_ld, float4* coef4,
-                        float* dgamma, float* dbeta, int N, cudaStream_t st);
+                        float* dgamma, float* dbeta, int N, cudaStream_t st, const float* ascale = nullptr, int ascale_stride = 0);
+// coef_se[n][c] = (gate s, dpm/P s, 1/s, 0); s = 1 unless dq_stats (sum, sum^2 of dq per (image, channel)) is given
 int launch_se_bwd_vec(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2, const float2* gate,
-                      const double* t12, float2* coef_se, float* v_pm, float* v_z, float* v_ds2, float* v_dz1, int N, int C,
-                      int SQ, cudaStream_t st);
+                      const double* t12, const double* dq_stats, float4* coef_se, float* v_pm, float* v_z, float* v_ds2,
+                      float* v_dz1, int N, int C, int SQ, cudaStream_t st);
 void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* dW, float* dbias, int N, int R, int Cc,
                       cudaStream_t st);
-void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
+void launch_dwconv_bwd(const void* dq, int dtg, const float4* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
                        void* du, double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st);
+// streaming packed-fp16 version (dwconv_bwd_stream.cu): dq bf16, h1 fp16, du fp16 SCALED by the s of coef_se; C % 64 == 0
+int launch_dwconv_bwd_stream(const void* dq, const float4* cse, const void* h1, const float2* coef2, const float* w, void* du,
+                             double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st);
 void launch_wgrad_1x1(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
                       int num_sms, cudaStream_t st);
 // the same on the tensor cores (wgrad_tc.cu, bf16 plan); non-zero = shape not covered, use the CUDA-core kernel

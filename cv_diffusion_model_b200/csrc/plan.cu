@@ -336,13 +336,16 @@ struct Builder {
     return d;
   }
   // out[M][Nc'] = dY[M][K] . W'^T  (input gradient of a 1x1 conv); all buffers in region G
-  void dgrad_gemm(const std::string& name, size_t dy_off, const DgradW& w, size_t out_off, int P) {
+  // stats_zb (optional, tensor-core plan): offset in region ZB of a zeroed [N][Nc][2] fp64 table that receives the
+  // per-(image, channel) sum / sum^2 of the output (the GEMM's statistics epilogue)
+  void dgrad_gemm(const std::string& name, size_t dy_off, const DgradW& w, size_t out_off, int P, size_t stats_zb = (size_t)-1) {
     lcm_plan* pl = p; const int n = N;
     pushb(name, pl->tc ? "gemm_tc" : "gemm_simt", {}, [=](const RunCtx& c, cudaStream_t st) {
       GemmParams gp{};
       gp.nseg = 1;
       gp.seg[0].A = c.g + dy_off; gp.seg[0].K = w.K; gp.seg[0].ld = w.K; gp.seg[0].mode = XF_NONE;
-      gp.Ktot = w.K; gp.W = pl->wbase + w.off; gp.out = c.g + out_off; gp.stats = nullptr;
+      gp.Ktot = w.K; gp.W = pl->wbase + w.off; gp.out = c.g + out_off;
+      gp.stats = (pl->tc && stats_zb != (size_t)-1) ? (double*)(c.zb + stats_zb) : nullptr;
       gp.P = P; gp.M = (long long)n * P; gp.Nc = w.Nc;
       if (pl->tc) { ConvGeom g{}; g.mode = -1; if (launch_gemm_tc(gp, g, w.block_n, pl->num_sms, st)) *c.launch_err = 1; }
       else launch_gemm_simt(gp, pl->bf16, st);
@@ -350,7 +353,8 @@ struct Builder {
   }
   // GroupNorm backward finalise for a view x (one or two tensors): (T1, T2) in ZB -> coef4 in FB, d gamma / d beta
   struct GnInfo { size_t coef, g_off, b_off; int G; double count; std::string wname; };
-  size_t gn_backward(const std::string& name, const View& x, const GnInfo& gi, size_t t12, int film_row0) {
+  // ascale_fb (optional): offset in region FB of a float4 table whose .z is multiplied into A (see gn_bwd_coef_kernel)
+  size_t gn_backward(const std::string& name, const View& x, const GnInfo& gi, size_t t12, int film_row0, size_t ascale_fb = (size_t)-1) {
     const int C = x.C();
     const size_t coef4 = p->fballoc((size_t)N * C * sizeof(float4));
     const size_t s0 = x.part[0]->stats_off; const int C0 = x.part[0]->C;
@@ -362,7 +366,8 @@ struct Builder {
       float* dfilm = film_row0 >= 0 ? (float*)(c.fb + pl->dfilm_fb_off) + film_row0 : nullptr;
       launch_gn_bwd_coef((const double*)(c.zb + t12), (const double*)(c.z + s0), C0, C1 ? (const double*)(c.z + s1) : nullptr, C1,
                          gi.G, gi.count, pl->wf(gi.g_off), pl->wf(gi.b_off), film, dfilm, pl->film_rows,
-                         (float4*)(c.fb + coef4), c.wg + dg, c.wg + db, n, st);
+                         (float4*)(c.fb + coef4), c.wg + dg, c.wg + db, n, st,
+                         ascale_fb != (size_t)-1 ? (const float*)(c.fb + ascale_fb) + 2 : nullptr, 4);
     });
     return coef4;
   }
@@ -582,7 +587,10 @@ struct Builder {
       const size_t dY = grad_r(out);
       // 1. project dgrad
       const size_t dq = galloc(M * Ch * gsz);
-      dgrad_gemm(name + ".project.dgrad", dY, wpT, dq, P);
+      // streaming packed-fp16 depthwise backward (tensor-core plan): needs sum dq^2 per (image, channel) for its scales
+      const bool dwb_stream = pl->tc && Ch % 64 == 0 && !getenv("LCM_NO_DWB_STREAM");
+      const size_t dq_stats = dwb_stream ? pl->zballoc((size_t)n * Ch * 2 * sizeof(double)) : (size_t)-1;
+      dgrad_gemm(name + ".project.dgrad", dY, wpT, dq, P, dq_stats);
       // 2. project (+ skip) wgrad
       {
         std::vector<std::string> writes{name + ".project.weight"};
@@ -622,12 +630,13 @@ struct Builder {
       pushb(name + ".se.dgate", "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
         launch_bwd_mask_reduce(c.g + dq, dtg, Ch, 0, c.a + h2->off, dth, Ch, 0, nullptr, 0, (double*)(c.zb + t12se), Ch, n, P, Ch, 0, st);
       });
-      const size_t coef_se = pl->fballoc((size_t)n * Ch * sizeof(float2));
+      const size_t coef_se = pl->fballoc((size_t)n * Ch * sizeof(float4));
       const size_t v_pm = pl->fballoc((size_t)n * Ch * 4), v_ds2 = pl->fballoc((size_t)n * Ch * 4);
       const size_t v_z = pl->fballoc((size_t)n * SQ * 4), v_dz1 = pl->fballoc((size_t)n * SQ * 4);
       pushb(name + ".se.bwd", "se_bwd_vec", {}, [=](const RunCtx& c, cudaStream_t st) {
         if (launch_se_bwd_vec((const double*)(c.z + pool), (float)(1.0 / P), pl->wf(w1), pl->wf(b1), pl->wf(w2),
-                              (const float2*)(c.f + gate), (const double*)(c.zb + t12se), (float2*)(c.fb + coef_se),
+                              (const float2*)(c.f + gate), (const double*)(c.zb + t12se),
+                              dwb_stream ? (const double*)(c.zb + dq_stats) : nullptr, (float4*)(c.fb + coef_se),
                               (float*)(c.fb + v_pm), (float*)(c.fb + v_z), (float*)(c.fb + v_ds2), (float*)(c.fb + v_dz1), n, Ch, SQ, st))
           *c.launch_err = 1;
       });
@@ -648,15 +657,22 @@ struct Builder {
       {
         const size_t g_dw = wg(name + ".depthwise.weight");
         pushb(name + ".depthwise.bwd", "dwconv_bwd", {name + ".depthwise.weight"}, [=](const RunCtx& c, cudaStream_t st) {
-          launch_dwconv_bwd(c.g + dq, dtg, (const float2*)(c.fb + coef_se), c.a + h1->off, dth, (const float2*)(c.f + gn2.coef),
+          if (dwb_stream) {
+            if (launch_dwconv_bwd_stream(c.g + dq, (const float4*)(c.fb + coef_se), c.a + h1->off, (const float2*)(c.f + gn2.coef),
+                                         pl->wf(dw_off), c.g + du, (double*)(c.zb + t12h), c.wg + g_dw, n, h, w, Ch, pl->num_sms, st))
+              *c.launch_err = 1;
+            return;
+          }
+          launch_dwconv_bwd(c.g + dq, dtg, (const float4*)(c.fb + coef_se), c.a + h1->off, dth, (const float2*)(c.f + gn2.coef),
                             pl->wf(dw_off), c.g + du, (double*)(c.zb + t12h), c.wg + g_dw, n, h, w, Ch, pl->num_sms, st);
         });
       }
       gfree(dq, M * Ch * gsz);
       // 6.-7. norm2 + FiLM backward, dh1 in place
-      const size_t coef4h = gn_backward(name + ".norm2.bwd", View::of(h1), gn2, t12h, row0);
+      // (streaming path: du is stored as fp16 scaled by s; the 1/s rides in A, the in-place result is the plan's gradient type)
+      const size_t coef4h = gn_backward(name + ".norm2.bwd", View::of(h1), gn2, t12h, row0, dwb_stream ? coef_se : (size_t)-1);
       pushb(name + ".norm2.apply", "bwd_affine3", {}, [=](const RunCtx& c, cudaStream_t st) {
-        launch_bwd_affine3(c.g + du, dtg, Ch, 0, c.a + h1->off, dth, Ch, 0, (const float4*)(c.fb + coef4h), Ch, 0, nullptr, 0, 0, 0,
+        launch_bwd_affine3(c.g + du, dwb_stream ? (int)DT_F16 : dtg, Ch, 0, c.a + h1->off, dth, Ch, 0, (const float4*)(c.fb + coef4h), Ch, 0, nullptr, 0, 0, 0,
                            c.g + du, dtg, Ch, 0, 0, n, P, Ch, st);
       });
       // 8. expand dgrad

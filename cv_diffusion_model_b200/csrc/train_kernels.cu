@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const double* __restri
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ film, float* __restrict__ dfilm, int film_ld,
                                                           float4* __restrict__ coef4, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta) {
+                                                          float* __restrict__ dbeta, const float* __restrict__ ascale,
+                                                          int ascale_stride) {
   __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
   const int n = blockIdx.x;
   const int C = C0 + C1;
@@ -295,15 +296,17 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const double* __restri
     atomicAdd(dgamma + c, sc * dxhat_y);
     atomicAdd(dbeta + c, sc * T1);
     const float k = gm * sc;
-    coef4[(size_t)n * C + c] = make_float4(r * k, -r * r * m2, -r * m1 + r * r * m2 * mu, 0.f);
+    // ascale: the gradient tensor this A multiplies is stored scaled (du * s of dwconv_bwd_stream.cu): A carries the 1/s
+    const float as = ascale ? ascale[((size_t)n * C + c) * ascale_stride] : 1.f;
+    coef4[(size_t)n * C + c] = make_float4(r * k * as, -r * r * m2, -r * m1 + r * r * m2 * mu, 0.f);
   }
 }
 
 void launch_gn_bwd_coef(const double* t12, const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
                         const float* gamma, const float* beta, const float* film, float* dfilm, int film_ld, float4* coef4,
-                        float* dgamma, float* dbeta, int N, cudaStream_t st) {
+                        float* dgamma, float* dbeta, int N, cudaStream_t st, const float* ascale, int ascale_stride) {
   gn_bwd_coef_kernel<<<N, 256, 0, st>>>(t12, stats0, C0, stats1, C1, groups, count, gamma, beta, film, dfilm, film_ld, coef4,
-                                        dgamma, dbeta);
+                                        dgamma, dbeta, ascale, ascale_stride);
 }
 
 // =================================================================================================
@@ -316,15 +319,33 @@ void launch_gn_bwd_coef(const double* t12, const double* stats0, int C0, const d
 __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restrict__ pool, float inv_count,
                                                          const float* __restrict__ w1, const float* __restrict__ b1,
                                                          const float* __restrict__ w2, const float2* __restrict__ gate,
-                                                         const double* __restrict__ t12, float2* __restrict__ coef_se,
-                                                         float* __restrict__ v_pm, float* __restrict__ v_z,
-                                                         float* __restrict__ v_ds2, float* __restrict__ v_dz1, int C, int SQ) {
+                                                         const double* __restrict__ t12, const double* __restrict__ dq_stats,
+                                                         float4* __restrict__ coef_se, float* __restrict__ v_pm,
+                                                         float* __restrict__ v_z, float* __restrict__ v_ds2,
+                                                         float* __restrict__ v_dz1, int C, int SQ) {
   extern __shared__ float sm[];
   float* pm = sm;            // [C]
   float* ds2 = pm + C;       // [C]
   float* z = ds2 + C;        // [SQ]
   float* dz1 = z + SQ;       // [SQ]
   const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // coef_se[n][c] = (gate s, dpm/P s, 1/s, 0).  s = 1 unless the streaming depthwise backward runs its packed-fp16
+  // arithmetic on this block (dq_stats = per-(image, channel) sum / sum^2 of dq from the project-dgrad GEMM): then s is the
+  // power of two with (gate rms(dq) + |dpm/P|) s in (0.5, 1] — see dwconv_bwd_stream.cu.
+  auto write_cse = [&](int c, float g, float dpm_p) {
+    float sc = 1.f;
+    if (dq_stats) {
+      const float ms = fmaxf((float)dq_stats[((size_t)n * C + c) * 2 + 1], 0.f) * inv_count;
+      const float bound = g * sqrtf(ms) + fabsf(dpm_p);
+      if (bound > 0.f && bound < 1e30f) {
+        int e;
+        frexpf(1.f / bound, &e);                        // 1 / bound = m 2^e, m in [0.5, 1)
+        e = max(-40, min(60, e - 1));
+        sc = ldexpf(1.f, e);
+      }
+    }
+    coef_se[(size_t)n * C + c] = make_float4(g * sc, dpm_p * sc, 1.f / sc, 0.f);
+  };
   for (int c = tid; c < C; c += 256) {
     const float m = (float)pool[(size_t)n * C + c] * inv_count;
     const float g = gate[(size_t)n * C + c].x;
@@ -420,7 +441,7 @@ __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restric
           const float r[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            coef_se[(size_t)n * C + c4 * 4 + e] = make_float2(gate[(size_t)n * C + c4 * 4 + e].x, r[e] * inv_count);
+            write_cse(c4 * 4 + e, gate[(size_t)n * C + c4 * 4 + e].x, r[e] * inv_count);
         }
       } else {
         const int parts = 256 / nc, c4 = tid % nc, part = tid / nc;   // nc in {32, 64, 96 -> parts 2 (64 threads idle), 128, 192}
@@ -437,7 +458,7 @@ __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restric
         for (int c = tid; c < C; c += 256) {
           float acc = 0.f;
           for (int q = 0; q < parts; ++q) acc += scr[q * C + c];
-          coef_se[(size_t)n * C + c] = make_float2(gate[(size_t)n * C + c].x, acc * inv_count);
+          write_cse(c, gate[(size_t)n * C + c].x, acc * inv_count);
         }
       }
     }
@@ -465,16 +486,16 @@ __global__ void __launch_bounds__(256) se_bwd_vec_kernel(const double* __restric
   for (int c = tid; c < C; c += 256) {            // dpm[c] = sum_j dz1[j] w1[j][c]
     float acc = 0.f;
     for (int j = 0; j < SQ; ++j) acc = fmaf(dz1[j], w1[(size_t)j * C + c], acc);
-    coef_se[(size_t)n * C + c] = make_float2(gate[(size_t)n * C + c].x, acc * inv_count);
+    write_cse(c, gate[(size_t)n * C + c].x, acc * inv_count);
   }
 }
 
 int launch_se_bwd_vec(const double* pool, float inv_count, const float* w1, const float* b1, const float* w2, const float2* gate,
-                      const double* t12, float2* coef_se, float* v_pm, float* v_z, float* v_ds2, float* v_dz1, int N, int C,
-                      int SQ, cudaStream_t st) {
+                      const double* t12, const double* dq_stats, float4* coef_se, float* v_pm, float* v_z, float* v_ds2,
+                      float* v_dz1, int N, int C, int SQ, cudaStream_t st) {
   const size_t smem = (size_t)(2 * C + 2 * SQ + 1024) * sizeof(float);
   if (ensure_dyn_smem_fn(se_bwd_vec_kernel, smem)) return 1;
-  se_bwd_vec_kernel<<<N, 256, smem, st>>>(pool, inv_count, w1, b1, w2, gate, t12, coef_se, v_pm, v_z, v_ds2, v_dz1, C, SQ);
+  se_bwd_vec_kernel<<<N, 256, smem, st>>>(pool, inv_count, w1, b1, w2, gate, t12, dq_stats, coef_se, v_pm, v_z, v_ds2, v_dz1, C, SQ);
   return 0;
 }
 
@@ -512,7 +533,7 @@ void launch_outer_sum(const float* A, int lda, const float* B, int ldb, float* d
 // registers over the whole range, the per-image sums are flushed when the image changes.  Two fp32 halo tiles of
 // 10 x 18 x 32 = 46 KB: four blocks per SM overlap one another's load and compute phases.
 template <bool F32>   // F32: the fp32 plan (all tensors fp32); else 16-bit tensors (gradients bf16, h1 bf16 or fp16)
-__global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float2* __restrict__ coef_se,
+__global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restrict__ dq, int dtg, const float4* __restrict__ coef_se,
                                                             const void* __restrict__ h1, int dth, const float2* __restrict__ coef2,
                                                             const float* __restrict__ w, void* __restrict__ du,
                                                             double* __restrict__ t12, float* __restrict__ dW, int N, int H, int W,
@@ -580,7 +601,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
     if (n != cur_n) {
       if (cur_n >= 0) flush(cur_n);     // (ends with a block-wide barrier: nobody still reads the old coefficients)
       cur_n = n;
-      if (tid < CB) s_cse[tid] = coef_se[(size_t)n * C + c0 + tid];
+      if (tid < CB) { const float4 e = coef_se[(size_t)n * C + c0 + tid]; s_cse[tid] = make_float2(e.x, e.y); }   // (s = 1 on this path)
       else if (tid < 2 * CB) s_c2[tid - CB] = coef2[(size_t)n * C + c0 + tid - CB];
     }
     const int ty0 = (tile / tilesX) * TSY, tx0 = (tile % tilesX) * TSX;
@@ -755,7 +776,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const void* __restri
   }
 }
 
-void launch_dwconv_bwd(const void* dq, int dtg, const float2* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
+void launch_dwconv_bwd(const void* dq, int dtg, const float4* coef_se, const void* h1, int dth, const float2* coef2, const float* w,
                        void* du, double* t12, float* dW, int N, int H, int W, int C, int num_sms, cudaStream_t st) {
   const int tilesX = (W + 15) / 16, tilesY = (H + 7) / 8;
   const long long total = (long long)N * tilesX * tilesY;
