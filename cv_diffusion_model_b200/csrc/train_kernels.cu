@@ -1411,11 +1411,15 @@ __global__ void __launch_bounds__(256) final_conv_bwd_kernel(const void* __restr
   const float sc_ext = gscale * (gscale_dev ? *gscale_dev : 1.f);
   const float sc = sc_ext / (float)((double)N * Co * H * W);
   const int tiles = tilesX * tilesY;
-  // weight-gradient entries owned by this thread: e = tid, tid + 256, ... over [9][Ci][Co]
-  const int nent = 9 * Ci * Co;
-  float wacc[8];
+  // weight gradient: thread = (input channel ci, row group g); it owns dW[tap][ci][co] partial sums for ALL taps and
+  // output channels (36 registers) over the rows g, g + G, ... of every tile: per pixel 3 new s values (the window slides
+  // along x), one broadcast dE and 27 FMAs — the previous entry-per-thread loop issued two LDS per FMA (4.4 ms per step).
+  const int wci = tid % Ci, wg = tid / Ci, wG = 256 / Ci;
+  float wacc[9][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wacc[j] = 0.f;
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wacc[t][j] = 0.f;
   float bacc = 0.f;   // thread co < Co accumulates dbias[co] (tid < Co)
   for (long long it = blockIdx.x; it < (long long)N * tiles; it += gridDim.x) {
     const int n = (int)(it / tiles), tile = (int)(it % tiles);
@@ -1491,23 +1495,35 @@ __global__ void __launch_bounds__(256) final_conv_bwd_kernel(const void* __restr
         }
       }
     }
-    // ---- weight gradient: entry (tap, ci, co) += sum over the tile's pixels dE[p][co] s[p + off(tap)][ci] ----
+    // ---- weight gradient (dE is zero outside the image, so out-of-image pixels of a ragged tile add nothing) ----
+    if (wg < wG) {
+      for (int py = wg; py < TS; py += wG) {
+        float sv[3][3];
 #pragma unroll
-    for (int slot = 0; slot < 8; ++slot) {
-      const int ent = tid + slot * 256;
-      if (ent >= nent) continue;
-      const int co = ent % Co, k = ent / Co;
-      const int ci = k % Ci, tap = k / Ci;
-      const int ky = tap / 3, kx = tap % 3;
-      float a = 0.f;
-      for (int py = 0; py < TS; ++py) {
-        if (ty0 + py >= H) break;
+        for (int ky = 0; ky < 3; ++ky) {
+          sv[ky][1] = ts[((py + ky) * HS + 0) * Ci + wci];
+          sv[ky][2] = ts[((py + ky) * HS + 1) * Ci + wci];
+        }
+#pragma unroll 4
         for (int pxx = 0; pxx < TS; ++pxx) {
-          if (tx0 + pxx >= W) break;
-          a = fmaf(te[((py + 1) * HS + pxx + 1) * 4 + co], ts[((py + ky) * HS + pxx + kx) * Ci + ci], a);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            sv[ky][0] = sv[ky][1]; sv[ky][1] = sv[ky][2];
+            sv[ky][2] = ts[((py + ky) * HS + pxx + 2) * Ci + wci];
+          }
+          const float4 e = *reinterpret_cast<const float4*>(te + ((py + 1) * HS + pxx + 1) * 4);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float sx = sv[ky][kx];
+              wacc[ky * 3 + kx][0] = fmaf(e.x, sx, wacc[ky * 3 + kx][0]);
+              wacc[ky * 3 + kx][1] = fmaf(e.y, sx, wacc[ky * 3 + kx][1]);
+              wacc[ky * 3 + kx][2] = fmaf(e.z, sx, wacc[ky * 3 + kx][2]);
+              wacc[ky * 3 + kx][3] = fmaf(e.w, sx, wacc[ky * 3 + kx][3]);
+            }
         }
       }
-      wacc[slot] += a;
     }
     if (tid < Co) {
       float a = 0.f;
@@ -1521,13 +1537,22 @@ __global__ void __launch_bounds__(256) final_conv_bwd_kernel(const void* __restr
       atomicAdd(t12 + ((size_t)n * Ci + c) * 2 + which, (double)s_t[i]);
     }
   }
+  // row groups -> one partial per (tap, ci, co) and block (shared-memory adds), then one global atomic each
+  __syncthreads();
+  float* wred = ts;   // [9][Ci][4]
+  for (int i = tid; i < 9 * Ci * 4; i += 256) wred[i] = 0.f;
+  __syncthreads();
+  if (wg < wG) {
 #pragma unroll
-  for (int slot = 0; slot < 8; ++slot) {
-    const int ent = tid + slot * 256;
-    if (ent >= nent) continue;
-    const int co = ent % Co, k = ent / Co;
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&wred[(t * Ci + wci) * 4 + j], wacc[t][j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * Ci * 4; i += 256) {
+    const int co = i & 3, k = i >> 2;
     const int ci = k % Ci, tap = k / Ci;
-    atomicAdd(dW + ((size_t)co * Ci + ci) * 9 + tap, wacc[slot]);   // final_conv.weight [Co][Ci][3][3]
+    if (co < Co) atomicAdd(dW + ((size_t)co * Ci + ci) * 9 + tap, wred[i]);   // final_conv.weight [Co][Ci][3][3]
   }
   if (tid < Co) atomicAdd(dbias + tid, bacc);
 }
@@ -1535,7 +1560,7 @@ __global__ void __launch_bounds__(256) final_conv_bwd_kernel(const void* __restr
 int launch_final_conv_bwd(const void* h, int dth, const float2* coef, const float* w, const float* eps, const float* target,
                           int loss_type, float gscale, const float* gscale_dev, void* dpre, int dtg, double* t12, float* dW,
                           float* dbias, int N, int H, int W, int Ci, int Co, int num_sms, cudaStream_t st) {
-  if (Ci > 64 || Ci % 8 || Co > 4 || 9 * Ci * Co > 8 * 256) return 1;
+  if (Ci > 64 || Ci % 8 || Co > 4) return 1;
   const int tilesX = (W + 15) / 16, tilesY = (H + 15) / 16;
   const size_t smem = ((size_t)18 * 18 * (Ci + 4) + 9 * Ci * 4 + 2 * Ci) * sizeof(float);
   if (ensure_dyn_smem_fn(final_conv_bwd_kernel, smem)) return 1;
@@ -1621,12 +1646,110 @@ __global__ void __launch_bounds__(256) init_conv_wgrad_kernel(const float* __res
   if (tid < Co) atomicAdd(dbias + tid, bacc);
 }
 
+// register-blocked version for the model's shape (CIN = 6): thread = (output channel co, row group g) owns all 9 x CIN
+// partial sums of its co (54 registers); per pixel one dY value and, per input channel, 3 new broadcast x values (the 3x3
+// window slides along x) feed 9 CIN FMAs — the entry-per-thread kernel above issues two LDS per FMA (2.0 ms per step).
+template <int CIN>
+__global__ void __launch_bounds__(256) init_conv_wgrad_rb_kernel(const float* __restrict__ xa, int ca, long long sa,
+                                                                 const float* __restrict__ xb, long long sb,
+                                                                 const void* __restrict__ dY, int dtg, float* __restrict__ dW,
+                                                                 float* __restrict__ dbias, int N, int H, int W, int Co, int tilesX,
+                                                                 int tilesY) {
+  constexpr int TS = 16, HS = TS + 2;
+  extern __shared__ __align__(16) float ism[];
+  float* tx = ism;                      // [CIN][HS*HS]
+  float* ty = tx + CIN * HS * HS;       // [TS*TS][Co]
+  const int tid = threadIdx.x;
+  const int wco = tid % Co, wg = tid / Co, wG = 256 / Co;
+  float wacc[CIN][9];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wacc[ci][t] = 0.f;
+  float bacc = 0.f;
+  const int tiles = tilesX * tilesY;
+  for (long long it = blockIdx.x; it < (long long)N * tiles; it += gridDim.x) {
+    const int n = (int)(it / tiles), tile = (int)(it % tiles);
+    const int ty0 = (tile / tilesX) * TS, tx0 = (tile % tilesX) * TS;
+    __syncthreads();
+    for (int i = tid; i < CIN * HS * HS; i += 256) {
+      const int ci = i / (HS * HS), px = i % (HS * HS);
+      const int yy = px / HS, xx = px % HS;
+      const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = ci < ca ? xa[n * sa + ((long long)ci * H + gy) * W + gx] : xb[n * sb + ((long long)(ci - ca) * H + gy) * W + gx];
+      tx[i] = v;
+    }
+    for (int i = tid; i < TS * TS * (Co / 8); i += 256) {
+      const int px = i / (Co / 8), cv = i % (Co / 8);
+      const int gy = ty0 + px / TS, gx = tx0 + px % TS;
+      float v[8];
+      if (gy < H && gx < W) ld8(dY, dtg, (((size_t)n * H + gy) * W + gx) * Co + cv * 8, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ty[px * Co + cv * 8 + j] = v[j];
+    }
+    __syncthreads();
+    if (wg < wG) {
+      for (int py = wg; py < TS; py += wG) {
+        float sv[CIN][3][3];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            sv[ci][ky][1] = tx[ci * HS * HS + (py + ky) * HS + 0];
+            sv[ci][ky][2] = tx[ci * HS * HS + (py + ky) * HS + 1];
+          }
+#pragma unroll 2
+        for (int pxx = 0; pxx < TS; ++pxx) {
+          const float g = ty[(py * TS + pxx) * Co + wco];     // 0 beyond a ragged edge
+          bacc += g;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              sv[ci][ky][0] = sv[ci][ky][1]; sv[ci][ky][1] = sv[ci][ky][2];
+              sv[ci][ky][2] = tx[ci * HS * HS + (py + ky) * HS + pxx + 2];
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) wacc[ci][ky * 3 + kx] = fmaf(g, sv[ci][ky][kx], wacc[ci][ky * 3 + kx]);
+            }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* wred = tx;     // [Co][CIN][9] + [Co]
+  for (int i = tid; i < Co * CIN * 9 + Co; i += 256) wred[i] = 0.f;
+  __syncthreads();
+  if (wg < wG) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&wred[(wco * CIN + ci) * 9 + t], wacc[ci][t]);
+    atomicAdd(&wred[Co * CIN * 9 + wco], bacc);
+  }
+  __syncthreads();
+  for (int i = tid; i < Co * CIN * 9; i += 256) atomicAdd(dW + i, wred[i]);   // init_conv.weight [Co][CIN][3][3]
+  for (int i = tid; i < Co; i += 256) atomicAdd(dbias + i, wred[Co * CIN * 9 + i]);
+}
+
 int launch_init_conv_wgrad(const float* xa, int ca, long long sa, const float* xb, int cb, long long sb, const void* dY, int dtg,
                            float* dW, float* dbias, int N, int H, int W, int Co, int num_sms, cudaStream_t st) {
   const int Cin = ca + cb;
-  if (9 * Cin * Co > 16 * 256 || Co % 8) return 1;   // 16 register slots of 256 threads hold every (tap, ci, co) entry
   const int tilesX = (W + 15) / 16, tilesY = (H + 15) / 16;
   const size_t smem = ((size_t)Cin * 18 * 18 + 256 * Co) * sizeof(float);
+  if (Cin == 6 && Co % 8 == 0 && Co <= 256 && (size_t)(Co * 6 * 9 + Co) <= (size_t)6 * 18 * 18) {
+    if (ensure_dyn_smem_fn(init_conv_wgrad_rb_kernel<6>, smem)) return 1;
+    long long blocks = (long long)N * tilesX * tilesY;
+    if (blocks > (long long)num_sms * 2) blocks = (long long)num_sms * 2;
+    init_conv_wgrad_rb_kernel<6><<<(int)blocks, 256, smem, st>>>(xa, ca, sa, xb, sb, dY, dtg, dW, dbias, N, H, W, Co, tilesX, tilesY);
+    return 0;
+  }
+  if (9 * Cin * Co > 16 * 256 || Co % 8) return 1;   // 16 register slots of 256 threads hold every (tap, ci, co) entry
   if (ensure_dyn_smem_fn(init_conv_wgrad_kernel, smem)) return 1;
   long long blocks = (long long)N * tilesX * tilesY;
   if (blocks > (long long)num_sms * 2) blocks = (long long)num_sms * 2;

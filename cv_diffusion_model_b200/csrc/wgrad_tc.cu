@@ -50,8 +50,12 @@ struct WTParams {
   uint32_t achunk[kMaxAChunksWT];             // seg | kvalid << 8 | mode << 24 | f16 << 28
   uint16_t achunk_c0[kMaxAChunksWT];          // first channel of the chunk inside its segment
   uint8_t mb_first[kMaxAChunksWT], mb_count[kMaxAChunksWT];   // M-block -> its 1-2 A chunks
+  // CTAs of M-block mb: [mb_cta0[mb], mb_cta0[mb + 1]) = n_nblocks x mb_splits[mb] (N-block major).  The pixel range is
+  // split in proportion to the bytes an M-block streams per pixel, so every CTA pulls about the same amount from HBM
+  // (a 32-channel residual segment next to a 128-channel hidden segment used to get the same 74 CTAs: half the SMs idle).
+  uint16_t mb_cta0[kMaxAChunksWT / 2 + 2], mb_splits[kMaxAChunksWT / 2 + 2];
   int n_mblocks, n_nblocks, nychunks, Nc;
-  int m_tiles, P, splits, stages;
+  int m_tiles, P, stages;
   uint32_t stage_bytes, y_off, coef_smem_off, misc_off;
   // dense 3x3 conv (stride 1 or 2): achunk's segment field is the TAP, the A chunk of tap (ky, kx) is the image box shifted
   // by (kx - 1, ky - 1) (out-of-image elements zero-filled by TMA = the conv's padding; stride 2: tensor map with element
@@ -95,13 +99,16 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_smem_off);     // [2 chunks][64]
 
   // this CTA: output tile (M-block mb, N-block nb) and a contiguous range of pixel tiles
-  const int ot = blockIdx.x / p.splits, split = blockIdx.x - ot * p.splits;
-  const int mb = ot / p.n_nblocks, nb = ot - mb * p.n_nblocks;
+  int mb = 0;
+  while (mb + 1 < p.n_mblocks && (int)blockIdx.x >= (int)p.mb_cta0[mb + 1]) ++mb;
+  const int nsplit = p.mb_splits[mb];
+  const int local = (int)blockIdx.x - (int)p.mb_cta0[mb];
+  const int nb = local / nsplit, split = local - nb * nsplit;
   const int nA = p.mb_count[mb], a0 = p.mb_first[mb];
   const int y0 = nb * kNChunksWT;
   const int nY = min(kNChunksWT, p.nychunks - y0);
-  const int t_begin = (int)((long long)p.m_tiles * split / p.splits);
-  const int t_end = (int)((long long)p.m_tiles * (split + 1) / p.splits);
+  const int t_begin = (int)((long long)p.m_tiles * split / nsplit);
+  const int t_end = (int)((long long)p.m_tiles * (split + 1) / nsplit);
 
   if (warp == kTmaWarpWT && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(xf_bar(s), kXfThreadsWT); mbar_init(empty_bar(s), 1); }
@@ -342,13 +349,33 @@ int launch_common(WTParams& p, int num_sms, cudaStream_t st) {
   p.coef_smem_off = (uint32_t)stages * p.stage_bytes;
   p.misc_off = p.coef_smem_off + 1024;
   const uint32_t smem = p.misc_off + 1024 + 1024;
-  const int out_tiles = nmb * p.n_nblocks;
-  int splits = num_sms / out_tiles;
-  if (splits < 1) splits = 1;
-  if (splits > p.m_tiles) splits = p.m_tiles;
-  p.splits = splits;
+  // pixel splits per M-block: greedy, one more split to the M-block with the most bytes per pixel and CTA, while CTAs are left
+  int cost[kMaxAChunksWT / 2 + 2], splits[kMaxAChunksWT / 2 + 2];
+  const int ych = (p.Nc < kNChunksWT * 64 ? p.Nc : kNChunksWT * 64);
+  for (int i = 0; i < nmb; ++i) {
+    int ach = 0;
+    for (int c = 0; c < p.mb_count[i]; ++c) ach += (int)((p.achunk[p.mb_first[i] + c] >> 8) & 0xff);
+    cost[i] = ach + ych;
+    splits[i] = 1;
+  }
+  int left = num_sms - nmb * p.n_nblocks;
+  while (left >= p.n_nblocks) {
+    int best = -1;
+    for (int i = 0; i < nmb; ++i)
+      if (splits[i] < p.m_tiles && (best < 0 || (long long)cost[i] * splits[best] > (long long)cost[best] * splits[i])) best = i;
+    if (best < 0) break;
+    ++splits[best];
+    left -= p.n_nblocks;
+  }
+  int ctas = 0;
+  for (int i = 0; i < nmb; ++i) {
+    p.mb_cta0[i] = (uint16_t)ctas;
+    p.mb_splits[i] = (uint16_t)splits[i];
+    ctas += splits[i] * p.n_nblocks;
+  }
+  p.mb_cta0[nmb] = (uint16_t)ctas;
   if (ensure_dyn_smem_fn(wgrad_tc_kernel, kSmemLimitWT)) return -2;
-  wgrad_tc_kernel<<<out_tiles * splits, kThreadsWT, smem, st>>>(p);
+  wgrad_tc_kernel<<<ctas, kThreadsWT, smem, st>>>(p);
   return 0;
 }
 }  // namespace
