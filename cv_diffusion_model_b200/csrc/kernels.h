@@ -199,7 +199,12 @@ void launch_wgrad_1x1(const GemmParams& p, const int* seg_dt, const void* dY, in
                       int num_sms, cudaStream_t st);
 // the same on the tensor cores (wgrad_tc.cu, bf16 plan); non-zero = shape not covered, use the CUDA-core kernel
 int launch_wgrad_tc(const GemmParams& p, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
-                    int num_sms, cudaStream_t st);
+                    int num_sms, cudaStream_t st, float* img_dst = nullptr);
+// project weight gradient + SE gate gradient from the per-image products R[n][k][o] = sum_p [h2 | x][p][k] dY[p][o]
+// (launch_wgrad_tc, per-image mode, h2 NOT gated):  dgate[n][c] = sum_o Wp[o][c] R[n][c][o] -> t12[(n Ch + c) 2 + 1] (+=),
+// dWp[o][c] += sum_n gate[n][c] R[n][c][o],  dWskip[o][ci] += sum_n R[n][Ch + ci][o] (dWs may be null: identity residual)
+void launch_se_project_combine(const float* R, const float* Wp, const float2* gate, double* t12, float* dWp, float* dWs, int N,
+                               int Ch, int Ci, int Co, cudaStream_t st);
 // dense 3x3 conv (pad 1, stride 1 or 2) on the tensor cores (bf16); H, W = INPUT size; bias via launch_colsum
 int launch_wgrad_conv3_tc(const void* in, const void* dY, float* dW, int N, int H, int W, int Ci, int Co, int stride, int num_sms,
                           cudaStream_t st);

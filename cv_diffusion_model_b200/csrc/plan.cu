@@ -580,6 +580,12 @@ struct Builder {
     const bool has_skip = Ci != Co;
     if (has_skip) wsT = make_dgrad_w(name + ".skip.weight", (int64_t)Co * Ci, Ci, Co, Ci, 0);       // [Ci][Co]
     View xv = x;
+    // (see step 2 below) per-image project weight gradient + SE gate gradient from its products; needs Wp as plain fp32
+    bool xparts16 = true;
+    for (int i = 0; i < x.n; ++i) xparts16 = xparts16 && x.part[i]->C % 16 == 0;
+    const bool se_from_wgrad = p->tc && P % 128 == 0 && P >= 8192 && Co % 16 == 0 && Ch % 16 == 0 && xparts16 &&
+                               !getenv("LCM_NO_SE_FROM_WGRAD");
+    const size_t wp_f32 = se_from_wgrad ? p->add_copy(name + ".project.weight", (int64_t)Co * Ch) : 0;
     on_backward([=]() {
       const size_t gsz = pl->gsz;
       const size_t M = (size_t)n * P;
@@ -591,18 +597,22 @@ struct Builder {
       const bool dwb_stream = pl->tc && Ch % 64 == 0 && !getenv("LCM_NO_DWB_STREAM");
       const size_t dq_stats = dwb_stream ? pl->zballoc((size_t)n * Ch * 2 * sizeof(double)) : (size_t)-1;
       dgrad_gemm(name + ".project.dgrad", dY, wpT, dq, P, dq_stats);
-      // 2. project (+ skip) wgrad
+      // 2. project (+ skip) wgrad.  At the high-resolution levels of the tensor-core plan the GEMM runs in per-image mode on
+      //    the UNGATED h2 and a small combine kernel produces dWp, dWskip AND the SE gate gradient sum_p dq h2 from its
+      //    per-image products (no pass over dq and h2: was 11 ms of bwd_mask_reduce per step).
+      const size_t t12se = pl->zballoc((size_t)n * Ch * 2 * sizeof(double));
+      const size_t Rimg = se_from_wgrad ? pl->zballoc((size_t)n * (Ch + Ci) * Co * sizeof(float)) : 0;
       {
         std::vector<std::string> writes{name + ".project.weight"};
         if (has_skip) writes.push_back(name + ".skip.weight");
         const size_t gp_w = wg(name + ".project.weight"), gs_w = has_skip ? wg(name + ".skip.weight") : 0;
-        pushb(name + ".project.wgrad", "wgrad_simt", writes, [=](const RunCtx& c, cudaStream_t st) {
+        pushb(name + ".project.wgrad", "wgrad_simt", se_from_wgrad ? std::vector<std::string>{} : writes, [=](const RunCtx& c, cudaStream_t st) {
           GemmParams gp{};
           int seg_dt[LCM_MAX_SEGS] = {0, 0, 0, 0};
           float* dst[LCM_MAX_SEGS] = {nullptr, nullptr, nullptr, nullptr};
           int dst_ld[LCM_MAX_SEGS] = {0, 0, 0, 0};
           gp.nseg = 1 + xv.n;
-          gp.seg[0].A = c.a + h2->off; gp.seg[0].K = Ch; gp.seg[0].ld = Ch; gp.seg[0].mode = XF_SCALE;
+          gp.seg[0].A = c.a + h2->off; gp.seg[0].K = Ch; gp.seg[0].ld = Ch; gp.seg[0].mode = se_from_wgrad ? XF_NONE : XF_SCALE;
           gp.seg[0].coef = (const float2*)(c.f + gate); gp.seg[0].coef_ld = Ch; gp.seg[0].coef_off = 0;
           seg_dt[0] = dth; dst[0] = c.wg + gp_w; dst_ld[0] = Ch;
           int col = 0;
@@ -615,9 +625,19 @@ struct Builder {
             col += xv.part[i]->C;
           }
           gp.Ktot = Ch + Ci; gp.P = P; gp.M = (long long)n * P; gp.Nc = Co;
+          if (se_from_wgrad) {
+            if (launch_wgrad_tc(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st, (float*)(c.zb + Rimg))) *c.launch_err = 1;
+            return;
+          }
           if (pl->tc && launch_wgrad_tc(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st) == 0) return;
           launch_wgrad_1x1(gp, seg_dt, c.g + dY, dtg, dst, dst_ld, pl->num_sms, st);
         });
+        if (se_from_wgrad) {
+          pushb(name + ".se.dgate", "se_project_combine", writes, [=](const RunCtx& c, cudaStream_t st) {
+            launch_se_project_combine((const float*)(c.zb + Rimg), pl->wf(wp_f32), (const float2*)(c.f + gate), (double*)(c.zb + t12se),
+                                      c.wg + gp_w, has_skip ? c.wg + gs_w : nullptr, n, Ch, Ci, Co, st);
+          });
+        }
       }
       // 3. residual path: identity (r = dY) or skip conv (r = dY Wskip)
       size_t dxres = 0;
@@ -626,7 +646,7 @@ struct Builder {
         dgrad_gemm(name + ".skip.dgrad", dY, wsT, dxres, P);
       }
       // 4. SE backward
-      const size_t t12se = pl->zballoc((size_t)n * Ch * 2 * sizeof(double));
+      if (!se_from_wgrad)
       pushb(name + ".se.dgate", "bwd_mask_reduce", {}, [=](const RunCtx& c, cudaStream_t st) {
         launch_bwd_mask_reduce(c.g + dq, dtg, Ch, 0, c.a + h2->off, dth, Ch, 0, nullptr, 0, (double*)(c.zb + t12se), Ch, n, P, Ch, 0, st);
       });

@@ -499,6 +499,48 @@ int launch_se_bwd_vec(const double* pool, float inv_count, const float* w1, cons
   return 0;
 }
 
+// SE gate gradient without a pass over dq and h2: with the per-image products R[n][k][o] = sum_p [h2 | x][p][k] dY[p][o] of
+// the project weight-gradient GEMM (h2 not gated) and dq = dY Wp,
+//     dgate[n][c] = sum_p dq[p][c] h2[p][c] = sum_o Wp[o][c] R[n][c][o]
+//     dWp[o][c]   = sum_n gate[n][c] R[n][c][o] ;  dWskip[o][ci] = sum_n R[n][Ch + ci][o]
+// One block per k (128 threads = Co-wide rows x image slices); R is a few MB.
+__global__ void __launch_bounds__(128) se_project_combine_kernel(const float* __restrict__ R, const float* __restrict__ Wp,
+                                                                 const float2* __restrict__ gate, double* __restrict__ t12,
+                                                                 float* __restrict__ dWp, float* __restrict__ dWs, int N, int Ch,
+                                                                 int Ci, int Co) {
+  const int k = blockIdx.x, Ktot = Ch + Ci;
+  const int lanes_o = Co < 128 ? Co : 128;             // threads across o (Co is a multiple of 16; 32 | lanes_o or lanes_o = 16 / 48 ...)
+  const int slices = 128 / lanes_o;
+  const int ot = threadIdx.x % lanes_o, sl = threadIdx.x / lanes_o;
+  const bool warp_rows = lanes_o % 32 == 0 && Co % 32 == 0;
+  if (sl >= slices) return;
+  for (int o = ot; o < Co; o += lanes_o) {
+    float wacc = 0.f;
+    const float wp = k < Ch ? Wp[(size_t)o * Ch + k] : 0.f;
+    for (int n = sl; n < N; n += slices) {
+      const float r = R[((size_t)n * Ktot + k) * Co + o];
+      if (k < Ch) {
+        wacc = fmaf(gate[(size_t)n * Ch + k].x, r, wacc);
+        float d = wp * r;
+        if (warp_rows) {      // the 32 lanes of a warp hold 32 output channels of the same (image, k)
+          for (int sft = 16; sft > 0; sft >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sft);
+          if ((threadIdx.x & 31) == 0) atomicAdd(t12 + ((size_t)n * Ch + k) * 2 + 1, (double)d);
+        } else {
+          atomicAdd(t12 + ((size_t)n * Ch + k) * 2 + 1, (double)d);
+        }
+      } else {
+        wacc += r;
+      }
+    }
+    if (k < Ch) atomicAdd(dWp + (size_t)o * Ch + k, wacc);
+    else if (dWs) atomicAdd(dWs + (size_t)o * Ci + (k - Ch), wacc);
+  }
+}
+void launch_se_project_combine(const float* R, const float* Wp, const float2* gate, double* t12, float* dWp, float* dWs, int N,
+                               int Ch, int Ci, int Co, cudaStream_t st) {
+  se_project_combine_kernel<<<Ch + Ci, 128, 0, st>>>(R, Wp, gate, t12, dWp, dWs, N, Ch, Ci, Co);
+}
+
 // dW[r][c] += sum_n A[n][r] * B[n][c] ; dbias[r] += sum_n A[n][r]   (weight gradients of the tiny FCs: SE, FiLM, time MLP)
 __global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                         float* __restrict__ dW, float* __restrict__ dbias, int N, int R, int Cc) {

@@ -56,6 +56,11 @@ struct WTParams {
   uint16_t mb_cta0[kMaxAChunksWT / 2 + 2], mb_splits[kMaxAChunksWT / 2 + 2];
   int n_mblocks, n_nblocks, nychunks, Nc;
   int m_tiles, P, stages;
+  // per-image mode: the product of every image goes to img_dst[img][k][n] (fp32 atomics, k = global A channel) instead of
+  // the weight-gradient tensors; the accumulator (two of them in TMEM) is drained at every image boundary of the CTA's range
+  float* img_dst;
+  int img_ktot;
+  uint16_t achunk_k0[kMaxAChunksWT];          // global A channel of the chunk's first channel
   uint32_t stage_bytes, y_off, coef_smem_off, misc_off;
   // dense 3x3 conv (stride 1 or 2): achunk's segment field is the TAP, the A chunk of tap (ky, kx) is the image box shifted
   // by (kx - 1, ky - 1) (out-of-image elements zero-filled by TMA = the conv's padding; stride 2: tensor map with element
@@ -94,7 +99,8 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   auto raw_bar = [&](int s) { return bar0 + 8u * s; };
   auto xf_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
-  const uint32_t done_bar = bar0 + 8u * 24;
+  auto done_bar = [&](int a) { return bar0 + 8u * (24 + a); };      // accumulator a holds a finished product
+  auto drained_bar = [&](int a) { return bar0 + 8u * (26 + a); };   // ... has been read out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.misc_off + 256);
   float2* s_coef = reinterpret_cast<float2*>(smem + p.coef_smem_off);     // [2 chunks][64]
 
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
 
   if (warp == kTmaWarpWT && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(xf_bar(s), kXfThreadsWT); mbar_init(empty_bar(s), 1); }
-    mbar_init(done_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(done_bar(a), 1); mbar_init(drained_bar(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap_y)) : "memory");
   }
@@ -124,6 +130,9 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img_all = p.P >> 7;
+  // a "product" ends at the last tile of the range and, in per-image mode, at the last tile of every image
+  auto ends_product = [&](int t, int tin) { return t == t_end - 1 || (p.img_dst != nullptr && tin == tiles_per_img_all - 1); };
 
   if (warp < 8) {
     // ================================ XF: prologue of the A chunks, in place ====================================
@@ -137,6 +146,42 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
     // fp16 chunks (a block's hidden tensor) always pass through here: tcgen05.mma kind::f16 wants A and B in the SAME
     // 16-bit format, and dY is bf16 — the prologue re-packs them as bf16
     for (int ci = 0; ci < nA; ++ci) any_xf |= ((p.achunk[a0 + ci] >> 24) & 0x1f) != XF_NONE;
+    // ---- epilogue (warps 0-3 = the four TMEM lane quadrants): product number e -> fp32 atomics --------------------
+    int nprod = 0;
+    auto epilogue = [&](int e, int im) {
+      const int acc = e & 1;
+      mbar_wait(done_bar(acc), (uint32_t)(e >> 1) & 1u);
+      tc_fence_after();
+      const int m = warp * 32 + lane;                 // TMEM lane = A channel within the M-block
+      const int ci = m >> 6, cc = m & 63;
+      const bool lane_ok = ci < nA;
+      const uint32_t cd = p.achunk[a0 + (lane_ok ? ci : 0)];
+      const int s = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = p.achunk_c0[a0 + (lane_ok ? ci : 0)];
+      float* dst = p.conv ? p.conv_dst : p.dst[s];
+      float* idst = p.img_dst ? p.img_dst + ((size_t)im * p.img_ktot + p.achunk_k0[a0 + (lane_ok ? ci : 0)] + cc) * p.Nc : nullptr;
+      const bool ok = lane_ok && cc < kvalid && (dst != nullptr || idst != nullptr);
+      const int ldd = p.conv ? 0 : p.dst_ld[s];
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)acc * 128u;
+      const int ncols = nY * 64;
+      for (int c = 0; c < ncols; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + (uint32_t)c, r);
+        tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = y0 * 64 + c + j;
+            if (n < p.Nc) {
+              if (idst) atomicAdd(idst + n, __uint_as_float(r[j]));
+              else if (p.conv) atomicAdd(dst + ((size_t)n * p.Ci + c0 + cc) * 9 + s, __uint_as_float(r[j]));   // s = tap
+              else atomicAdd(dst + (size_t)n * ldd + c0 + cc, __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(drained_bar(acc));
+    };
     for (int t = t_begin; t < t_end; ++t) {
       if (any_xf && img != coef_img) {
         bar_sync(1, kXfThreadsWT);
@@ -187,38 +232,8 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
       }
       mbar_arrive(xf_bar(stage));
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      if (warp < 4 && ends_product(t, tin)) { epilogue(nprod, img); ++nprod; }
       if (++tin == tiles_per_img) { tin = 0; ++img; }
-    }
-    // ================================ epilogue: TMEM -> fp32 atomics =============================================
-    if (t_end > t_begin && warp < 4) {
-      mbar_wait(done_bar, 0);
-      tc_fence_after();
-      const int m = warp * 32 + lane;                 // TMEM lane = A channel within the M-block
-      const int ci = m >> 6, cc = m & 63;
-      const bool lane_ok = ci < nA;
-      const uint32_t cd = p.achunk[a0 + (lane_ok ? ci : 0)];
-      const int s = cd & 0xff, kvalid = (cd >> 8) & 0xff, c0 = p.achunk_c0[a0 + (lane_ok ? ci : 0)];
-      float* dst = p.conv ? p.conv_dst : p.dst[s];
-      const bool ok = lane_ok && cc < kvalid && dst != nullptr;
-      const int ldd = p.conv ? 0 : p.dst_ld[s];
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      const int ncols = nY * 64;
-      for (int c = 0; c < ncols; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(lane_base + (uint32_t)c, r);
-        tmem_wait_ld();
-        if (ok) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = y0 * 64 + c + j;
-            if (n < p.Nc) {
-              if (p.conv) atomicAdd(dst + ((size_t)n * p.Ci + c0 + cc) * 9 + s, __uint_as_float(r[j]));   // s = tap
-              else atomicAdd(dst + (size_t)n * ldd + c0 + cc, __uint_as_float(r[j]));
-            }
-          }
-        }
-      }
-      tc_fence_before();
     }
   } else if (warp == kTmaWarpWT) {
     // ================================ TMA producer ===============================================================
@@ -261,20 +276,29 @@ __global__ void __launch_bounds__(kThreadsWT, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t a_lbo = nA == 2 ? kChunkWT : 0u;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int stage = 0; uint32_t phase = 0;
+    int tin = t_begin % tiles_per_img_all;
+    int e = 0;                 // product number: accumulator e & 1
+    bool first = true;
     for (int t = t_begin; t < t_end; ++t) {
+      if (first && e >= 2) { mbar_wait(drained_bar(e & 1), (uint32_t)((e >> 1) - 1) & 1u); tc_fence_after(); }
       mbar_wait(xf_bar(stage), phase);
       tc_fence_after();
+      const bool last = ends_product(t, tin);
       if (elect_one()) {
         const uint32_t sb = sbase + (uint32_t)stage * p.stage_bytes;
         const uint64_t ad = desc_mn(sb, a_lbo), bd = desc_mn(sb + p.y_off, kChunkWT);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_u, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (2048 >> 4)), idesc, (t == t_begin && k == 0) ? 0u : 1u);
+          umma_bf16(tmem_u + (uint32_t)(e & 1) * 128u, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (2048 >> 4)), idesc,
+                    (first && k == 0) ? 0u : 1u);
         umma_commit(empty_bar(stage));
-        if (t == t_end - 1) umma_commit(done_bar);
+        if (last) umma_commit(done_bar(e & 1));
       }
       __syncwarp();
+      first = last;
+      if (last) ++e;
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      if (++tin == tiles_per_img_all) tin = 0;
     }
   }
 
@@ -293,15 +317,18 @@ int launch_common(WTParams& p, int num_sms, cudaStream_t st);
 // Returns 0 when launched, non-zero when the shape is not covered (the caller falls back to the CUDA-core kernel):
 // 16-bit operands, P % 128 == 0 (a 128-pixel tile lies inside one image: per-image prologue coefficients), segment widths
 // multiples of 16, Nc a multiple of 16.
+// img_dst (optional): per-image mode — img_dst[img][k][n] += sum over the image's pixels of xform(A)[p][k] dY[p][n]
+// (fp32 [M / P][Ktot][Nc], zeroed by the caller); dst / dst_ld are ignored.
 int launch_wgrad_tc(const GemmParams& g, const int* seg_dt, const void* dY, int dty, float* const* dst, const int* dst_ld,
-                    int num_sms, cudaStream_t st) {
+                    int num_sms, cudaStream_t st, float* img_dst) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("LCM_NO_WGRAD_TC"); off = (e && atoi(e)) ? 1 : 0; }
   if (off || dty != DT_BF16 || g.P % 128 || g.M % g.P || g.M <= 0 || g.M > 0x7fffff00LL || g.Nc % 16 || g.nseg < 1 || g.nseg > LCM_MAX_SEGS)
     return -1;
   WTParams p;
   memset(&p, 0, sizeof(p));
-  int nch = 0, nmb = 0;
+  int nch = 0, nmb = 0, k0 = 0;
+  p.img_dst = img_dst;
   for (int s = 0; s < g.nseg; ++s) {
     if (seg_dt[s] == DT_F32 || g.seg[s].K % 16 || g.seg[s].ld % 8) return -1;
     if (g.seg[s].mode != XF_NONE && !g.seg[s].coef) return -1;
@@ -314,9 +341,12 @@ int launch_wgrad_tc(const GemmParams& g, const int* seg_dt, const void* dY, int 
       if (nch >= kMaxAChunksWT) return -1;
       const int kv = g.seg[s].K - c0 < 64 ? g.seg[s].K - c0 : 64;
       p.achunk_c0[nch] = (uint16_t)c0;
+      p.achunk_k0[nch] = (uint16_t)(k0 + c0);
       p.achunk[nch++] = (uint32_t)s | ((uint32_t)kv << 8) | ((uint32_t)g.seg[s].mode << 24) | ((f16 ? 1u : 0u) << 28);
     }
+    k0 += g.seg[s].K;
   }
+  p.img_ktot = k0;
   // M-blocks = consecutive pairs of chunks (they may span segments: mode, destination and source map are per chunk, and the
   // prologue hands every chunk to the tensor core as bf16)
   for (int c = 0; c < nch; c += 2) {
