@@ -341,9 +341,15 @@ def main():
                 "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic,
                 "traffic_capture": traffic_of, "algorithmic_bytes_per_launch_avg": tk["bytes"] / tk["n"],
                 "peak_source": peak_src,
+                # whole model: SURVEY App. A accounting (every op of the reference's sequence reads its inputs / writes its output
+                # once); `moved_gb_per_forward` is the same sum over the kernels actually launched (the fused expand -> depthwise
+                # kernel never writes the 4x-wide hidden tensor), i.e. the bytes that really have to cross HBM
                 "whole_model": {"algorithmic_gb_per_forward": eng.algorithmic_bytes / 1e9,
                                 "achieved_gbs": value / world * LCM_STEPS * eng.algorithmic_bytes / B / 1e9,
-                                "frac": value / world * LCM_STEPS * eng.algorithmic_bytes / B / 1e9 / hbm_gbs},
+                                "frac": value / world * LCM_STEPS * eng.algorithmic_bytes / B / 1e9 / hbm_gbs,
+                                "moved_gb_per_forward": eng.fused_bytes / 1e9,
+                                "moved_gbs": value / world * LCM_STEPS * eng.fused_bytes / B / 1e9,
+                                "moved_frac": value / world * LCM_STEPS * eng.fused_bytes / B / 1e9 / hbm_gbs},
                 "per_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"], "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] else 0,
                                    "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["ms"] else 0} for k, v in by_kernel.items()}}
     launches = LCM_STEPS * eng.launches_per_forward

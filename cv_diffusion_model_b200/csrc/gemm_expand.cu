@@ -72,6 +72,7 @@ struct XParams {
   uint32_t chunk[kMaxChunksX];   // seg | kvalid << 8 | c0/8 << 16 | coef base << 24
   uint32_t w_off, stg_off, coef_smem_off, misc_off;
   int debug;
+  int dbg2;   // LCM_X_DBG bottleneck experiments: 1 skip the XF math, 2 skip the Gram MMAs, 4 one prologue thread group only
 };
 
 __device__ __forceinline__ void tma_load_2d_x(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -94,6 +95,10 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
 __device__ long long g_xtimeline[64 * 16];   // LCM_X_TIMELINE: clock64 stamps of block 0, first 64 tiles
 #define XSTAMP(tile_idx, slot) do { if (p.debug && blockIdx.x == 0 && (tile_idx) < 64) g_xtimeline[(tile_idx) * 16 + (slot)] = clock64(); } while (0)
 
+// kStatsOnly: the statistics half alone — S and G of the transformed input, no main MMAs, nothing stored.  It runs ahead
+// of the fused expand -> depthwise kernel (xdw_fused.cu), which needs the GroupNorm2 coefficients of a tensor it never
+// materialises; the pass reads only the (4x narrower) block input.
+template <bool kStatsOnly>
 __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_constant__ XParams p) {
   extern __shared__ uint8_t xsm_raw[];
   const uint32_t sraw = smem_u32(xsm_raw);
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
         }
         mbar_wait(raw_bar(stage), phase);
         if (ci == 0 && xt == 0) XSTAMP(t - t_begin, 1);
-        if (act) {
+        if (act && !(p.dbg2 & 1)) {
           uint4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = lds128(a_smem + (uint32_t)(xt + i * kXfThreadsX) * 16u);
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     if (coef_img >= 0) flush_cs(coef_img);
   } else if (warp == kTmaWarp) {
     // ================================ TMA: weights once, activation chunks ================================
-    if (elect_one()) {
+    if (!kStatsOnly && elect_one()) {
       const uint32_t wbytes = (uint32_t)p.NB * p.nchunks * kWChunkBytes;
       mbar_expect_tx(wres_bar, wbytes);
       for (uint32_t o = 0; o < wbytes; o += kWChunkBytes)
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     const int ks0 = (int)((p.chunk[0] >> 8) & 0xff) >> 4;                          // K steps of 16 per chunk
     const int ks1 = p.nchunks > 1 ? (int)((p.chunk[1] >> 8) & 0xff) >> 4 : 0;
     const uint64_t wd0 = umma_desc(sbase + p.w_off);
-    mbar_wait(wres_bar, 0);
+    if (!kStatsOnly) mbar_wait(wres_bar, 0);
     int stage = 0; uint32_t phase = 0;      // activation ring position of the CURRENT tile's first chunk
     int g = 0;                               // n-blocks issued so far (accumulator = g & 1)
     for (int t = t_begin; t < t_end; ++t) {
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
       // The issue code runs on the uniform datapath, where every dependent instruction costs several cycles: keep it
       // to constant-offset descriptor adds and predicated MMAs (the generic loop version took ~600 cycles per n-block).
       const uint64_t ad0 = umma_desc(sbase + (uint32_t)stage * kChunkBytes);   // chunk ci at + ci * (16384 >> 4)
-      for (int j = 0; j < p.NB; ++j, ++g) {
+      for (int j = 0; j < (kStatsOnly ? 0 : p.NB); ++j, ++g) {
         const int acc = g & 1;
         mbar_wait(tempty_bar(acc), ((uint32_t)(g >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
         const uint64_t d0 = umma_desc_mn(sbase + (uint32_t)stage * kChunkBytes, gram_lbo);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_u + kGramCol0, d0 + (uint64_t)(k * (2048 >> 4)), d0 + (uint64_t)(k * (2048 >> 4)), idesc_gram, (first_tile && k == 0) ? 0u : 1u);
+          if (!(p.dbg2 & 2)) umma_bf16(tmem_u + kGramCol0, d0 + (uint64_t)(k * (2048 >> 4)), d0 + (uint64_t)(k * (2048 >> 4)), idesc_gram, (first_tile && k == 0) ? 0u : 1u);
         umma_commit(gdone_bar);
         for (int ci = 0; ci < p.nchunks; ++ci) umma_commit(empty_bar(stage + ci));   // the other reader of the tile's chunks
       }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     // image flush (group 0): Gram matrix TMEM -> scratch.  `lt` = CTA-local index of the image's last tile; gdone
     // completes one phase per tile and cannot run ahead of this wait (the next image's first Gram MMA waits for sread)
     auto flush = [&](int im, int lt) {
-      mbar_wait(gdone_bar, (uint32_t)lt & 1u);
+      if (!kStatsOnly) mbar_wait(gdone_bar, (uint32_t)lt & 1u);
       tc_fence_after();
       if (ew * 32 < kw) {
         double* grow = p.gram + ((size_t)im * kGramLd + et) * kGramLd;
@@ -360,6 +365,18 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
     };
     int t = t_begin, j = 0;
     int img = t_begin / tiles_per_img, tin = t_begin - img * tiles_per_img;   // image of tile t, tile index inside it
+    if (kStatsOnly) {
+      // only the image flushes of group 0 remain
+      // (nothing else paces these warps, so they follow gdone tile by tile: a parity wait is only meaningful when the
+      // waiter is less than one phase behind)
+      if (grp == 0) {
+        for (; t < t_end; ++t) {
+          mbar_wait(gdone_bar, (uint32_t)(t - t_begin) & 1u);
+          if (tin == tiles_per_img - 1 || t == t_end - 1) flush(img, t - t_begin);
+          if (++tin == tiles_per_img) { tin = 0; ++img; }
+        }
+      }
+    } else {
     // every 128-column accumulator is drained by both groups: group grp takes columns [64 grp, 64 grp + 64)
     for (int g = 0; g < total_g; ++g) {
       // (t - tin) is the first tile of the current image: the previous image ended one tile before it
@@ -407,6 +424,7 @@ __global__ void __launch_bounds__(kThreadsX, 1) gemm_expand_kernel(const __grid_
       if (++j == p.NB) { j = 0; ++t; if (++tin == tiles_per_img) { tin = 0; ++img; } }
     }
     if (grp == 0 && cur_img >= 0) flush(cur_img, t_end - 1 - t_begin);
+    }
   }
 
   tc_fence_before();
@@ -563,11 +581,27 @@ bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P) {
 
 size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd * kGramLd + kGramLd) * sizeof(double); }
 
+// (S, G) scratch -> (sum, sum^2) of the expand output; W packed as for gemm_expand with `nchunks` 64-wide K chunks per n-block
+// (the statistics pass of the fused expand -> depthwise path, xstats.cu, ends with this)
+int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st) {
+  if (nchunks < 1 || nchunks > 2 || Nc % 32) return -1;
+  if (ensure_dyn_smem_fn(expand_stats_kernel<128>, (128 * 128 + 128 + 128 * 32 + 512) * 4) ||
+      ensure_dyn_smem_fn(expand_stats_kernel<64>, (64 * 64 + 64 + 64 * 32 + 512) * 4)) return -2;
+  const double* gram = reinterpret_cast<const double*>(scratch);
+  const double* colsum = gram + (size_t)images * kGramLd * kGramLd;
+  const dim3 sg(images, Nc / 32);
+  if (nchunks == 1)
+    launch_pdl(expand_stats_kernel<64>, sg, dim3(128), (size_t)(64 * 64 + 64 + 64 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
+  else
+    launch_pdl(expand_stats_kernel<128>, sg, dim3(128), (size_t)(128 * 128 + 128 + 128 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
+  return 0;
+}
+
 // W: bf16 image packed with block_n = 64 and the x6 scale (PackJob::scale) — see plan.cu / ops_api.cu.
 // scratch: gemm_expand_scratch_bytes(images) bytes; zero_scratch: clear it here, on the stream (the plan hands in a slice
 // of its zeroed region instead, which keeps a memset node out of every block of the graph).
-int launch_gemm_expand(const GemmParams& g, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st) {
-  if (g.nseg < 1 || g.nseg > 2 || !g.out_f16 || !g.stats || !scratch || g.P % 128 || g.M % g.P || g.M <= 0 || g.M > 0x7fffff00LL) return -1;
+int launch_gemm_expand(const GemmParams& g, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st, bool stats_only) {
+  if (g.nseg < 1 || g.nseg > 2 || (!g.out_f16 && !stats_only) || !g.stats || !scratch || g.P % 128 || g.M % g.P || g.M <= 0 || g.M > 0x7fffff00LL) return -1;
   int segK[2] = {0, 0};
   for (int s = 0; s < g.nseg; ++s) {
     if (g.seg[s].mode != XF_AFFINE_RELU6 || g.seg[s].f16 || !g.seg[s].coef || g.seg[s].ld % 8) return -1;
@@ -596,15 +630,19 @@ int launch_gemm_expand(const GemmParams& g, void* scratch, bool zero_scratch, in
     cbase += g.seg[s].K;
   }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_X_TIMELINE"); dbg = (e && atoi(e)) ? 1 : 0; } p.debug = dbg; }
-  if (ensure_dyn_smem_fn(gemm_expand_kernel, kSmemLimitX) ||
+  { static int d2 = -1; if (d2 < 0) { const char* e = getenv("LCM_X_DBG"); d2 = e ? atoi(e) : 0; } p.dbg2 = d2; }
+  if (ensure_dyn_smem_fn(gemm_expand_kernel<false>, kSmemLimitX) || ensure_dyn_smem_fn(gemm_expand_kernel<true>, kSmemLimitX) ||
       ensure_dyn_smem_fn(expand_stats_kernel<128>, (128 * 128 + 128 + 128 * 32 + 512) * 4) ||
       ensure_dyn_smem_fn(expand_stats_kernel<64>, (64 * 64 + 64 + 64 * 32 + 512) * 4)) return -2;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   if (zero_scratch) {
     if (cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(images), st) != cudaSuccess) return -2;
-    gemm_expand_kernel<<<grid, kThreadsX, L.total, st>>>(p);
+    if (stats_only) gemm_expand_kernel<true><<<grid, kThreadsX, L.total, st>>>(p);
+    else gemm_expand_kernel<false><<<grid, kThreadsX, L.total, st>>>(p);
+  } else if (stats_only) {
+    launch_pdl(gemm_expand_kernel<true>, dim3(grid), dim3(kThreadsX), L.total, st, p);
   } else {
-    launch_pdl(gemm_expand_kernel, dim3(grid), dim3(kThreadsX), L.total, st, p);
+    launch_pdl(gemm_expand_kernel<false>, dim3(grid), dim3(kThreadsX), L.total, st, p);
   }
   const dim3 sg(images, g.Nc / 32);
   if (L.nchunks == 1)

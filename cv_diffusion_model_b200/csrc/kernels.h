@@ -154,7 +154,17 @@ int launch_gemm_tc(const GemmParams& p, const ConvGeom& g, int block_n, int num_
 // weights packed with block_n = 128 and scale = 6.  `supported` is a pure shape test (plan time).
 bool gemm_expand_supported(int nseg, const int* segK, int Nc, int P);
 size_t gemm_expand_scratch_bytes(int images);   // Gram / column-sum scratch; must be zero at launch (zero_scratch: cleared on the stream)
-int launch_gemm_expand(const GemmParams& p, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st);
+// fused expand -> GN2 / FiLM / ReLU6 -> depthwise 3x3 + SE pool (xdw_fused.cu); the GroupNorm2 coefficients come from the
+// statistics-only pass of the expand kernel (launch_gemm_expand(..., stats_only = true))
+// (xstats.cu: t = relu6(GN1(x)) / 6 as one dense bf16 tensor + its per-image Gram matrix / column sums;
+//  launch_expand_stats_finalize turns those into the statistics of the expand output h1, which is never materialised)
+bool xstats_supported(int Ktot, int P);
+int launch_xstats(const GemmParams& g, void* t, void* scratch, int num_sms, cudaStream_t st);
+int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st);
+bool xdw_fused_supported(int nseg, const int* segK, int Nc, int H, int W);
+int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2* coef2, const float* wdw, void* out, double* pool,
+                     int N, int H, int W, int num_sms, cudaStream_t st);
+int launch_gemm_expand(const GemmParams& p, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st, bool stats_only = false);
 // gemm_wide.cu: the same operation for 128 <= K <= 448 (activation tile stationary, weights streamed; statistics from the
 // epilogue, accumulated into p.stats).  Weights packed like gemm_expand's (block_n = 128, x6).
 bool gemm_wide_supported(int nseg, const int* segK, int Nc, int P);

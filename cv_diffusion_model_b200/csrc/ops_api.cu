@@ -1,4 +1,6 @@
 // Single-kernel C entry points (include/lcm_unet.h, "single-kernel entry points"): unit parity, ncu.
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/lcm_unet.h"
@@ -161,6 +163,64 @@ int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, 
   int rc = finish(st);
   cudaFree(wbuf);
   return bad ? LCM_ERR_INVALID : rc;
+}
+
+int lcm_op_xdw(const lcm_gemm_seg* segs, int nseg, const float* w_dev, const void* coef2_dev, const float* wdw_dev, void* t_dev,
+               void* out_dev, double* pool_dev, double* stats_dev, int N, int H, int W, int Nc, int repeat, float* ms_out,
+               void* stream) {
+  if (!segs || nseg < 1 || nseg > 2 || !w_dev || !coef2_dev || !wdw_dev || !t_dev || !out_dev || !pool_dev || !stats_dev || repeat < 1)
+    return LCM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int Kt = 0;
+  GemmParams gp{};
+  for (int i = 0; i < nseg; ++i) {
+    if (!segs[i].coef || segs[i].mode != XF_AFFINE_RELU6 || segs[i].f16) return LCM_ERR_INVALID;
+    gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
+    gp.seg[i].coef = (const float2*)segs[i].coef; gp.seg[i].coef_ld = segs[i].K; gp.seg[i].coef_off = 0;
+    gp.seg[i].mode = XF_AFFINE_RELU6; gp.seg[i].f16 = 0;
+    Kt += segs[i].K;
+  }
+  gp.nseg = nseg; gp.P = H * W; gp.M = (long long)N * H * W;
+  if (Kt % 16 || Kt > 128 || !xstats_supported(Kt, H * W) || Nc % 128 || W % 64 || H % 2) return LCM_ERR_INVALID;
+  const int Kpad = (Kt + 63) / 64 * 64;
+  void* wbuf = nullptr; float* dwbuf = nullptr; void* scratch = nullptr;
+  if (cudaMalloc(&wbuf, (size_t)Nc * Kpad * 2) != cudaSuccess || cudaMalloc((void**)&dwbuf, (size_t)9 * Nc * 4) != cudaSuccess ||
+      cudaMalloc(&scratch, gemm_expand_scratch_bytes(N)) != cudaSuccess) {
+    cudaFree(wbuf); cudaFree(dwbuf); cudaFree(scratch);
+    return LCM_ERR_CUDA;
+  }
+  cudaMemsetAsync(wbuf, 0, (size_t)Nc * Kpad * 2, st);
+  {
+    PackJob j{};
+    j.kind = PACK_MAT; j.layout = WL_UMMA; j.bf16 = 1; j.dst = wbuf; j.R = Nc; j.Cc = Kt; j.src_ld = Kt; j.src_col0 = 0; j.ld = Kpad; j.off = 0;
+    j.block_n = 128; j.scale = 6.f;
+    launch_pack(j, w_dev, st);
+    PackJob d{}; d.kind = PACK_DW; d.dst = dwbuf; d.R = Nc;
+    launch_pack(d, wdw_dev, st);
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc = 0;
+  Timer t(st, ms_out, repeat);
+  for (int r = 0; r < repeat && rc == 0; ++r) {
+    cudaMemsetAsync(scratch, 0, gemm_expand_scratch_bytes(N), st);
+    cudaMemsetAsync(stats_dev, 0, (size_t)N * Nc * 2 * sizeof(double), st);
+    cudaMemsetAsync(pool_dev, 0, (size_t)N * Nc * sizeof(double), st);
+    const bool dbg = getenv("LCM_XDW_SYNC") != nullptr;   // debugging aid: locate a failing launch
+    auto stage = [&](const char* what) {
+      if (!dbg) return;
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      fprintf(stderr, "lcm_op_xdw: %s -> rc %d, %s\n", what, rc, cudaGetErrorString(e));
+    };
+    rc = launch_xstats(gp, t_dev, scratch, sms, st); stage("xstats");
+    if (!rc) { rc = launch_expand_stats_finalize(scratch, wbuf, stats_dev, N, Nc, Kpad / 64, st); stage("finalize"); }
+    if (!rc) { rc = launch_xdw_fused(t_dev, Kt, wbuf, Nc, (const float2*)coef2_dev, dwbuf, out_dev, pool_dev, N, H, W, sms, st); stage("fused"); }
+  }
+  t.stop();
+  int rc2 = finish(st);
+  cudaFree(wbuf); cudaFree(dwbuf); cudaFree(scratch);
+  return rc ? LCM_ERR_INVALID : rc2;
 }
 
 }  // extern "C"

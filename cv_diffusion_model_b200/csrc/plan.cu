@@ -216,6 +216,7 @@ struct lcm_plan {
   std::map<std::string, TensorP> tap_map;
   std::vector<std::string> tap_order;
   double total_bytes = 0, total_flops = 0;
+  double total_bytes_ref = 0;   // the same sum with every op accounted as the reference's op sequence moves it
 
   size_t walloc(size_t bytes) { size_t o = wbytes; wbytes += align_up(bytes, 256); return o; }
   size_t zalloc(size_t bytes) { size_t o = z_bytes; z_bytes += align_up(bytes, 256); return o; }
@@ -372,9 +373,11 @@ struct Builder {
     return coef4;
   }
 
-  void push(const std::string& name, const char* kernel, double bytes, double flops, RunFn fn) {
+  // ref_bytes: what the reference's op sequence moves for this op where a fusion of ours moves less (default: the same)
+  void push(const std::string& name, const char* kernel, double bytes, double flops, RunFn fn, double ref_bytes = -1.0) {
     Op o; o.name = name; o.kernel = kernel; o.bytes = bytes; o.flops = flops; o.run = std::move(fn);
     p->total_bytes += bytes; p->total_flops += flops;
+    p->total_bytes_ref += ref_bytes >= 0.0 ? ref_bytes : bytes;
     p->ops.push_back(std::move(o));
   }
 
@@ -481,6 +484,9 @@ struct Builder {
     // tcgen05 path: both hidden tensors are fp16 (dwconv_stream.cu explains why)
     const bool hid16 = p->tc;
     TensorP h1 = p->new_tensor(Ch, h, w, true, name + ".expand", hid16);
+    bool fused = false;
+    GemmW xw;
+    TensorP xt;     // fused path: t = relu6(GN1(x)) / 6, written by the statistics pass
     {
       std::vector<int> segK;
       for (int i = 0; i < x.n; ++i) segK.push_back(x.part[i]->C);
@@ -492,8 +498,37 @@ struct Builder {
         p->add_weight(name + ".expand.weight", (int64_t)Ch * Ci, mat_job(we, i, PACK_MAT, Ch, x.part[i]->C, Ci, col));
         col += x.part[i]->C;
       }
+      // Inference plans fuse expand -> norm2 / FiLM / ReLU6 -> depthwise into ONE kernel where the expand kernel applies
+      // (xdw_fused.cu): h1 is never materialised; its statistics come from a pass over the block input alone.
+      fused = p->tc && !p->train && !p->taps && we.expand && xdw_fused_supported((int)segK.size(), segK.data(), Ch, h, w);
+      if (fused) {
+        // the weights once more, packed as ONE dense K segment (t concatenates the input parts)
+        xw = make_w(Ch, std::vector<int>{Ci}, h * w);
+        p->add_weight(name + ".expand.weight", (int64_t)Ch * Ci, mat_job(xw, 0, PACK_MAT, Ch, Ci, Ci, 0));
+        xt = p->new_tensor(Ci, h, w, false, "", false);
+        lcm_plan* pl = p; const int n = N;
+        const size_t xs = p->zalloc(gemm_expand_scratch_bytes(N));
+        std::vector<SegSpec> sg = segs;
+        const GemmW wv = xw;
+        const TensorP tt = xt;
+        push(name + ".expand.stats", "xstats", 2.0 * Ci * N * P * es, 2.0 * N * P * Ci * Ci, [=](const RunCtx& c, cudaStream_t st) {
+          GemmParams gp{};
+          gp.nseg = (int)sg.size();
+          for (int i = 0; i < gp.nseg; ++i) {
+            gp.seg[i].A = c.a + sg[i].t->off; gp.seg[i].K = sg[i].t->C; gp.seg[i].ld = sg[i].t->C;
+            gp.seg[i].coef = (const float2*)(c.f + sg[i].coef); gp.seg[i].coef_ld = sg[i].coef_ld; gp.seg[i].coef_off = sg[i].coef_off;
+            gp.seg[i].mode = sg[i].mode; gp.seg[i].f16 = 0;
+          }
+          gp.P = h * w; gp.M = (long long)n * gp.P;
+          if (launch_xstats(gp, c.a + tt->off, c.z + xs, pl->num_sms, st) ||
+              launch_expand_stats_finalize(c.z + xs, pl->wbase + wv.off, (double*)(c.z + h1->stats_off), n, wv.Nc, (wv.Ktot + 63) / 64, st))
+            *c.launch_err = 1;
+        }, (Ci + Ch) * N * P * es + (double)Ci * Ch * es);
+        p->ops.back().launches = 2;
+      } else {
       gemm(name + ".expand", segs, we, h1, true, (Ci + Ch) * N * P * es + (double)Ci * Ch * es, 2.0 * N * P * Ci * Ch);
       if (we.expand) p->ops.back().launches = 2;   // GEMM + statistics finalisation
+      }
     }
     // norm2 + FiLM + ReLU6 -> depthwise (:212-220), SE pool (:97)
     const GnInfo gn2 = gn_coef(name + ".norm2", View::of(h1), name + ".norm2", row0);
@@ -502,6 +537,17 @@ struct Builder {
     const size_t pool = p->zalloc((size_t)N * Ch * sizeof(double));
     const size_t dw_off = p->walloc((size_t)9 * Ch * sizeof(float));
     { PackJob j{}; j.kind = PACK_DW; j.dst = (void*)dw_off; j.R = Ch; p->add_weight(name + ".depthwise.weight", (int64_t)Ch * 9, j); }
+    if (fused) {
+      lcm_plan* pl = p; const int n = N;
+      const GemmW wv = xw;
+      const TensorP tt = xt;
+      push(name + ".expand_depthwise", "xdw_fused", ((double)Ci + Ch) * N * P * es + (double)Ci * Ch * es + 36.0 * Ch,
+           2.0 * N * P * Ci * Ch + 18.0 * N * P * Ch, [=](const RunCtx& c, cudaStream_t st) {
+        if (launch_xdw_fused(c.a + tt->off, wv.Ktot, pl->wbase + wv.off, wv.Nc, (const float2*)(c.f + coef2), pl->wf(dw_off),
+                             c.a + h2->off, (double*)(c.z + pool), n, h, w, pl->num_sms, st)) *c.launch_err = 1;
+      }, 2.0 * Ch * N * P * es + 36.0 * Ch);
+      p->release(xt);
+    } else
     {
       lcm_plan* pl = p; const int n = N;
       push(name + ".depthwise", hid16 ? "dwconv_stream" : "dwconv", 2.0 * Ch * N * P * es + 36.0 * Ch, 18.0 * N * P * Ch,
@@ -1239,7 +1285,7 @@ int build_plan(lcm_plan* p) {
     }
     Op& f = p->ops[film_op_index];
     f.bytes = (double)rows * ted * 4; f.flops = 2.0 * N * rows * ted;
-    p->total_bytes += f.bytes; p->total_flops += f.flops;
+    p->total_bytes += f.bytes; p->total_flops += f.flops; p->total_bytes_ref += f.bytes;
     f.run = [=](const RunCtx& cx, cudaStream_t st) {
       launch_film((const float*)(cx.f + p->silu_f_off), p->wf(fw), p->wf(fb), (float*)(cx.f + p->film_f_off), N, rows, ted, st);
     };
@@ -1790,7 +1836,8 @@ int lcm_plan_launches_per_forward(const lcm_plan* plan) {   // kernels of this l
   if (plan) for (const Op& o : plan->ops) n += o.launches;
   return n;
 }
-double lcm_plan_algorithmic_bytes(const lcm_plan* plan) { return plan ? plan->total_bytes : 0; }
+double lcm_plan_algorithmic_bytes(const lcm_plan* plan) { return plan ? plan->total_bytes_ref : 0; }
+double lcm_plan_fused_bytes(const lcm_plan* plan) { return plan ? plan->total_bytes : 0; }
 double lcm_plan_algorithmic_flops(const lcm_plan* plan) { return plan ? plan->total_flops : 0; }
 
 }  // extern "C"

@@ -211,6 +211,11 @@ class Engine:
         return self.lib.lcm_plan_algorithmic_bytes(self.handle)
 
     @property
+    def fused_bytes(self) -> float:
+        """Algorithmic bytes of the kernels this plan launches (<= algorithmic_bytes: fusions keep tensors on chip)."""
+        return self.lib.lcm_plan_fused_bytes(self.handle)
+
+    @property
     def algorithmic_flops(self) -> float:
         return self.lib.lcm_plan_algorithmic_flops(self.handle)
 

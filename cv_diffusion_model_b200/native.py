@@ -91,6 +91,7 @@ SIGNATURES = {
     "lcm_plan_launches_per_forward": (C.c_int, [C.c_void_p]),
     "lcm_plan_algorithmic_bytes": (C.c_double, [C.c_void_p]),
     "lcm_plan_algorithmic_flops": (C.c_double, [C.c_void_p]),
+    "lcm_plan_fused_bytes": (C.c_double, [C.c_void_p]),
     "lcm_plan_profile_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OpProfileC),
                                            C.c_int]),
@@ -102,6 +103,8 @@ SIGNATURES = {
                                  C.c_void_p]),
     "lcm_op_dwconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "lcm_op_xdw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
 }
 
 _lib = None

@@ -97,6 +97,37 @@ def dwconv(x: torch.Tensor, coef: torch.Tensor, weight: torch.Tensor, impl: int 
     return (out, pool, ms.value) if timing else (out, pool)
 
 
+def xdw(segs: Sequence[Tuple[torch.Tensor, torch.Tensor]], weight: torch.Tensor, coef2: torch.Tensor, dw_weight: torch.Tensor,
+        repeat: int = 1, timing: bool = False):
+    """Fused expand -> GN2/FiLM/ReLU6 -> depthwise 3x3 + SE pool (csrc/xstats.cu + csrc/xdw_fused.cu).
+    segs: [(x NHWC [N,H,W,K] bfloat16, coef1 [N,K,2] fp32)] (1-2 concat parts, GroupNorm1 + ReLU6 prologue);
+    weight fp32 [Nc, sum K]; coef2 fp32 [N,Nc,2]; dw_weight fp32 [Nc,1,3,3].
+    Returns (h2 fp16 [N,H,W,Nc], pool [N,Nc] f64, stats of the expand output [N,Nc,2] f64, t bf16 [N,H,W,sum K][, ms])."""
+    x0 = segs[0][0]
+    n, h, w_, _ = x0.shape
+    nc = weight.shape[0]
+    arr = (native.GemmSegC * len(segs))()
+    keep = []
+    kt = 0
+    for i, (a, coef) in enumerate(segs):
+        a = a.contiguous(); coef = coef.to(torch.float32).contiguous()
+        keep += [a, coef]
+        arr[i].A = a.data_ptr(); arr[i].coef = coef.data_ptr(); arr[i].K = a.shape[-1]; arr[i].mode = 2; arr[i].f16 = 0
+        kt += a.shape[-1]
+    wt = weight.to(torch.float32).contiguous()
+    c2 = coef2.to(torch.float32).contiguous()
+    dw = dw_weight.to(torch.float32).contiguous()
+    t = torch.empty(n, h, w_, kt, dtype=torch.bfloat16, device=x0.device)
+    out = torch.empty(n, h, w_, nc, dtype=torch.float16, device=x0.device)
+    pool = torch.zeros(n, nc, dtype=torch.float64, device=x0.device)
+    stats = torch.zeros(n, nc, 2, dtype=torch.float64, device=x0.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(x0.device):
+        native.check(native.lib().lcm_op_xdw(arr, len(segs), _p(wt), _p(c2), _p(dw), _p(t), _p(out), _p(pool), _p(stats),
+                                             n, h, w_, nc, repeat, C.byref(ms) if timing else None, _stream_ptr()))
+    return (out, pool, stats, t, ms.value) if timing else (out, pool, stats, t)
+
+
 def image_preprocess_u8(images: torch.Tensor) -> torch.Tensor:
     """uint8 RGB ``[N,H,W,3]`` on the device -> fp32 ``[N,3,H,W]`` in [-1, 1]: ``x / 127.5 - 1``
     (the reference's ``preprocess_image`` after its resize, scripts/inference.py:111-116; bit-identical)."""

@@ -201,8 +201,11 @@ int lcm_plan_read_tap(lcm_plan* plan, const char* name, float* out_nchw_dev, voi
 
 /* Number of kernels the plan launches per UNet forward (for bench.py's gpu_launches). */
 int lcm_plan_launches_per_forward(const lcm_plan* plan);
-/* Algorithmic HBM bytes / FLOPs of one UNet forward under SURVEY §8(d) accounting. */
+/* Algorithmic HBM bytes / FLOPs of one UNet forward under SURVEY §8(d) accounting (every op of the reference's sequence reads
+ * its inputs and writes its output once).  lcm_plan_fused_bytes: the same sum for the kernels THIS plan launches — smaller where
+ * a fusion keeps a tensor on chip (the expand -> depthwise kernel never writes the 4x-wide hidden tensor). */
 double lcm_plan_algorithmic_bytes(const lcm_plan* plan);
+double lcm_plan_fused_bytes(const lcm_plan* plan);
 double lcm_plan_algorithmic_flops(const lcm_plan* plan);
 
 /* Per-kernel profile of one forward: runs the forward with a cudaEvent pair around every op and
@@ -246,6 +249,15 @@ int lcm_debug_timeline(long long* host, int n);
  * precision LCM_ACT_F16 selects the TMA-streamed fp16 kernel of the tensor-core plan (impl ignored) */
 int lcm_op_dwconv(const void* in_dev, const void* coef_dev, const float* w_dev, void* out_dev, double* pool_dev, int N,
                   int H, int W, int C, int precision, int impl, int repeat, float* ms_out, void* stream);
+/* fused expand -> GroupNorm2 / FiLM / ReLU6 -> depthwise 3x3 + SE pool of an inverted-residual block (efficient_unet.py:207-220,
+ * :97) in three launches, none of which writes the 4x-wide hidden tensor: xstats (t = relu6(GN1(x)) / 6 -> t_dev [N][H][W][Kt]
+ * bf16, Gram / column sums), statistics finalisation (stats_dev [N][Nc][2] of the expand output), fused kernel (out_dev fp16
+ * [N][H][W][Nc], pool_dev [N][Nc]).  segs: 1-2 bf16 input parts with their GroupNorm1 (a, b) coefficients, mode 2;
+ * w_dev [Nc][Kt] fp32; coef2_dev [N][Nc][2] fp32; wdw_dev [Nc][1][3][3].  Note: the CALLER supplies coef2 (in the plan it is
+ * derived from stats_dev by the GroupNorm finalisation between the second and the third launch). */
+int lcm_op_xdw(const lcm_gemm_seg* segs, int nseg, const float* w_dev, const void* coef2_dev, const float* wdw_dev, void* t_dev,
+               void* out_dev, double* pool_dev, double* stats_dev, int N, int H, int W, int Nc, int repeat, float* ms_out,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -168,6 +168,50 @@ def test_dwconv_f16_stream(N, H, W, C):
     assert torch.allclose(pool.float(), pref, rtol=5e-3, atol=0.01 * H * W ** 0.5), (pool.float() - pref).abs().max()
 
 
+XDW_CASES = [  # (N, H, W, [K...], Nc)
+    (2, 64, 64, [32], 128),           # level 0 block
+    (3, 32, 64, [64], 256),
+    (2, 64, 128, [64, 32], 384),      # decoder block on a concat input: K = 96, three n-blocks
+    (4, 256, 256, [64, 32], 384),     # several items per CTA, weight reload between n-blocks, CTA ranges straddling images
+    (5, 128, 128, [32, 32], 128),
+    (2, 34, 64, [16], 128),           # ragged row segments (H not a multiple of the segment height)
+    (1, 64, 192, [48], 256),          # base-variant widths
+]
+
+
+@pytest.mark.parametrize("N,H,W,Ks,Nc", XDW_CASES)
+def test_xdw_fused(N, H, W, Ks, Nc):
+    """Fused expand -> GN2/ReLU6 -> depthwise path (xstats.cu + xdw_fused.cu) against the unfused kernel
+    pair it replaces (gemm_expand / gemm_tc2 + dwconv_stream, themselves checked against torch above) and against torch fp32."""
+    from cv_diffusion_model_b200 import ops
+    if os.environ.get("LCM_SKIP_TC"):
+        pytest.skip("LCM_SKIP_TC set")
+    g = torch.Generator(device="cuda").manual_seed(23)
+    P = H * W
+    xs = [torch.randn(N, H, W, K, device="cuda", generator=g).bfloat16() for K in Ks]
+    c1 = [torch.stack([torch.rand(N, K, device="cuda", generator=g) + 0.5, torch.randn(N, K, device="cuda", generator=g) * 0.5 + 1.0], -1) for K in Ks]
+    Kt = sum(Ks)
+    w = torch.randn(Nc, Kt, device="cuda", generator=g) / Kt ** 0.5
+    c2 = torch.stack([torch.rand(N, Nc, device="cuda", generator=g) + 0.5, torch.randn(N, Nc, device="cuda", generator=g)], -1)
+    wd = torch.randn(Nc, 1, 3, 3, device="cuda", generator=g) / 3
+    h2, pool, stats, t = ops.xdw(list(zip(xs, c1)), w, c2, wd)
+    # unfused pair
+    h1, stats_ref = ops.gemm([(x.reshape(N * P, -1), c, 2) for x, c in zip(xs, c1)], w, P, impl=1, out_f16=True)
+    h2_ref, pool_ref = ops.dwconv(h1.view(N, H, W, Nc), c2, wd)
+    # t = relu6(a x + b) / 6 in bf16
+    t_ref = torch.cat([((x.float() * c[:, None, None, :, 0] + c[:, None, None, :, 1]).clamp(0, 6) / 6) for x, c in zip(xs, c1)], -1)
+    assert (t.float() - t_ref).abs().max().item() < 5e-3
+    assert torch.allclose(stats, stats_ref, rtol=2e-4, atol=1e-3 * P ** 0.5), (stats - stats_ref).abs().max()
+    d = (h2.float() - h2_ref.float()).abs().max().item()
+    assert d == 0.0, d            # same MMAs, same fp16 roundings, same HFMA2 sequences
+    assert torch.allclose(pool, pool_ref, rtol=1e-5, atol=1e-2), (pool - pool_ref).abs().max()
+    # and against torch fp32
+    a = (h1.float().view(N, H, W, Nc) * c2[:, None, None, :, 0] + c2[:, None, None, :, 1]).clamp(0, 6).permute(0, 3, 1, 2)
+    ref = F.conv2d(a, wd, padding=1, groups=Nc).permute(0, 2, 3, 1)
+    rel = ((h2.float() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rel < 2e-3, rel
+
+
 GEMM_F16_CASES = [  # (images, P, [K...], [segment is fp16], Nc, modes, out_f16)
     (2, 256, [32], [False], 128, [2], True),                 # expand: bf16 in, fp16 hidden out
     (3, 64, [64, 32], [False, False], 384, [2, 2], True),
