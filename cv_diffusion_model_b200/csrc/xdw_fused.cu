@@ -42,9 +42,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreadsF = 448;            // 14 warps at 128 registers (the register file is per SM sub-partition: 4 warps x 144 would not
-                                          // fit, and ptxas does not raise a region's budget on setmaxnreg.inc below the launch bound)
-constexpr int kConvWarps = 8, kEpiWarp0 = 8, kMmaWarpF = 12, kTmaWarpF = 13;
+// A conv warp is a strip of kPxS = 8 pixels x 128 channels (~110 registers: three window rows of 10 pixels x 4 channels, the taps).
+// The conv role is latency-bound (ncu: its warps are busy ~90 % of the time at ~0.12 instructions per cycle each).  Measured
+// alternatives: kPxS = 4 with 16 conv warps (22 warps -> 80 registers each, spills in the row loop and in the epilogue role):
+// 0.63 vs 0.45 ms per level-0 launch; prefetching the next row into a fourth register row at 128 registers: 0.74 ms.
+// The register file is per SM sub-partition (4 warps x 144 registers do not fit), and ptxas does not raise a role's budget
+// on setmaxnreg.inc above the launch bound's, so 8 conv warps at 128 registers it is.
+constexpr int kPxS = 8;
+static_assert(kPxS == 8, "only the 8-pixel strip is validated");
+constexpr int kConvWarps = 64 / kPxS, kEpiWarp0 = kConvWarps, kMmaWarpF = kConvWarps + 4, kTmaWarpF = kConvWarps + 5;
+constexpr int kThreadsF = (kConvWarps + 6) * 32;   // 14 warps
 constexpr uint32_t kChunkF = 16384;       // 128 rows x 64 16-bit elements
 constexpr uint32_t kSlotF = 16384;        // ring slot: 64 px x 128 ch fp16
 constexpr uint32_t kHaloRowF = 512;       // halo buffer: per row [2 sides][128 ch] fp16
@@ -90,14 +97,14 @@ __device__ __forceinline__ ItemF decode_f(int item, const FParams& p) {
   return q;
 }
 
-typedef __half2 RowF[10][2];
+typedef __half2 RowF[kPxS + 2][2];
 
 template <bool kRagged>
 __device__ __forceinline__ void emit_row_f(const RowF& r0, const RowF& r1, const RowF& r2, const __half2 (&w6)[9][2], __half* orow, int C,
                                            int nvalid, float (&psum)[4]) {
   __half2 s0 = __float2half2_rn(0.f), s1 = s0;
 #pragma unroll
-  for (int px = 0; px < 8; ++px) {
+  for (int px = 0; px < kPxS; ++px) {
     __half2 a0 = __hmul2(r0[px][0], w6[0][0]), a1 = __hmul2(r0[px][1], w6[0][1]);
     a0 = __hfma2(r0[px + 1][0], w6[1][0], a0); a1 = __hfma2(r0[px + 1][1], w6[1][1], a1);
     a0 = __hfma2(r0[px + 2][0], w6[2][0], a0); a1 = __hfma2(r0[px + 2][1], w6[2][1], a1);
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
   const int ntiles = p.hseg / 2 + 2;     // per item: 1 halo tile + hseg/2 + 1 main tiles (hseg is even)
 
   if (warp < kConvWarps) {
-    // ================================ CONV: strip of 8 pixels, lane = 4 channels ===================================
+    // ================================ CONV: strip of kPxS pixels, lane = 4 channels ===================================
     const int strip = warp;
     int slot = 0; uint32_t sphase = 0;
     const __half2 hz = __float2half2_rn(0.f);
@@ -170,8 +177,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++k) {
       const ItemF q = decode_f(item, p);
       const int c = q.nb * 128 + lane * 4;
-      const int x0 = q.bx * 64, xs = x0 + strip * 8;
-      const int nvalid = min(8, p.W - xs);
+      const int x0 = q.bx * 64, xs = x0 + strip * kPxS;
       const int y0 = q.sy * p.hseg, y1 = min(p.H, y0 + p.hseg);
       const int hb = k & 1;
       const uint32_t halo = sbase + p.halo_off + (uint32_t)hb * p.halo_bytes + (uint32_t)lane * 8u;
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       }
       uint32_t zmask = 0;
 #pragma unroll
-      for (int i = 0; i < 10; ++i) { const int x = xs - 1 + i; if (x < 0 || x >= p.W) zmask |= 1u << i; }
+      for (int i = 0; i < kPxS + 2; ++i) { const int x = xs - 1 + i; if (x < 0 || x >= p.W) zmask |= 1u << i; }
 
       mbar_wait(hfull_bar(hb), (uint32_t)(k >> 1) & 1u);     // the item's halo columns are in place
 
@@ -194,31 +200,31 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       auto load_row = [&](RowF& r, int y) {
         if (y < 0 || y >= p.H) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) r[i][0] = r[i][1] = hz;
+          for (int i = 0; i < kPxS + 2; ++i) r[i][0] = r[i][1] = hz;
           return;
         }
         mbar_wait(sfull_bar(slot), sphase);
         const uint32_t rowb = sbase + p.ring_off + (uint32_t)slot * kSlotF + hoff;
         const uint32_t hrow = halo + (uint32_t)(y - (y0 - 1)) * kHaloRowF;
-        uint2 v[10];
+        uint2 v[kPxS + 2];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
+        for (int i = 0; i < kPxS + 2; ++i) {
           if (i == 0 && strip == 0) v[i] = lds64f(hrow);                       // left neighbour column
-          else if (i == 9 && strip == kConvWarps - 1) v[i] = lds64f(hrow + 256u);   // right neighbour column
+          else if (i == kPxS + 1 && strip == kConvWarps - 1) v[i] = lds64f(hrow + 256u);   // right neighbour column
           else {
-            // band pixel pb = strip * 8 - 1 + i; unit (lane >> 1) of pixel pb sits at unit ^ (pb & 7) (pb & 7 = (i + 7) & 7)
-            const uint32_t pb = (uint32_t)(strip * 8 - 1 + i);
-            v[i] = lds64f(rowb + pb * 256u + (ux ^ ((uint32_t)((i + 7) & 7) << 4)));
+            // band pixel pb = strip * kPxS - 1 + i; unit (lane >> 1) of pixel pb sits at unit ^ (pb & 7)
+            const uint32_t pb = (uint32_t)(strip * kPxS - 1 + i);
+            v[i] = lds64f(rowb + pb * 256u + (ux ^ ((pb & 7u) << 4)));
           }
         }
 #pragma unroll
-        for (int i = 0; i < 10; ++i) { r[i][0] = as_h2f(v[i].x); r[i][1] = as_h2f(v[i].y); }
+        for (int i = 0; i < kPxS + 2; ++i) { r[i][0] = as_h2f(v[i].x); r[i][1] = as_h2f(v[i].y); }
         __syncwarp();
         if (lane == 0) mbar_arrive(sempty_bar(slot));
         if (++slot == p.ring) { slot = 0; sphase ^= 1u; }
         if (zmask) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i)
+          for (int i = 0; i < kPxS + 2; ++i)
             if (zmask & (1u << i)) r[i][0] = r[i][1] = hz;
         }
       };
@@ -229,11 +235,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       load_row(rb, y0);
       __half* orow = p.out + (((size_t)q.n * p.H + y0) * p.W + xs) * p.Ch + c;
       const size_t ostep = (size_t)p.W * p.Ch;
-      const bool ragged = nvalid < 8;
-      auto emit = [&](const RowF& r0, const RowF& r1, const RowF& r2) {
-        if (p.dbg & 1) { orow += ostep; return; }
-        if (!ragged) emit_row_f<false>(r0, r1, r2, w6, orow, p.Ch, 8, psum);
-        else emit_row_f<true>(r0, r1, r2, w6, orow, p.Ch, nvalid, psum);
+      auto emit = [&](const RowF& r0, const RowF& r1, const RowF& r2) {   // (W % 64 == 0: a strip is never ragged)
+        if (!(p.dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, p.Ch, kPxS, psum);
         orow += ostep;
       };
       for (int y = y0; y < y1; y += 3) {
