@@ -75,6 +75,7 @@ struct alignas(64) Tc2Params {
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
+  int fastissue;         // unrolled register-resident issue loops of the TMA / MMA warps for plain resident-weight GEMMs (LCM_TC_FASTISSUE)
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
   uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
 };
@@ -426,6 +427,26 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
         }
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
+        if (p.fastissue && !conv && p.resident && !p.conv_halo && !p.conv_tma && p.nchunks <= 8 && !(dbg & 1)) {
+          // fast path (see the MMA warp): plain 1x1 GEMM, resident weights — one 2-D tile load per chunk, unrolled
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            if (ci < p.nchunks) {
+              const int stage = ring.stage;
+              const uint32_t cd = p.chunk[ci];
+              mbar_wait_relaxed(empty_bar(stage), ring.phase ^ 1u);
+              if (ci == 0) TSTAMP(0);
+              if (elect_one()) {
+                mbar_expect_tx(raw_bar(stage), kStageA2);
+                tma_load_2d(sbase + stage * p.stage_bytes, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
+              }
+              __syncwarp();
+              last_stage = stage; last_phase = ring.phase;
+              ring.advance();
+            }
+          }
+          continue;
+        }
         int ty0 = 0, tx0 = 0;               // conv_tma: first pixel of this tile inside its image
         if (p.conv_tma) { ty0 = ti.rem / p.Wout; tx0 = ti.rem - ty0 * p.Wout; }   // first OUTPUT pixel of the tile
         for (int ci = 0; ci < p.achunks; ++ci, ring.advance()) {
@@ -479,6 +500,27 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      // Experimental issue path (LCM_TC_FASTISSUE=1, default off) — 1x1 GEMM with smem-resident weights and at most 8 K
+      // chunks: everything a chunk needs is packed into registers once, the chunk loop is unrolled, the MMAs are predicated.
+      // The generic loop below spends ~700 cycles per chunk in dependent constant-bank loads (timeline: 2100 of the 3100
+      // cycles of a level-0 project tile, K = 128 + 32, N = 32) and this path cuts that to ~500 — but the WHOLE kernel gets
+      // slower, 334 -> 462 us at 64 x 256^2, for any ring depth from 3 to 16 stages (tests/diag_timeline.py project0).  The
+      // tile period of a CTA is set by the arrival of its TMA tiles either way; issuing the next load the moment a stage
+      // drains makes the SMs' request streams burstier and the memory system slower.  Kept as a measured negative result.
+      const bool fastmma = p.fastissue && !conv && p.resident && !p.conv_halo && !p.bpair && p.nchunks <= 8;
+      uint32_t pk_ks = 0, pk_lo = 0, pk_h = 0;        // per chunk: K steps (4 bits), low-order slot (4 bits, 0xf none), fp16 flag
+      if (fastmma) {
+        for (int ci = 0; ci < p.nchunks; ++ci) {
+          const uint32_t cd = p.chunk[ci];
+          pk_ks |= ((cd >> 12) & 0xfu) << (4 * ci);
+          const uint32_t lo = (p.wgate && p.lo_slot[ci] != 0xff) ? (uint32_t)p.lo_slot[ci] : 0xfu;
+          pk_lo |= (lo & 0xfu) << (4 * ci);
+          pk_h |= ((cd >> 7) & 1u) << ci;
+        }
+      }
+      const uint32_t nch_u = (uint32_t)p.nchunks;
+      const uint64_t bd0 = umma_desc(sbase + p.bres_off);
+      const uint32_t bstep = b_chunk_bytes >> 4;        // descriptor address units per weight chunk
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         if (p.resident && (ti.n_tile != cur_nt || (p.wgate && ti.img != cur_img))) {
           mbar_wait(p.wgate ? bsc_bar : bres_bar, bres_phase);
@@ -490,7 +532,39 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         TSTAMP(3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
-        if (p.conv_halo) {
+        if (fastmma) {
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+            if ((uint32_t)ci < nch_u) {
+              const int stage = ring.stage;
+              mbar_wait(p.all_raw ? raw_bar(stage) : xf_bar(stage), ring.phase);
+              if (ci == 0) TSTAMP(4);
+              if (ci == 1) TSTAMP(15);
+              tc_fence_after();
+              const uint32_t ksteps = (pk_ks >> (4 * ci)) & 0xfu, lo = (pk_lo >> (4 * ci)) & 0xfu;
+              const uint32_t idesc = ((pk_h >> ci) & 1u) ? idesc_h : idesc_b;
+              const uint64_t ad = umma_desc(sbase + (uint32_t)stage * p.stage_bytes);
+              const uint64_t bd = bd0 + (uint64_t)((uint32_t)ci * bstep);
+              const uint64_t bl = bd0 + (uint64_t)((nch_u + lo) * bstep);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if ((uint32_t)k < ksteps) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
+                if (lo != 0xfu) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if ((uint32_t)k < ksteps) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
+                }
+                if (ci == 0) TSTAMP(14);
+                umma_commit(empty_bar(stage));
+                if ((uint32_t)ci == nch_u - 1) umma_commit(tfull_bar(acc));
+              }
+              __syncwarp();
+              if ((uint32_t)ci == nch_u - 1) TSTAMP(5);
+              ring.advance();
+            }
+          }
+        } else if (p.conv_halo) {
           // one halo stage per 64-channel chunk; tap (ky, kx) is the same buffer read from pixel (ky * 130 + kx) on —
           // a shift by whole 128-byte rows inside the SWIZZLE_128B pattern the TMA wrote
           const int nchh = p.achunks;
@@ -523,6 +597,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const uint32_t cd = p.chunk[ci];
           mbar_wait(p.all_raw ? raw_bar(stage) : xf_bar(stage), ring.phase);
           if (ci == 0) TSTAMP(4);
+          if (ci == 1) TSTAMP(15);
           if (conv && !p.resident) mbar_wait(raw_bar(stage), ring.phase);   // streamed weights of a 3x3 conv
           tc_fence_after();
           const int ksteps = (cd >> 12) & 0xf;
@@ -537,6 +612,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
             if (gated)
               for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
+            if (ci == 0) TSTAMP(14);
             if (p.bpair)
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                                empty_bar(stage)), "h"((uint16_t)3)
@@ -871,6 +947,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   if (p.conv_mode < 0 && !p.conv_tma)
     for (int s2 = 0; s2 < g.nseg; ++s2) has_gate |= g.seg[s2].mode == XF_SCALE;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  { static int fi = -1; if (fi < 0) { const char* e = getenv("LCM_TC_FASTISSUE"); fi = e ? atoi(e) : 0; } p.fastissue = fi; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;

@@ -20,8 +20,12 @@ CASES = {
     "project_m": (64, 1024, [1024, 256], 256, [4, 0], [1, 0], 0),
     "project_m128": (64, 1024, [1024, 256], 128, [4, 0], [1, 0], 0),
     "project_m_raw": (64, 1024, [1024, 256], 256, [0, 0], [1, 0], 0),
+    "project0_raw": (64, 65536, [128, 32], 32, [0, 0], [1, 0], 0),
+    "project0_n64": (64, 65536, [128, 32], 64, [0, 0], [1, 0], 0),
+    "project0_k64": (64, 65536, [64, 32], 32, [0, 0], [1, 0], 0),
 }
 images, P, Ks, Nc, modes, h16, o16 = CASES[sys.argv[1] if len(sys.argv) > 1 else "expand0"]
+images = int(os.environ.get("LCM_DIAG_IMAGES", images))
 g = torch.Generator(device="cuda").manual_seed(7)
 M = images * P
 segs = []
@@ -34,7 +38,8 @@ w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / sum(Ks) ** 0.5
 ops.gemm(segs, w, P, impl=1, out_f16=bool(o16))
 out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True, out_f16=bool(o16))
 if os.environ.get("LCM_TIME_ONLY"):
-    print(f"{ms*1e3:.1f} us")
+    by = images * P * (sum(K * 2 for K in Ks) + Nc * 2)
+    print(f"{ms*1e3:.1f} us  images {images}: {by / ms / 1e6:.0f} GB/s algorithmic")
     if int(os.environ.get("LCM_W_DEBUG", "0")) & 16:
         b8 = (C.c_longlong * 8)()
         native.lib().lcm_debug_timeline(b8, 8)
@@ -44,7 +49,7 @@ if os.environ.get("LCM_TIME_ONLY"):
 buf = (C.c_longlong * 1024)()
 native.lib().lcm_debug_timeline(buf, 1024)
 t0 = min(buf[i] for i in range(16) if buf[i] > 0)
-names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done", "xf_cu", "xf_sts", "xf_fence"]
+names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done", "xf_cu", "xf_sts", "xf_fence", "mma_c0iss", "mma_c1rdy"]
 print(f"{ms*1e3:.1f} us;  cycles relative to first stamp")
 
 print("tile " + " ".join(f"{n:>10s}" for n in names))
