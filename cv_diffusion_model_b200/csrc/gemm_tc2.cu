@@ -75,6 +75,7 @@ struct alignas(64) Tc2Params {
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
+  int interleave;        // tile t of CTA b = b + t * gridDim.x instead of a contiguous range (LCM_TC_INTERLEAVE, experiment)
   int fastissue;         // unrolled register-resident issue loops of the TMA / MMA warps for plain resident-weight GEMMs (LCM_TC_FASTISSUE)
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
   uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
@@ -172,7 +173,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   const long long total_tiles = p.m_tiles * p.n_tiles;
   long long t_begin = total_tiles * blockIdx.x / gridDim.x;
   int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
-  const int tstep = p.bpair ? 2 : 1;
+  int tstep = p.bpair ? 2 : 1;
+  if (p.interleave && !p.bpair && p.n_tiles == 1) {
+    t_begin = blockIdx.x;
+    my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    tstep = (int)gridDim.x;
+  }
   const uint32_t pair_rank = blockIdx.x & 1u;   // = %cluster_ctarank for a (2,1,1) cluster
   if (p.bpair) {
     // the two CTAs of a cluster take tiles 2u and 2u + 1 of the same pair-unit u: same n tile (m_tiles is even), same
@@ -773,6 +779,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (kDebug && (p.debug & 256) && tid == 0 && blockIdx.x < 512) {   // per-CTA finish time (ns): load balance across the grid
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    g_timeline[blockIdx.x] = (long long)tns;
+    g_timeline[512 + blockIdx.x] = (long long)my_tiles;
+  }
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -948,6 +960,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
     for (int s2 = 0; s2 < g.nseg; ++s2) has_gate |= g.seg[s2].mode == XF_SCALE;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   { static int fi = -1; if (fi < 0) { const char* e = getenv("LCM_TC_FASTISSUE"); fi = e ? atoi(e) : 0; } p.fastissue = fi; }
+  { static int il = -1; if (il < 0) { const char* e = getenv("LCM_TC_INTERLEAVE"); il = e ? atoi(e) : 0; } p.interleave = il; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
