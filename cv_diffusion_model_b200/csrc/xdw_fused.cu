@@ -70,6 +70,7 @@ struct FParams {
   int N, H, W, Ch, NB;
   int hseg, bandsX, segsY, items, stages, ring;
   uint32_t w_off, ring_off, halo_off, halo_bytes, misc_off;
+  int spin;
   int dbg;   // LCM_XDW_DBG bottleneck experiments: 1 conv warps skip the arithmetic, 2 EPI skips conversion + stores
 };
 
@@ -87,6 +88,11 @@ __device__ __forceinline__ uint2 lds64f(uint32_t addr) {
 __device__ __forceinline__ __half2 as_h2f(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t as_u32f(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
+// every wait of this kernel suspends with a time hint instead of re-polling: the polling loops of the waiting roles were 12 % of
+// all executed instructions (ncu), issued on the sub-partitions the conv warps need (LCM_XDW_SPIN=1: plain try_wait loops)
+__device__ __forceinline__ void waitf_impl(uint32_t bar, uint32_t parity, bool spin) {
+  if (spin) mbar_wait(bar, parity); else mbar_wait_relaxed(bar, parity);
+}
 struct ItemF { int nb, n, bx, sy; };
 __device__ __forceinline__ ItemF decode_f(int item, const FParams& p) {
   ItemF q;
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
   const uint32_t sbase = (sraw + 1023u) & ~1023u;
   uint8_t* smem = fsm_raw2 + (sbase - sraw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool spin = p.spin != 0;
+  auto waitf = [&](uint32_t bar, uint32_t parity) { waitf_impl(bar, parity, spin); };
 
   const uint32_t bar0 = sbase + p.misc_off;
   auto raw_bar = [&](int s) { return bar0 + 8u * s; };                 // TMA -> MMA          (stages)
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < kPxS + 2; ++i) { const int x = xs - 1 + i; if (x < 0 || x >= p.W) zmask |= 1u << i; }
 
-      mbar_wait(hfull_bar(hb), (uint32_t)(k >> 1) & 1u);     // the item's halo columns are in place
+      waitf(hfull_bar(hb), (uint32_t)(k >> 1) & 1u);     // the item's halo columns are in place
 
       // (prefetching row y + 2 into a fourth register row while row y is computed was tried: at the 128 registers that four
       //  warps per sub-partition allow it spills inside the row loop and is 60 % slower)
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
           for (int i = 0; i < kPxS + 2; ++i) r[i][0] = r[i][1] = hz;
           return;
         }
-        mbar_wait(sfull_bar(slot), sphase);
+        waitf(sfull_bar(slot), sphase);
         const uint32_t rowb = sbase + p.ring_off + (uint32_t)slot * kSlotF + hoff;
         const uint32_t hrow = halo + (uint32_t)(y - (y0 - 1)) * kHaloRowF;
         uint2 v[kPxS + 2];
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
         // destination of this thread's pixel (128 channels = 256 bytes)
         uint32_t dst; bool swz; int px = 0; bool valid; int sl = -1;
         if (tl == 0) {
-          mbar_wait(hempty_bar(hb), ((uint32_t)(k >> 1) & 1u) ^ 1u);
+          waitf(hempty_bar(hb), ((uint32_t)(k >> 1) & 1u) ^ 1u);
           const int side = et >> 6, hr = et & 63;
           dst = sbase + p.halo_off + (uint32_t)hb * p.halo_bytes + (uint32_t)hr * kHaloRowF + (uint32_t)side * 256u;
           swz = false;
@@ -309,11 +317,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
           if (valid) {
             sl = (int)(idx % p.ring);
             const uint32_t ph = (uint32_t)((idx / p.ring) & 1);
-            mbar_wait(sempty_bar(sl), ph ^ 1u);
+            waitf(sempty_bar(sl), ph ^ 1u);
             dst = sbase + p.ring_off + (uint32_t)sl * kSlotF + (uint32_t)px * 256u;
           }
         }
-        mbar_wait(tfull_bar(acc), (uint32_t)(tcount >> 1) & 1u);
+        waitf(tfull_bar(acc), (uint32_t)(tcount >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = lane_base + (uint32_t)acc * 128u;
         // 32 columns per step; the load of step i + 1 is in flight while step i is converted and stored
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       const int x0 = q.bx * 64, y0 = q.sy * p.hseg;
       if (q.nb != cur_nb) {
         // every MMA that reads the old weights has completed when the last stage issued has been released
-        if (last_stage >= 0) mbar_wait(empty_bar(last_stage), last_phase);
+        if (last_stage >= 0) waitf(empty_bar(last_stage), last_phase);
         if (elect_one()) {
           const uint32_t wbytes = (uint32_t)p.nchunks * kChunkF;
           mbar_expect_tx(wres_bar, wbytes);
@@ -411,17 +419,17 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
     uint32_t wphase = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const ItemF q = decode_f(item, p);
-      if (q.nb != cur_nb) { mbar_wait(wres_bar, wphase); wphase ^= 1u; cur_nb = q.nb; }
+      if (q.nb != cur_nb) { waitf(wres_bar, wphase); wphase ^= 1u; cur_nb = q.nb; }
       for (int tl = 0; tl < ntiles; ++tl, ++tcount) {
         const int acc = tcount & 1;
         {
           int s2 = stage; uint32_t ph2 = phase;
           for (int ci = 0; ci < p.nchunks; ++ci) {
-            mbar_wait(raw_bar(s2), ph2);
+            waitf(raw_bar(s2), ph2);
             if (++s2 == p.stages) { s2 = 0; ph2 ^= 1u; }
           }
         }
-        mbar_wait(tempty_bar(acc), ((uint32_t)(tcount >> 1) & 1u) ^ 1u);
+        waitf(tempty_bar(acc), ((uint32_t)(tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad0 = umma_desc(sbase + (uint32_t)stage * kChunkF);
@@ -539,6 +547,7 @@ int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2
   const uint32_t total = off + 1024;
   if (total > kSmemLimitF) return -1;
   { static int d = -1; if (d < 0) { const char* e = getenv("LCM_XDW_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
+  { static int sp = -1; if (sp < 0) { const char* e = getenv("LCM_XDW_SPIN"); sp = (e && atoi(e)) ? 1 : 0; } p.spin = sp; }
   if (ensure_dyn_smem_fn(xdw_fused_kernel, kSmemLimitF)) return -2;
   const int grid = p.items < num_sms ? p.items : num_sms;
   launch_pdl(xdw_fused_kernel, dim3(grid), dim3(kThreadsF), total, st, p);
