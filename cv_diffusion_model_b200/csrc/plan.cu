@@ -629,7 +629,9 @@ struct Builder {
     // (see step 2 below) per-image project weight gradient + SE gate gradient from its products; needs Wp as plain fp32
     bool xparts16 = true;
     for (int i = 0; i < x.n; ++i) xparts16 = xparts16 && x.part[i]->C % 16 == 0;
-    const bool se_from_wgrad = p->tc && P % 128 == 0 && P >= 8192 && Co % 16 == 0 && Ch % 16 == 0 && xparts16 &&
+    static int se_minp = -1;
+    if (se_minp < 0) { const char* e = getenv("LCM_SE_WGRAD_MINP"); se_minp = e ? atoi(e) : 4096; }   // 8192 -> 4096: 82.4 -> 81.1 ms per step (the 64^2 level joins)
+    const bool se_from_wgrad = p->tc && P % 128 == 0 && P >= se_minp && Co % 16 == 0 && Ch % 16 == 0 && xparts16 &&
                                !getenv("LCM_NO_SE_FROM_WGRAD");
     const size_t wp_f32 = se_from_wgrad ? p->add_copy(name + ".project.weight", (int64_t)Co * Ch) : 0;
     on_backward([=]() {
