@@ -276,6 +276,32 @@ def get_engine(unet, batch: int, height: int, width: int, device, precision: Opt
 
 
 # ---- functions behind the reference surface -----------------------------------------------------------------
+FP16_MAX = 65504.0
+
+
+def hidden_range_report(unet, x: torch.Tensor, timestep: torch.Tensor) -> Dict[str, object]:
+    """Range check for a checkpoint before it is served on the bf16 / tcgen05 plan.
+
+    That plan stores (or, on the fused expand -> depthwise path, converts in registers) the hidden tensors of every
+    inverted-residual block as fp16 with ``cvt.rn.satfinite``: a value beyond +-65504 is clamped, silently.  Random-init
+    and normally trained weights stay orders of magnitude below that; this helper proves it for a given checkpoint and
+    input by running the fp32 verification plan with taps and returning the largest magnitude of every hidden tensor:
+    ``{"max_abs": {tap: value}, "worst": (tap, value), "fits_fp16": bool, "headroom": 65504 / worst}``."""
+    _require_cuda(x, "x")
+    b, _, h, w = x.shape
+    eng = Engine(unet, b, h, w, precision="fp32", taps=True, device=x.device)
+    try:
+        eng.forward(x, timestep)
+        max_abs = {}
+        for name in eng.taps():
+            if name.endswith(".expand") or name.endswith(".depthwise"):
+                max_abs[name] = float(eng.read_tap(name).abs().max().item())
+    finally:
+        eng.close()
+    worst = max(max_abs.items(), key=lambda kv: kv[1])
+    return {"max_abs": max_abs, "worst": worst, "fits_fp16": worst[1] < 0.5 * FP16_MAX, "headroom": FP16_MAX / max(worst[1], 1e-30)}
+
+
 def unet_forward(unet, x: torch.Tensor, timestep: torch.Tensor) -> torch.Tensor:
     _require_cuda(x, "x")
     if x.dim() != 4:

@@ -447,3 +447,25 @@ def test_enhance_add_conditioning_vs_reference_golden(golden, weight_digests, pr
     assert out["noise_pred"].shape == (2, 3, 64, 64)
     with pytest.raises(NotImplementedError):
         pipe.compute_loss(low.cuda(), lat0.cuda().clamp(-1, 1))
+
+
+def test_fp16_hidden_range_report_and_saturation():
+    """The bf16 plan keeps the blocks' hidden tensors in fp16 (cvt.rn.satfinite).  `hidden_range_report` (fp32 plan + taps)
+    must clear the default-init model with a wide margin, must flag a checkpoint whose expand weights are blown up past the
+    fp16 range, and the bf16 path must stay finite on that checkpoint (saturation, never inf / nan)."""
+    from cv_diffusion_model_b200.engine import Engine, hidden_range_report
+    from tests.util import seeded_unet
+    m = seeded_unet("small", 64, affine=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 64, 64, generator=g).cuda()
+    t = torch.tensor([739, 19], device="cuda")
+    rep = hidden_range_report(m, x, t)
+    assert rep["fits_fp16"] and rep["headroom"] > 100, rep["worst"]
+    with torch.no_grad():
+        m.encoder_blocks[0][0].expand.weight.mul_(3e5)
+    rep2 = hidden_range_report(m, x, t)
+    assert not rep2["fits_fp16"] and rep2["worst"][0].startswith("encoder_blocks.0.0"), rep2["worst"]
+    eng = Engine(m, 2, 64, 64, precision="bf16", device="cuda")
+    y = eng.forward(x, t)
+    eng.close()
+    assert torch.isfinite(y).all()
