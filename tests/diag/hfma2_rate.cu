@@ -21,6 +21,9 @@ __global__ void rate(float* out, long long* cyc, int iters) {
       if (MODE == 1) f[i] = fmaf(f[i], fm, fc);
       if (MODE == 2) a[i] = __hadd2(a[i], c);
       if (MODE == 3) { a[i] = __hfma2(a[i], m, a[(i + 1) & 15]); }   // three distinct register operands
+      if (MODE == 4) { if (i & 1) a[i] = __hfma2(a[i], m, c); else f[i] = fmaf(f[i], fm, fc); }          // 1 : 1 mix
+      if (MODE == 5) { if ((i & 3) == 3) f[i] = fmaf(f[i], fm, fc); else a[i] = __hfma2(a[i], m, c); }   // 3 HFMA2 : 1 FFMA
+      if (MODE == 6) { if (i & 1) a[i] = __hfma2(a[i], m, c); else f[i] = __int_as_float(__float_as_int(f[i]) * 3 + i); }   // HFMA2 : IMAD
     }
   }
   const long long t1 = clock64();
@@ -42,7 +45,7 @@ void run(const char* name, int warps) {
   long long h[148];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   const double per_smsp = (double)iters * 16 * warps / 4.0 / (double)h[0];
-  printf("%-8s warps/SM %2d: %.3f warp-instr / cycle / SMSP\n", name, warps, per_smsp);
+  printf("%-16s warps/SM %2d: %.3f warp-instr / cycle / SMSP\n", name, warps, per_smsp);
   cudaFree(out); cudaFree(cyc);
 }
 
@@ -52,6 +55,9 @@ int main() {
     run<3>("HFMA2.3r", w);
     run<1>("FFMA", w);
     run<2>("HADD2", w);
+    run<4>("HFMA2+FFMA 1:1", w);
+    run<5>("HFMA2+FFMA 3:1", w);
+    run<6>("HFMA2+IMAD 1:1", w);
   }
   return 0;
 }
