@@ -75,6 +75,7 @@ struct alignas(64) Tc2Params {
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
+  int pace;              // fast issue path: minimum cycles between two activation-chunk loads of a CTA (LCM_TC_PACE, experiment)
   int interleave;        // tile t of CTA b = b + t * gridDim.x instead of a contiguous range (LCM_TC_INTERLEAVE, experiment)
   int fastissue;         // unrolled register-resident issue loops of the TMA / MMA warps for plain resident-weight GEMMs (LCM_TC_FASTISSUE)
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
       int last_stage = -1; uint32_t last_phase = 0;   // ring slot / phase of the last activation chunk issued
+      long long next_issue = clock64();
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
         if (p.resident) {
@@ -433,22 +435,30 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
         }
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
-        if (p.fastissue && !conv && p.resident && !p.conv_halo && !p.conv_tma && p.nchunks <= 8 && !(dbg & 1)) {
-          // fast path (see the MMA warp): plain 1x1 GEMM, resident weights — one 2-D tile load per chunk, unrolled
+        if ((p.fastissue & 2) && !conv && p.resident && !p.conv_halo && !p.conv_tma && p.nchunks <= 8 && !(dbg & 1)) {
+          // fast path (see the MMA warp): plain 1x1 GEMM, resident weights — one 2-D tile load per chunk, unrolled.
+          // fastissue & 4: the loads of a tile are issued in groups of up to 4 chunks back to back (after ALL their stages are
+          // free): the 64-channel chunks of one K segment are the 128-byte pieces of the same pixel rows, and DRAM sees them
+          // together instead of ~700 cycles apart.
+          const int grp = (p.fastissue & 4) ? (p.nchunks < 4 ? p.nchunks : 4) : 1;
 #pragma unroll
-          for (int ci = 0; ci < 8; ++ci) {
-            if (ci < p.nchunks) {
-              const int stage = ring.stage;
-              const uint32_t cd = p.chunk[ci];
-              mbar_wait_relaxed(empty_bar(stage), ring.phase ^ 1u);
-              if (ci == 0) TSTAMP(0);
-              if (elect_one()) {
-                mbar_expect_tx(raw_bar(stage), kStageA2);
-                tma_load_2d(sbase + stage * p.stage_bytes, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
+          for (int c0 = 0; c0 < 8; c0 += 1) {
+            if (c0 < p.nchunks && (c0 % grp) == 0) {
+              const int ng = (p.nchunks - c0) < grp ? (p.nchunks - c0) : grp;
+              Ring r2 = ring;
+              for (int j = 0; j < ng; ++j) { mbar_wait_relaxed(empty_bar(r2.stage), r2.phase ^ 1u); r2.advance(); }
+              if (c0 == 0) TSTAMP(0);
+              for (int j = 0; j < ng; ++j) {
+                const int stage = ring.stage;
+                const uint32_t cd = p.chunk[c0 + j];
+                if (elect_one()) {
+                  mbar_expect_tx(raw_bar(stage), kStageA2);
+                  tma_load_2d(sbase + stage * p.stage_bytes, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
+                }
+                __syncwarp();
+                last_stage = stage; last_phase = ring.phase;
+                ring.advance();
               }
-              __syncwarp();
-              last_stage = stage; last_phase = ring.phase;
-              ring.advance();
             }
           }
           continue;
@@ -511,9 +521,12 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       // The generic loop below spends ~700 cycles per chunk in dependent constant-bank loads (timeline: 2100 of the 3100
       // cycles of a level-0 project tile, K = 128 + 32, N = 32) and this path cuts that to ~500 — but the WHOLE kernel gets
       // slower, 334 -> 462 us at 64 x 256^2, for any ring depth from 3 to 16 stages (tests/diag_timeline.py project0).  The
-      // tile period of a CTA is set by the arrival of its TMA tiles either way; issuing the next load the moment a stage
-      // drains makes the SMs' request streams burstier and the memory system slower.  Kept as a measured negative result.
-      const bool fastmma = p.fastissue && !conv && p.resident && !p.conv_halo && !p.bpair && p.nchunks <= 8;
+      // tile period of a CTA is set by the arrival of its TMA tiles either way (load latency ~8000 cycles with the ring full:
+      // the kernel is bound by what the memory system delivers for this request pattern, 4.8 TB/s).  Bits: 1 = this MMA path,
+      // 2 = the TMA warp's, 4 = a tile's loads issued back to back.  1 alone 352 us, 2 alone 343 .. 496 us depending on code
+      // shape, 1 + 2 462 us, 2 + 4 385 us; pacing the loads (LCM_TC_PACE cycles apart) changes nothing.  Kept as measured
+      // negative results; the generic loops are the product path.
+      const bool fastmma = (p.fastissue & 1) && !conv && p.resident && !p.conv_halo && !p.bpair && p.nchunks <= 8;
       uint32_t pk_ks = 0, pk_lo = 0, pk_h = 0;        // per chunk: K steps (4 bits), low-order slot (4 bits, 0xf none), fp16 flag
       if (fastmma) {
         for (int ci = 0; ci < p.nchunks; ++ci) {
@@ -961,6 +974,7 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   { static int fi = -1; if (fi < 0) { const char* e = getenv("LCM_TC_FASTISSUE"); fi = e ? atoi(e) : 0; } p.fastissue = fi; }
   { static int il = -1; if (il < 0) { const char* e = getenv("LCM_TC_INTERLEAVE"); il = e ? atoi(e) : 0; } p.interleave = il; }
+  { static int pc = -1; if (pc < 0) { const char* e = getenv("LCM_TC_PACE"); pc = e ? atoi(e) : 0; } p.pace = pc; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;
