@@ -41,6 +41,27 @@ __global__ void copy_v4(const uint4* in, uint4* out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
+// read-only stream (sum into one word per thread) and the project GEMM's traffic shape, 5 reads : 1 write
+__global__ void read_v4(const uint4* in, uint32_t* out, size_t n) {
+  uint32_t acc = 0;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i + 3 * st < n; i += 4 * st) {
+    const uint4 a = in[i], b = in[i + st], c = in[i + 2 * st], d = in[i + 3 * st];
+    acc += a.x ^ b.y ^ c.z ^ d.w;
+  }
+  for (; i < n; i += st) acc += in[i].x;
+  if (acc == 0x12345678u) out[0] = acc;
+}
+__global__ void mix51(const uint4* in, uint4* out, size_t nout) {   // out row i <- 5 input vectors (in has 5 * nout)
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t st = (size_t)gridDim.x * blockDim.x;
+  for (; i < nout; i += st) {
+    const uint4 a = in[i], b = in[i + nout], c = in[i + 2 * nout], d = in[i + 3 * nout], e = in[i + 4 * nout];
+    out[i] = make_uint4(a.x ^ b.x, c.y ^ d.y, e.z, a.w);
+  }
+}
+
 template <typename F> float timeit(F f, int n = 10) {
   f(); cudaDeviceSynchronize();
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -72,5 +93,11 @@ int main() {
   }
   ms = timeit([&] { copy_v4<<<148 * 16, 512>>>((const uint4*)x, (uint4*)y, n); }); printf("copy 1:1          %7.0f GB/s (r+w)\n", 2.0 * bytes / ms / 1e6);
   ms = timeit([&] { mix14<<<148 * 16, 512>>>((const uint4*)x, (uint4*)y, n / 4); }); printf("mix 1r:4w         %7.0f GB/s (r+w)\n", (bytes / 4.0 * 5) / ms / 1e6);
+  uint32_t* flag; cudaMalloc(&flag, 4);
+  for (int g : {148 * 8, 148 * 16, 148 * 32}) {
+    ms = timeit([&] { read_v4<<<g, 512>>>((const uint4*)x, flag, n); }); printf("read-only grid %5d %7.0f GB/s\n", g, bytes / ms / 1e6);
+  }
+  { const size_t nout = n / 5;
+    ms = timeit([&] { mix51<<<148 * 16, 512>>>((const uint4*)x, (uint4*)y, nout); }); printf("mix 5r:1w         %7.0f GB/s (r+w)\n", nout * 16.0 * 6 / ms / 1e6); }
   return 0;
 }
