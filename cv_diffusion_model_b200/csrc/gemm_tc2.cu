@@ -873,9 +873,14 @@ bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides)
     for (int i = 0; i < rank && i < 5; ++i) estr[i] = elem_strides[i];
+  // L2 promotion: the granularity at which a TMA read allocates in L2 (LCM_TMAP_L2 = 0 none, 1 64 B, 2 128 B, 3 256 B)
+  static int l2p = -1;
+  if (l2p < 0) { const char* e = getenv("LCM_TMAP_L2"); l2p = e ? atoi(e) : 2; if (l2p < 0 || l2p > 3) l2p = 2; }
+  const CUtensorMapL2promotion prom = l2p == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2p == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : l2p == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   return enc(out, dtype == TMAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
              const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, prom,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
