@@ -75,9 +75,6 @@ struct alignas(64) Tc2Params {
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
-  int pace;              // fast issue path: minimum cycles between two activation-chunk loads of a CTA (LCM_TC_PACE, experiment)
-  int interleave;        // tile t of CTA b = b + t * gridDim.x instead of a contiguous range (LCM_TC_INTERLEAVE, experiment)
-  int fastissue;         // unrolled register-resident issue loops of the TMA / MMA warps for plain resident-weight GEMMs (LCM_TC_FASTISSUE)
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
   uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
 };
@@ -174,12 +171,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
   const long long total_tiles = p.m_tiles * p.n_tiles;
   long long t_begin = total_tiles * blockIdx.x / gridDim.x;
   int my_tiles = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x - t_begin);
-  int tstep = p.bpair ? 2 : 1;
-  if (p.interleave && !p.bpair && p.n_tiles == 1) {
-    t_begin = blockIdx.x;
-    my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    tstep = (int)gridDim.x;
-  }
+  const int tstep = p.bpair ? 2 : 1;
   const uint32_t pair_rank = blockIdx.x & 1u;   // = %cluster_ctarank for a (2,1,1) cluster
   if (p.bpair) {
     // the two CTAs of a cluster take tiles 2u and 2u + 1 of the same pair-unit u: same n tile (m_tiles is even), same
@@ -409,7 +401,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;   // accumulator stage / phase of the PREVIOUS tile
       int last_stage = -1; uint32_t last_phase = 0;   // ring slot / phase of the last activation chunk issued
-      long long next_issue = clock64();
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         const bf16* wt = p.W + (size_t)ti.n_tile * p.nchunks * p.block_n * 64;
         if (p.resident) {
@@ -435,34 +426,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           if (it > 0) { acc ^= 1; if (acc == 0) aphase ^= 1u; }
         }
         if (conv && p.resident) continue;   // nothing per chunk: the gather warps fill A themselves
-        if ((p.fastissue & 2) && !conv && p.resident && !p.conv_halo && !p.conv_tma && p.nchunks <= 8 && !(dbg & 1)) {
-          // fast path (see the MMA warp): plain 1x1 GEMM, resident weights — one 2-D tile load per chunk, unrolled.
-          // fastissue & 4: the loads of a tile are issued in groups of up to 4 chunks back to back (after ALL their stages are
-          // free): the 64-channel chunks of one K segment are the 128-byte pieces of the same pixel rows, and DRAM sees them
-          // together instead of ~700 cycles apart.
-          const int grp = (p.fastissue & 4) ? (p.nchunks < 4 ? p.nchunks : 4) : 1;
-#pragma unroll
-          for (int c0 = 0; c0 < 8; c0 += 1) {
-            if (c0 < p.nchunks && (c0 % grp) == 0) {
-              const int ng = (p.nchunks - c0) < grp ? (p.nchunks - c0) : grp;
-              Ring r2 = ring;
-              for (int j = 0; j < ng; ++j) { mbar_wait_relaxed(empty_bar(r2.stage), r2.phase ^ 1u); r2.advance(); }
-              if (c0 == 0) TSTAMP(0);
-              for (int j = 0; j < ng; ++j) {
-                const int stage = ring.stage;
-                const uint32_t cd = p.chunk[c0 + j];
-                if (elect_one()) {
-                  mbar_expect_tx(raw_bar(stage), kStageA2);
-                  tma_load_2d(sbase + stage * p.stage_bytes, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
-                }
-                __syncwarp();
-                last_stage = stage; last_phase = ring.phase;
-                ring.advance();
-              }
-            }
-          }
-          continue;
-        }
         int ty0 = 0, tx0 = 0;               // conv_tma: first pixel of this tile inside its image
         if (p.conv_tma) { ty0 = ti.rem / p.Wout; tx0 = ti.rem - ty0 * p.Wout; }   // first OUTPUT pixel of the tile
         for (int ci = 0; ci < p.achunks; ++ci, ring.advance()) {
@@ -516,30 +479,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
       Ring ring{0, 0u, p.stages};
       int acc = 0; uint32_t aphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      // Experimental issue path (LCM_TC_FASTISSUE=1, default off) — 1x1 GEMM with smem-resident weights and at most 8 K
-      // chunks: everything a chunk needs is packed into registers once, the chunk loop is unrolled, the MMAs are predicated.
-      // The generic loop below spends ~700 cycles per chunk in dependent constant-bank loads (timeline: 2100 of the 3100
-      // cycles of a level-0 project tile, K = 128 + 32, N = 32) and this path cuts that to ~500 — but the WHOLE kernel gets
-      // slower, 334 -> 462 us at 64 x 256^2, for any ring depth from 3 to 16 stages (tests/diag_timeline.py project0).  The
-      // tile period of a CTA is set by the arrival of its TMA tiles either way (load latency ~8000 cycles with the ring full:
-      // the kernel is bound by what the memory system delivers for this request pattern, 4.8 TB/s).  Bits: 1 = this MMA path,
-      // 2 = the TMA warp's, 4 = a tile's loads issued back to back.  1 alone 352 us, 2 alone 343 .. 496 us depending on code
-      // shape, 1 + 2 462 us, 2 + 4 385 us; pacing the loads (LCM_TC_PACE cycles apart) changes nothing.  Kept as measured
-      // negative results; the generic loops are the product path.
-      const bool fastmma = (p.fastissue & 1) && !conv && p.resident && !p.conv_halo && !p.bpair && p.nchunks <= 8;
-      uint32_t pk_ks = 0, pk_lo = 0, pk_h = 0;        // per chunk: K steps (4 bits), low-order slot (4 bits, 0xf none), fp16 flag
-      if (fastmma) {
-        for (int ci = 0; ci < p.nchunks; ++ci) {
-          const uint32_t cd = p.chunk[ci];
-          pk_ks |= ((cd >> 12) & 0xfu) << (4 * ci);
-          const uint32_t lo = (p.wgate && p.lo_slot[ci] != 0xff) ? (uint32_t)p.lo_slot[ci] : 0xfu;
-          pk_lo |= (lo & 0xfu) << (4 * ci);
-          pk_h |= ((cd >> 7) & 1u) << ci;
-        }
-      }
-      const uint32_t nch_u = (uint32_t)p.nchunks;
-      const uint64_t bd0 = umma_desc(sbase + p.bres_off);
-      const uint32_t bstep = b_chunk_bytes >> 4;        // descriptor address units per weight chunk
       for (int it = 0; it < my_tiles; ++it, ti.next(m_tiles, p.P)) {
         if (p.resident && (ti.n_tile != cur_nt || (p.wgate && ti.img != cur_img))) {
           mbar_wait(p.wgate ? bsc_bar : bres_bar, bres_phase);
@@ -551,39 +490,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
         TSTAMP(3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_u + (uint32_t)acc * 256u;
-        if (fastmma) {
-#pragma unroll
-          for (int ci = 0; ci < 8; ++ci) {
-            if ((uint32_t)ci < nch_u) {
-              const int stage = ring.stage;
-              mbar_wait(p.all_raw ? raw_bar(stage) : xf_bar(stage), ring.phase);
-              if (ci == 0) TSTAMP(4);
-              if (ci == 1) TSTAMP(15);
-              tc_fence_after();
-              const uint32_t ksteps = (pk_ks >> (4 * ci)) & 0xfu, lo = (pk_lo >> (4 * ci)) & 0xfu;
-              const uint32_t idesc = ((pk_h >> ci) & 1u) ? idesc_h : idesc_b;
-              const uint64_t ad = umma_desc(sbase + (uint32_t)stage * p.stage_bytes);
-              const uint64_t bd = bd0 + (uint64_t)((uint32_t)ci * bstep);
-              const uint64_t bl = bd0 + (uint64_t)((nch_u + lo) * bstep);
-              if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if ((uint32_t)k < ksteps) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
-                if (lo != 0xfu) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if ((uint32_t)k < ksteps) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
-                }
-                if (ci == 0) TSTAMP(14);
-                umma_commit(empty_bar(stage));
-                if ((uint32_t)ci == nch_u - 1) umma_commit(tfull_bar(acc));
-              }
-              __syncwarp();
-              if ((uint32_t)ci == nch_u - 1) TSTAMP(5);
-              ring.advance();
-            }
-          }
-        } else if (p.conv_halo) {
+        if (p.conv_halo) {
           // one halo stage per 64-channel chunk; tap (ky, kx) is the same buffer read from pixel (ky * 130 + kx) on —
           // a shift by whole 128-byte rows inside the SWIZZLE_128B pattern the TMA wrote
           const int nchh = p.achunks;
@@ -616,7 +523,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
           const uint32_t cd = p.chunk[ci];
           mbar_wait(p.all_raw ? raw_bar(stage) : xf_bar(stage), ring.phase);
           if (ci == 0) TSTAMP(4);
-          if (ci == 1) TSTAMP(15);
           if (conv && !p.resident) mbar_wait(raw_bar(stage), ring.phase);   // streamed weights of a 3x3 conv
           tc_fence_after();
           const int ksteps = (cd >> 12) & 0xf;
@@ -631,7 +537,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
               umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (ci | k) != 0 ? 1u : 0u);
             if (gated)
               for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
-            if (ci == 0) TSTAMP(14);
             if (p.bpair)
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                                empty_bar(stage)), "h"((uint16_t)3)
@@ -792,12 +697,6 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (kDebug && (p.debug & 256) && tid == 0 && blockIdx.x < 512) {   // per-CTA finish time (ns): load balance across the grid
-    unsigned long long tns;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
-    g_timeline[blockIdx.x] = (long long)tns;
-    g_timeline[512 + blockIdx.x] = (long long)my_tiles;
-  }
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -873,14 +772,9 @@ bool encode_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides)
     for (int i = 0; i < rank && i < 5; ++i) estr[i] = elem_strides[i];
-  // L2 promotion: the granularity at which a TMA read allocates in L2 (LCM_TMAP_L2 = 0 none, 1 64 B, 2 128 B, 3 256 B)
-  static int l2p = -1;
-  if (l2p < 0) { const char* e = getenv("LCM_TMAP_L2"); l2p = e ? atoi(e) : 2; if (l2p < 0 || l2p > 3) l2p = 2; }
-  const CUtensorMapL2promotion prom = l2p == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2p == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                    : l2p == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   return enc(out, dtype == TMAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
              const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, prom,
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -977,9 +871,6 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   if (p.conv_mode < 0 && !p.conv_tma)
     for (int s2 = 0; s2 < g.nseg; ++s2) has_gate |= g.seg[s2].mode == XF_SCALE;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LCM_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  { static int fi = -1; if (fi < 0) { const char* e = getenv("LCM_TC_FASTISSUE"); fi = e ? atoi(e) : 0; } p.fastissue = fi; }
-  { static int il = -1; if (il < 0) { const char* e = getenv("LCM_TC_INTERLEAVE"); il = e ? atoi(e) : 0; } p.interleave = il; }
-  { static int pc = -1; if (pc < 0) { const char* e = getenv("LCM_TC_PACE"); pc = e ? atoi(e) : 0; } p.pace = pc; }
   // shared-memory layout
   const uint32_t b_chunk = (uint32_t)block_n * 128u;
   const uint32_t stg_stride = (uint32_t)block_n * 2u + 16u;

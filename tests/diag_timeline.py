@@ -37,15 +37,6 @@ for K, mode, is16 in zip(Ks, modes, h16):
 w = torch.randn(Nc, sum(Ks), device="cuda", generator=g) / sum(Ks) ** 0.5
 ops.gemm(segs, w, P, impl=1, out_f16=bool(o16))
 out, stats, ms = ops.gemm(segs, w, P, impl=1, repeat=1, timing=True, out_f16=bool(o16))
-if int(os.environ.get("LCM_TC_DEBUG", "0")) & 256:
-    buf = (C.c_longlong * 1024)()
-    native.lib().lcm_debug_timeline(buf, 1024)
-    ends = [buf[i] for i in range(512) if buf[i] > 0]
-    e0 = min(ends)
-    rel = sorted((e - e0) / 1e3 for e in ends)
-    print(f"{ms*1e3:.1f} us; {len(ends)} CTAs; finish-time spread (us after the first CTA to finish): "
-          f"median {rel[len(rel)//2]:.1f}, p90 {rel[int(len(rel)*0.9)]:.1f}, max {rel[-1]:.1f}")
-    sys.exit(0)
 if os.environ.get("LCM_TIME_ONLY"):
     by = images * P * (sum(K * 2 for K in Ks) + Nc * 2)
     print(f"{ms*1e3:.1f} us  images {images}: {by / ms / 1e6:.0f} GB/s algorithmic")
@@ -58,7 +49,7 @@ if os.environ.get("LCM_TIME_ONLY"):
 buf = (C.c_longlong * 1024)()
 native.lib().lcm_debug_timeline(buf, 1024)
 t0 = min(buf[i] for i in range(16) if buf[i] > 0)
-names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done", "xf_cu", "xf_sts", "xf_fence", "mma_c0iss", "mma_c1rdy"]
+names = ["tma_empty", "xf_raw", "xf_arrive", "mma_tempty", "mma_xf", "mma_commit", "e1_tfull", "e1_sempty", "e1_done", "e2_sfull", "e2_done", "xf_cu", "xf_sts", "xf_fence"]
 print(f"{ms*1e3:.1f} us;  cycles relative to first stamp")
 
 print("tile " + " ".join(f"{n:>10s}" for n in names))
