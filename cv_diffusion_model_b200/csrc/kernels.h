@@ -165,6 +165,10 @@ bool xdw_fused_supported(int nseg, const int* segK, int Nc, int H, int W);
 int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2* coef2, const float* wdw, void* out, double* pool,
                      int N, int H, int W, int num_sms, cudaStream_t st);
 int launch_gemm_expand(const GemmParams& p, void* scratch, bool zero_scratch, int num_sms, cudaStream_t st, bool stats_only = false);
+// proj_stream.cu: the level-0 project GEMM (K = 128 fp16 SE-gated + 32 bf16 -> N = 32) as a barrier-free streaming kernel on mma.sync;
+// W row-major [Nc][160] 16-bit (fp16 | bf16 columns)
+bool proj_stream_supported(int nseg, const int* segK, const int* seg_f16, const int* seg_mode, int Nc, int P);
+int launch_proj_stream(const GemmParams& g, int num_sms, cudaStream_t st);
 // gemm_wide.cu: the same operation for 128 <= K <= 448 (activation tile stationary, weights streamed; statistics from the
 // epilogue, accumulated into p.stats).  Weights packed like gemm_expand's (block_n = 128, x6).
 bool gemm_wide_supported(int nseg, const int* segK, int Nc, int P);

@@ -64,6 +64,12 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
     for (int i = 0; i < nseg; ++i) { segK[i] = segs[i].K; wide = wide && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6 && !segs[i].f16; }
     wide = wide && gemm_wide_supported(nseg, segK, Nc, P) && M % 128 == 0;
   }
+  bool pstream = false;   // level-0 project shape: the streaming kernel (proj_stream.cu), row-major 16-bit weights
+  if (tc && !out16 && stats_dev && nseg == 2 && segs[0].coef && M % P == 0) {
+    const int sk[2] = {segs[0].K, segs[1].K}, sf[2] = {segs[0].f16 ? 1 : 0, segs[1].f16 ? 1 : 0};
+    const int sm[2] = {segs[0].coef ? segs[0].mode : XF_NONE, segs[1].coef ? segs[1].mode : XF_NONE};
+    pstream = proj_stream_supported(2, sk, sf, sm, Nc, P);
+  }
   const int block_n = tc ? ((expand || wide) ? 128 : gemm_tc_pick_block_n(Nc)) : 0;
   const size_t wbytes = tc ? (size_t)Nc * Kpad * 2 : (size_t)Nc * Ktot * (bf ? 2 : 4);
   void* wbuf = nullptr;
@@ -72,8 +78,8 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   for (int i = 0; i < nseg; ++i) {
     PackJob j{};
     if (segs[i].f16 && !tc) { cudaFree(wbuf); return LCM_ERR_INVALID; }
-    j.kind = PACK_MAT; j.layout = tc ? WL_UMMA : WL_ROWMAJOR; j.bf16 = segs[i].f16 ? 2 : (bf ? 1 : 0); j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
-    j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = tc ? Kpad : Ktot; j.off = tc ? poff[i] : off[i]; j.block_n = block_n;
+    j.kind = PACK_MAT; j.layout = (tc && !pstream) ? WL_UMMA : WL_ROWMAJOR; j.bf16 = segs[i].f16 ? 2 : (bf ? 1 : 0); j.dst = wbuf; j.R = Nc; j.Cc = segs[i].K;
+    j.src_ld = Ktot; j.src_col0 = off[i]; j.ld = (tc && !pstream) ? Kpad : Ktot; j.off = (tc && !pstream) ? poff[i] : off[i]; j.block_n = block_n;
     j.scale = (tc && segs[i].coef && segs[i].mode == XF_AFFINE_RELU6) ? 6.f : 0.f;   // relu6 prologue = 6 sat(.) on the tcgen05 path
     launch_pack(j, w_dev, st);
     gp.seg[i].A = segs[i].A; gp.seg[i].K = segs[i].K; gp.seg[i].ld = segs[i].K;
@@ -90,7 +96,8 @@ int lcm_op_gemm(const lcm_gemm_seg* segs, int nseg, const float* w_dev, void* ou
   Timer t(st, ms_out, repeat);
   for (int r = 0; r < repeat && rc == 0; ++r) {
     if ((expand || wide) && repeat > 1 && stats_dev) cudaMemsetAsync(stats_dev, 0, (size_t)(M / P) * Nc * 2 * sizeof(double), st);   // the finalisation kernel owns its entries
-    if (expand) rc = launch_gemm_expand(gp, xscratch, true, sms, st);
+    if (pstream) rc = launch_proj_stream(gp, sms, st);
+    else if (expand) rc = launch_gemm_expand(gp, xscratch, true, sms, st);
     else if (wide) rc = launch_gemm_wide(gp, sms, st);
     else if (tc) { ConvGeom g{}; g.mode = -1; rc = launch_gemm_tc(gp, g, block_n, sms, st); }
     else launch_gemm_simt(gp, bf, st);

@@ -119,6 +119,7 @@ typedef std::function<void(const RunCtx&, cudaStream_t)> RunFn;
 struct Op {
   std::string name, kernel;
   double bytes = 0, flops = 0;
+  double ref_bytes = 0;   // SURVEY accounting of the reference op(s) this op stands for (= bytes unless a fusion moves less)
   int launches = 1;   // kernels this op enqueues
   RunFn run;
 };
@@ -376,8 +377,9 @@ struct Builder {
   // ref_bytes: what the reference's op sequence moves for this op where a fusion of ours moves less (default: the same)
   void push(const std::string& name, const char* kernel, double bytes, double flops, RunFn fn, double ref_bytes = -1.0) {
     Op o; o.name = name; o.kernel = kernel; o.bytes = bytes; o.flops = flops; o.run = std::move(fn);
+    o.ref_bytes = ref_bytes >= 0.0 ? ref_bytes : bytes;
     p->total_bytes += bytes; p->total_flops += flops;
-    p->total_bytes_ref += ref_bytes >= 0.0 ? ref_bytes : bytes;
+    p->total_bytes_ref += o.ref_bytes;
     p->ops.push_back(std::move(o));
   }
 
@@ -576,7 +578,37 @@ struct Builder {
     }
     // SE scale -> project -> + (skip conv | identity)(x)  (:100,226,230-234) as ONE GEMM over [h2 | x]
     TensorP out = p->new_tensor(Co, h, w, true, name + ".out");
-    {
+    bool pstream = false;
+    if (p->tc && hid16 && x.n == 1) {
+      const int sk[2] = {Ch, Ci}, sf[2] = {1, 0}, sm[2] = {XF_SCALE, XF_NONE};
+      pstream = proj_stream_supported(2, sk, sf, sm, Co, h * w);
+    }
+    if (pstream) {
+      // level-0 shape (K = 128 + 32 -> N = 32): the streaming kernel (proj_stream.cu), weights row-major [Co][Ch + Ci] 16-bit
+      const size_t woff = p->walloc((size_t)Co * (Ch + Ci) * sizeof(bf16));
+      PackJob j{};
+      j.kind = PACK_MAT; j.layout = WL_ROWMAJOR; j.bf16 = 2; j.dst = (void*)woff; j.R = Co; j.Cc = Ch; j.src_ld = Ch; j.src_col0 = 0;
+      j.ld = Ch + Ci; j.off = 0;
+      p->add_weight(name + ".project.weight", (int64_t)Co * Ch, j);
+      PackJob k = j;
+      k.bf16 = 1; k.Cc = Ci; k.src_ld = Ci; k.off = Ch;
+      if (Ci != Co) p->add_weight(name + ".skip.weight", (int64_t)Co * Ci, k);
+      else { k.kind = PACK_IDENTITY; p->identity_jobs.push_back(k); }
+      lcm_plan* pl = p; const int n = N;
+      const TensorP xin = x.part[0];
+      const double bytes = (Ch + Ci + Co) * N * P * es + (double)Ch * Co * es + (Ci != Co ? (double)Ci * Co * es : 0.0);
+      const double flops = 2.0 * N * P * Ch * Co + (Ci != Co ? 2.0 * N * P * Ci * Co : 0.0);
+      push(name + ".project", "proj_stream", bytes, flops, [=](const RunCtx& c, cudaStream_t st) {
+        GemmParams gp{};
+        gp.nseg = 2;
+        gp.seg[0].A = c.a + h2->off; gp.seg[0].K = Ch; gp.seg[0].ld = Ch; gp.seg[0].mode = XF_SCALE; gp.seg[0].f16 = 1;
+        gp.seg[0].coef = (const float2*)(c.f + gate); gp.seg[0].coef_ld = Ch; gp.seg[0].coef_off = 0;
+        gp.seg[1].A = c.a + xin->off; gp.seg[1].K = Ci; gp.seg[1].ld = Ci; gp.seg[1].mode = XF_NONE; gp.seg[1].f16 = 0;
+        gp.Ktot = Ch + Ci; gp.W = pl->wbase + woff; gp.out = c.a + out->off; gp.stats = (double*)(c.z + out->stats_off);
+        gp.P = h * w; gp.M = (long long)n * gp.P; gp.Nc = Co; gp.out_f16 = 0;
+        if (launch_proj_stream(gp, pl->num_sms, st)) *c.launch_err = 1;
+      });
+    } else {
       std::vector<int> pk;
       pk.push_back(Ch);
       for (int i = 0; i < x.n; ++i) pk.push_back(x.part[i]->C);
@@ -1287,6 +1319,7 @@ int build_plan(lcm_plan* p) {
     }
     Op& f = p->ops[film_op_index];
     f.bytes = (double)rows * ted * 4; f.flops = 2.0 * N * rows * ted;
+    f.ref_bytes = f.bytes;
     p->total_bytes += f.bytes; p->total_flops += f.flops; p->total_bytes_ref += f.bytes;
     f.run = [=](const RunCtx& cx, cudaStream_t st) {
       launch_film((const float*)(cx.f + p->silu_f_off), p->wf(fw), p->wf(fb), (float*)(cx.f + p->film_f_off), N, rows, ted, st);
@@ -1381,7 +1414,7 @@ int run_forward(lcm_plan* p, RunCtx& c, cudaStream_t st, lcm_op_profile* rec, in
       snprintf(r.name, sizeof(r.name), "%s", p->ops[i].name.c_str());
       snprintf(r.kernel, sizeof(r.kernel), "%s", p->ops[i].kernel.c_str());
       cudaEventElapsedTime(&r.ms, ev[i], ev[i + 1]);
-      r.bytes = p->ops[i].bytes; r.flops = p->ops[i].flops;
+      r.bytes = p->ops[i].bytes; r.flops = p->ops[i].flops; r.ref_bytes = p->ops[i].ref_bytes;
     }
     for (auto& e : ev) cudaEventDestroy(e);
   }

@@ -232,7 +232,7 @@ class Engine:
                 self.handle, C.c_void_p(x.data_ptr()), x.shape[1], x.stride(0), None, 0, 0, C.c_void_p(t.data_ptr()),
                 C.c_void_p(eps.data_ptr()), C.c_void_p(self.workspace.data_ptr()), _stream_ptr(), recs, cap))
         return [dict(name=recs[i].name.decode(), kernel=recs[i].kernel.decode(), ms=recs[i].ms, bytes=recs[i].bytes,
-                     flops=recs[i].flops) for i in range(min(n, cap))]
+                     flops=recs[i].flops, ref_bytes=recs[i].ref_bytes) for i in range(min(n, cap))]
 
     def close(self) -> None:
         if getattr(self, "_graphs", None):

@@ -35,7 +35,7 @@ class GemmSegC(C.Structure):
 
 class OpProfileC(C.Structure):
     _fields_ = [("name", C.c_char * 96), ("kernel", C.c_char * 32), ("ms", C.c_float), ("bytes", C.c_double),
-                ("flops", C.c_double)]
+                ("flops", C.c_double), ("ref_bytes", C.c_double)]
 
 
 # name -> (restype, argtypes); also the list tests check against include/lcm_unet.h

@@ -214,8 +214,10 @@ typedef struct {
   char name[96];
   char kernel[32];
   float ms;
-  double bytes;   /* algorithmic */
+  double bytes;   /* algorithmic bytes of the kernels this op launches */
   double flops;
+  double ref_bytes; /* the same under SURVEY 8(d) accounting: what the reference's op sequence moves for this op (>= bytes where a
+                     * fusion keeps a tensor on chip: xstats carries the expand op's bytes, xdw_fused the depthwise op's) */
 } lcm_op_profile;
 int lcm_plan_profile_forward(lcm_plan* plan, const float* xa_dev, int ca, int64_t xa_batch_stride,
                              const float* xb_dev, int cb, int64_t xb_batch_stride, const int64_t* t_dev,

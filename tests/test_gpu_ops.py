@@ -215,7 +215,8 @@ def test_xdw_fused(N, H, W, Ks, Nc):
 GEMM_F16_CASES = [  # (images, P, [K...], [segment is fp16], Nc, modes, out_f16)
     (2, 256, [32], [False], 128, [2], True),                 # expand: bf16 in, fp16 hidden out
     (3, 64, [64, 32], [False, False], 384, [2, 2], True),
-    (3, 256, [128, 32], [True, False], 32, [4, 0], False),   # project: fp16 hidden (SE-gated, folded into weights) + bf16 residual
+    (3, 256, [128, 32], [True, False], 32, [4, 0], False),   # project: fp16 hidden (SE-gated) + bf16 residual — the level-0 shape runs on proj_stream.cu
+    (7, 4096, [128, 32], [True, False], 32, [4, 0], False),  # same shape, more tiles than warps: tile rings wrap, CTA ranges straddle images
     (2, 384, [384, 64, 32], [True, False, False], 32, [4, 0, 0], False),
     (2, 64, [128, 32], [True, False], 64, [4, 0], False),    # tile spans images -> A-side gating of the fp16 operand
     (2, 128, [1024, 256], [True, False], 256, [4, 0], False),
