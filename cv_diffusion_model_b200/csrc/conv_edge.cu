@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restr
   pdl_wait();
   pdl_trigger();
   // CoT = total output channels; blockIdx.z = image * nblk + channel block (CO channels each: 48 = 3 x 16, 64 = 2 x 32)
-  constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 4;   // smem row: 34 used columns, padded to 36
+  // smem row: pixel x0 + j sits at column j + 4 (the 32 interior floats are 16-byte aligned: one 16-byte cp.async per four
+  // pixels), left / right halo at columns 3 / 36
+  constexpr int TW = 32, TH = 8, ROWS = 64, SW_ = TW + 8;
   constexpr int CH_PITCH = (TH + 2) * SW_;                  // floats per input channel plane
   constexpr int NT = CO / 8, KS = 5, PPITCH = CO * 2 + 16;  // n-tiles, max K steps, output patch row pitch (bytes)
   __shared__ __align__(16) float in_s[2][8 * CH_PITCH];     // double-buffered fp32 halo tile, filled with cp.async
@@ -56,7 +58,33 @@ __global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int n = blockIdx.z / nblk, co0 = (blockIdx.z % nblk) * CO, x0 = blockIdx.x * TW, yb = blockIdx.y * ROWS;
   const int yend = min(yb + ROWS, H);
+  const bool wide = (W % 32 == 0) && ((sa | sb) % 4 == 0) &&   // full-width tiles, 16-byte aligned rows
+                    ((reinterpret_cast<uintptr_t>(xa) | reinterpret_cast<uintptr_t>(xb)) % 16 == 0);
   auto stage = [&](int y0, int buf) {
+    if (wide) {
+      // 10 copies per tile line: 8 x 16 bytes (interior) + the two halo pixels.  The element-wise version below issued 34
+      // 4-byte copies per line and its address arithmetic was 45 % of the kernel's instructions (ncu source view).
+      for (int u = tid; u < Cin * (TH + 2) * 10; u += 128) {
+        const int line = u / 10, part = u - line * 10;
+        const int ci = line / (TH + 2), r = line - ci * (TH + 2);
+        const int gy = y0 + r - 1;
+        const bool yok = gy >= 0 && gy < H;
+        const float* row = (ci < ca ? xa + n * sa + ((long long)ci * H + (yok ? gy : 0)) * W
+                                    : xb + n * sb + ((long long)(ci - ca) * H + (yok ? gy : 0)) * W);
+        float* drow = &in_s[buf][ci * CH_PITCH + r * SW_];
+        if (part < 8) {
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(drow + 4 + part * 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(row + x0 + part * 4), "r"(yok ? 16 : 0) : "memory");
+        } else {
+          const int gx = part == 8 ? x0 - 1 : x0 + TW;
+          const bool ok = yok && gx >= 0 && gx < W;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(drow + (part == 8 ? 3 : TW + 4));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(row + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
     for (int line = tid >> 5; line < Cin * (TH + 2); line += 4) {
       const int ci = line / (TH + 2), r = line - ci * (TH + 2);
       const int gy = y0 + r - 1;
@@ -66,7 +94,7 @@ __global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restr
       for (int c = tid & 31; c < TW + 2; c += 32) {
         const int gx = x0 + c - 1;
         const bool ok = yok && gx >= 0 && gx < W;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&in_s[buf][ci * CH_PITCH + r * SW_ + c]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&in_s[buf][ci * CH_PITCH + r * SW_ + c + 3]);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
       }
     }
@@ -82,7 +110,7 @@ __global__ void __launch_bounds__(128) init_conv_mma_kernel(const float* __restr
     for (int q = 0; q < 4; ++q) {
       const int k = ks * 16 + 2 * t + (q & 1) + (q >> 1) * 8;
       const int tap = k / Cin, ci = k - tap * Cin;
-      koff[ks][q] = k < K ? ci * CH_PITCH + (tap / 3) * SW_ + tap % 3 : 0;
+      koff[ks][q] = k < K ? ci * CH_PITCH + (tap / 3) * SW_ + tap % 3 + 3 : 3;
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
