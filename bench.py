@@ -143,7 +143,7 @@ OTHER = {
 
 
 def other_configs_leg(dev, world, rank, timed, hbm_gbs):
-    """Bounded runs (1 warm-up + 2 timed enhance calls) of BASELINE configs 3 and 4 at their per-GPU shapes, and one
+    """Bounded runs (3 warm-up + 2 timed enhance calls) of BASELINE configs 3 and 4 at their per-GPU shapes, and one
     data-parallel training step config (config 5) — so that these get driver-side numbers too."""
     import torch
     from cv_diffusion_model_b200 import LowLightDiffusion
@@ -159,7 +159,8 @@ def other_configs_leg(dev, world, rank, timed, hbm_gbs):
         lat0 = torch.randn(B, 3, S, S, generator=g).to(dev)
         noises = torch.randn(c["steps"] - 1, B, 3, S, S, generator=g).to(dev)
         fn = lambda: pipe.enhance(low, latents=lat0, noises=noises)
-        fn()
+        for _ in range(3):   # the third call with one schedule captures the loop as a CUDA graph (engine.py): keep that out of the timing
+            fn()
         n = 2
         ms = timed(fn, n)
         eng = get_engine(pipe.unet, B, S, S, dev)
