@@ -197,9 +197,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
         w6[t][0] = __floats2half2_rn(6.f * wv.x, 6.f * wv.y);
         w6[t][1] = __floats2half2_rn(6.f * wv.z, 6.f * wv.w);
       }
-      uint32_t zmask = 0;
-#pragma unroll
-      for (int i = 0; i < kPxS + 2; ++i) { const int x = xs - 1 + i; if (x < 0 || x >= p.W) zmask |= 1u << i; }
+      // (no padding mask here: band pixels are always inside the image (W % 64 == 0) and the EPI warps write ZEROS into the halo
+      //  buffer for a neighbour column outside it, so the zero padding after the activation costs this role nothing)
 
       waitf(hfull_bar(hb), (uint32_t)(k >> 1) & 1u);     // the item's halo columns are in place
 
@@ -230,11 +229,6 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(sempty_bar(slot));
         if (++slot == p.ring) { slot = 0; sphase ^= 1u; }
-        if (zmask) {
-#pragma unroll
-          for (int i = 0; i < kPxS + 2; ++i)
-            if (zmask & (1u << i)) r[i][0] = r[i][1] = hz;
-        }
       };
 
       float psum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -297,13 +291,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       for (int tl = 0; tl < ntiles; ++tl, ++tcount) {
         const int acc = tcount & 1;
         // destination of this thread's pixel (128 channels = 256 bytes)
-        uint32_t dst; bool swz; int px = 0; bool valid; int sl = -1;
+        uint32_t dst; bool swz; int px = 0; bool valid; int sl = -1; bool hzero = false;
         if (tl == 0) {
           waitf(hempty_bar(hb), ((uint32_t)(k >> 1) & 1u) ^ 1u);
           const int side = et >> 6, hr = et & 63;
           dst = sbase + p.halo_off + (uint32_t)hb * p.halo_bytes + (uint32_t)hr * kHaloRowF + (uint32_t)side * 256u;
           swz = false;
           valid = hr < p.hseg + 2;
+          hzero = side == 0 ? q.bx == 0 : q.bx == p.bandsX - 1;   // that neighbour column is outside the image: zero padding
         } else {
           const int j = tl - 1;
           const int ra = y0 - 1 + 2 * j, rbw = ra + 1;
@@ -339,6 +334,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
               v.y = as_u32f(__hfma2_sat(as_h2f(a4.y), as_h2f(pack_f16(__uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]))), as_h2f(b4.y)));
               v.z = as_u32f(__hfma2_sat(as_h2f(a4.z), as_h2f(pack_f16(__uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]))), as_h2f(b4.z)));
               v.w = as_u32f(__hfma2_sat(as_h2f(a4.w), as_h2f(pack_f16(__uint_as_float(r[o + 6]), __uint_as_float(r[o + 7]))), as_h2f(b4.w)));
+              if (hzero) v = make_uint4(0u, 0u, 0u, 0u);
               const uint32_t uu = swz ? (uint32_t)(unit ^ (px & 7)) : (uint32_t)unit;
               sts128(dst + (uu << 4), v);
             }
