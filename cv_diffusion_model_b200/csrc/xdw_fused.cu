@@ -129,14 +129,18 @@ __device__ __forceinline__ void emit_row_f(const RowF& r0, const RowF& r1, const
   psum[0] += f0.x; psum[1] += f0.y; psum[2] += f1.x; psum[3] += f1.y;
 }
 
+// kDbg: the LCM_XDW_DBG / LCM_XDW_SPIN experiment switches are compiled into a second instantiation only (the row loop of the conv
+// role pays for every instruction)
+template <bool kDbg>
 __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_constant__ FParams p) {
   extern __shared__ uint8_t fsm_raw2[];
   const uint32_t sraw = smem_u32(fsm_raw2);
   const uint32_t sbase = (sraw + 1023u) & ~1023u;
   uint8_t* smem = fsm_raw2 + (sbase - sraw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool spin = p.spin != 0;
-  auto waitf = [&](uint32_t bar, uint32_t parity) { waitf_impl(bar, parity, spin); };
+  const bool spin = kDbg && p.spin != 0;
+  const int dbg = kDbg ? p.dbg : 0;
+  auto waitf = [&](uint32_t bar, uint32_t parity) { if (kDbg) waitf_impl(bar, parity, spin); else mbar_wait_relaxed(bar, parity); };
 
   const uint32_t bar0 = sbase + p.misc_off;
   auto raw_bar = [&](int s) { return bar0 + 8u * s; };                 // TMA -> MMA          (stages)
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       __half* orow = p.out + (((size_t)q.n * p.H + y0) * p.W + xs) * p.Ch + c;
       const size_t ostep = (size_t)p.W * p.Ch;
       auto emit = [&](const RowF& r0, const RowF& r1, const RowF& r2) {   // (W % 64 == 0: a strip is never ragged)
-        if (!(p.dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, p.Ch, kPxS, psum);
+        if (!(dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, p.Ch, kPxS, psum);
         orow += ostep;
       };
       for (int y = y0; y < y1; y += 3) {
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
         const uint32_t taddr = lane_base + (uint32_t)acc * 128u;
         // 32 columns per step; the load of step i + 1 is in flight while step i is converted and stored
         auto emit32 = [&](const uint32_t (&r0)[16], const uint32_t (&r1)[16], int cb) {
-          if (valid && !(p.dbg & 2)) {
+          if (valid && !(dbg & 2)) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const uint32_t* r = u < 2 ? r0 : r1;
@@ -544,9 +548,14 @@ int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2
   if (total > kSmemLimitF) return -1;
   { static int d = -1; if (d < 0) { const char* e = getenv("LCM_XDW_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
   { static int sp = -1; if (sp < 0) { const char* e = getenv("LCM_XDW_SPIN"); sp = (e && atoi(e)) ? 1 : 0; } p.spin = sp; }
-  if (ensure_dyn_smem_fn(xdw_fused_kernel, kSmemLimitF)) return -2;
   const int grid = p.items < num_sms ? p.items : num_sms;
-  launch_pdl(xdw_fused_kernel, dim3(grid), dim3(kThreadsF), total, st, p);
+  if (p.dbg || p.spin) {
+    if (ensure_dyn_smem_fn(xdw_fused_kernel<true>, kSmemLimitF)) return -2;
+    launch_pdl(xdw_fused_kernel<true>, dim3(grid), dim3(kThreadsF), total, st, p);
+  } else {
+    if (ensure_dyn_smem_fn(xdw_fused_kernel<false>, kSmemLimitF)) return -2;
+    launch_pdl(xdw_fused_kernel<false>, dim3(grid), dim3(kThreadsF), total, st, p);
+  }
   return 0;
 }
 
