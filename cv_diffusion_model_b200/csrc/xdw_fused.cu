@@ -131,7 +131,9 @@ __device__ __forceinline__ void emit_row_f(const RowF& r0, const RowF& r1, const
 
 // kDbg: the LCM_XDW_DBG / LCM_XDW_SPIN experiment switches are compiled into a second instantiation only (the row loop of the conv
 // role pays for every instruction)
-template <bool kDbg>
+// kCh: the hidden width as a compile-time constant (0 = p.Ch): the eight h2 stores of a row get immediate offsets instead of an
+// IMAD.WIDE each — on the pipe the HFMA2s need
+template <bool kDbg, int kCh>
 __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_constant__ FParams p) {
   extern __shared__ uint8_t fsm_raw2[];
   const uint32_t sraw = smem_u32(fsm_raw2);
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       __half* orow = p.out + (((size_t)q.n * p.H + y0) * p.W + xs) * p.Ch + c;
       const size_t ostep = (size_t)p.W * p.Ch;
       auto emit = [&](const RowF& r0, const RowF& r1, const RowF& r2) {   // (W % 64 == 0: a strip is never ragged)
-        if (!(dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, p.Ch, kPxS, psum);
+        if (!(dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, kCh ? kCh : p.Ch, kPxS, psum);
         orow += ostep;
       };
       for (int y = y0; y < y1; y += 3) {
@@ -549,14 +551,18 @@ int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2
   { static int d = -1; if (d < 0) { const char* e = getenv("LCM_XDW_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
   { static int sp = -1; if (sp < 0) { const char* e = getenv("LCM_XDW_SPIN"); sp = (e && atoi(e)) ? 1 : 0; } p.spin = sp; }
   const int grid = p.items < num_sms ? p.items : num_sms;
-  if (p.dbg || p.spin) {
-    if (ensure_dyn_smem_fn(xdw_fused_kernel<true>, kSmemLimitF)) return -2;
-    launch_pdl(xdw_fused_kernel<true>, dim3(grid), dim3(kThreadsF), total, st, p);
-  } else {
-    if (ensure_dyn_smem_fn(xdw_fused_kernel<false>, kSmemLimitF)) return -2;
-    launch_pdl(xdw_fused_kernel<false>, dim3(grid), dim3(kThreadsF), total, st, p);
+  auto go = [&](auto kfn) -> int {
+    if (ensure_dyn_smem_fn(kfn, kSmemLimitF)) return -2;
+    launch_pdl(kfn, dim3(grid), dim3(kThreadsF), total, st, p);
+    return 0;
+  };
+  if (p.dbg || p.spin) return go(xdw_fused_kernel<true, 0>);
+  switch (Nc) {
+    case 128: return go(xdw_fused_kernel<false, 128>);
+    case 256: return go(xdw_fused_kernel<false, 256>);
+    case 384: return go(xdw_fused_kernel<false, 384>);
+    default: return go(xdw_fused_kernel<false, 0>);
   }
-  return 0;
 }
 
 }  // namespace lcm
