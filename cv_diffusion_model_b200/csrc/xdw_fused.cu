@@ -85,6 +85,16 @@ __device__ __forceinline__ uint2 lds64f(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
   return v;
 }
+template <int OFF>
+__device__ __forceinline__ uint2 lds64f_imm(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int I>
+__device__ __forceinline__ uint2 lds_px(uint32_t rw, const uint32_t (&xo)[8]) {   // window pixel I of a strip: band pixel strip * 8 - 1 + I
+  return lds64f_imm<(I - 1) * 256>(rw + xo[(I + 7) & 7]);
+}
 __device__ __forceinline__ __half2 as_h2f(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t as_u32f(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -187,6 +197,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
     int slot = 0; uint32_t sphase = 0;
     const __half2 hz = __float2half2_rn(0.f);
     const uint32_t ux = (uint32_t)(lane >> 1) << 4, hoff = (uint32_t)(lane & 1) * 8u;
+    // unit (lane >> 1) of a pixel sits at unit ^ (pixel & 7): the eight XOR patterns of this lane, kept in registers so that a row's
+    // ten loads are one add + an immediate pixel offset each
+    uint32_t xo[8];
+#pragma unroll
+    for (int sx = 0; sx < 8; ++sx) xo[sx] = (ux ^ ((uint32_t)sx << 4)) + hoff + (uint32_t)(strip * kPxS) * 256u;
     int k = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++k) {
       const ItemF q = decode_f(item, p);
@@ -217,19 +232,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
           return;
         }
         waitf(sfull_bar(slot), sphase);
-        const uint32_t rowb = sbase + p.ring_off + (uint32_t)slot * kSlotF + hoff;
+        const uint32_t rw = sbase + p.ring_off + (uint32_t)slot * kSlotF;
         const uint32_t hrow = halo + (uint32_t)(y - (y0 - 1)) * kHaloRowF;
         uint2 v[kPxS + 2];
-#pragma unroll
-        for (int i = 0; i < kPxS + 2; ++i) {
-          if (i == 0 && strip == 0) v[i] = lds64f(hrow);                       // left neighbour column
-          else if (i == kPxS + 1 && strip == kConvWarps - 1) v[i] = lds64f(hrow + 256u);   // right neighbour column
-          else {
-            // band pixel pb = strip * kPxS - 1 + i; unit (lane >> 1) of pixel pb sits at unit ^ (pb & 7)
-            const uint32_t pb = (uint32_t)(strip * kPxS - 1 + i);
-            v[i] = lds64f(rowb + pb * 256u + (ux ^ ((pb & 7u) << 4)));
-          }
-        }
+        v[0] = strip == 0 ? lds64f(hrow) : lds_px<0>(rw, xo);                                 // left neighbour column from the halo buffer
+        v[1] = lds_px<1>(rw, xo); v[2] = lds_px<2>(rw, xo); v[3] = lds_px<3>(rw, xo); v[4] = lds_px<4>(rw, xo);
+        v[5] = lds_px<5>(rw, xo); v[6] = lds_px<6>(rw, xo); v[7] = lds_px<7>(rw, xo); v[8] = lds_px<8>(rw, xo);
+        v[9] = strip == kConvWarps - 1 ? lds64f(hrow + 256u) : lds_px<9>(rw, xo);             // right neighbour column
 #pragma unroll
         for (int i = 0; i < kPxS + 2; ++i) { r[i][0] = as_h2f(v[i].x); r[i][1] = as_h2f(v[i].y); }
         __syncwarp();
