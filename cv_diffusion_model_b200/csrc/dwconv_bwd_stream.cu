@@ -226,9 +226,14 @@ __global__ void __launch_bounds__(STRIPS * 32, 512 / (STRIPS * 32)) dwconv_bwd_s
       ++consumed;
       if (++slot == p.ring) { slot = 0; phase ^= 1u; }
       if (zmask) {
+        if ((zmask & 0x1feu) == 0) {   // the usual case (W % 8 == 0): only a neighbour column can lie outside the image
+          if (zmask & 1u) r[0] = hz;
+          if (zmask & 0x200u) r[9] = hz;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 10; ++i)
-          if (zmask & (1u << i)) r[i] = hz;
+          for (int i = 0; i < 10; ++i)
+            if (zmask & (1u << i)) r[i] = hz;
+        }
       }
       return got;
     };
