@@ -38,6 +38,7 @@ struct XsParams {
   double* colsum;
   int P;            // pixels per image
   long long tiles;  // team tiles in total
+  int prefetch;     // pull the warp's next pixel tile towards L2 while the Gram update of this one runs
 };
 
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
@@ -191,6 +192,16 @@ __device__ __forceinline__ void xstats_body(const XsParams& p, double* gs, doubl
       if (lane_on) {
 #pragma unroll
         for (int i = 0; i < U; ++i) v[i] = *reinterpret_cast<const uint4*>(lsrc + (size_t)(px0 + i * PPP + lpx) * lK);
+      }
+      // The loads of a warp are in flight for only part of an iteration (transform, stores, team barriers and the Gram MMAs
+      // follow), so the DRAM latency of its NEXT tile is started now: one bulk L2 prefetch per segment (contiguous WPX pixels)
+      const long long nt = end + team + (long long)(p.prefetch - 1) * TEAMS;
+      if (p.prefetch && lane < p.nseg && nt < te) {
+        const int sk = lane ? p.segK[1] : p.segK[0];
+        const bf16* nx = (lane ? p.x[1] : p.x[0]) + (size_t)(nt * TP + (long long)gw * WPX) * sk;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((uint32_t)(WPX * 2) * (uint32_t)sk) : "memory");
+      }
+      if (lane_on) {
 #pragma unroll
         for (int i = 0; i < U; ++i) {
           const int px = i * PPP + lpx;
@@ -244,6 +255,9 @@ template <int KT, int GROUP, int KSW>
 int launch_one(const XsParams& p0, long long M, int num_sms, cudaStream_t st) {
   constexpr int K = KT * 16, TP = 16 * KSW * GROUP, TEAMS = kXsWarps / GROUP;
   XsParams p = p0;
+  static int pf = -1;
+  if (pf < 0) { const char* e = getenv("LCM_XS_PREFETCH"); pf = e ? atoi(e) : 1; }
+  p.prefetch = pf;
   if (p.P % TP) return -1;
   p.tiles = M / TP;
   const size_t smem = (size_t)(K * (K + 1) + K) * 8 + (size_t)TEAMS * TP * (K * 2 + 16);
