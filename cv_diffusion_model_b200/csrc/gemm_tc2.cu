@@ -75,6 +75,7 @@ struct alignas(64) Tc2Params {
                           // (achunks = activation stages per tile; the weight chunks stay per (tap, chunk))
   uint32_t stage_bytes, bres_off, stg_off, stg_stride, stg_bytes, coef_off, misc_off;
   int debug;
+  int prefetch;   // L2 prefetch distance of the activation chunks (0 = off): set when the ring is shorter than a tile
   uint32_t chunk[kMaxChunks2];  // seg/tap (7 bits) | fp16 segment << 7 | kvalid << 8 | c0 << 16
   uint8_t lo_slot[kMaxChunks2]; // wgate: index (after the nchunks weight chunks) of the chunk's low-order weight image, or 0xff
 };
@@ -445,6 +446,19 @@ __global__ void __launch_bounds__(kThreads2, 1) gemm_tc2_kernel(const __grid_con
                 tma_load_4d(a_smem, &p.tmap[0], (int)(cd >> 16), p.conv_stride * tx0 + kx - 1, p.conv_stride * ty0 + ky - 1, ti.img, raw_bar(stage));
               } else {
                 tma_load_2d(a_smem, &p.tmap[cd & 0x7f], (int)(cd >> 16), ti.m0, raw_bar(stage));
+                if (p.prefetch) {
+                  // rings of 2-3 stages (K >= 640) cannot hide the DRAM latency of a 16 KB activation chunk: ask L2 for the
+                  // chunk `prefetch` positions ahead (same tile, or the next tile of this CTA in the same n row)
+                  int pc = ci + p.prefetch, pm0 = ti.m0;
+                  bool ok = true;
+                  if (pc >= p.achunks) { pc -= p.achunks; pm0 += 128 * ti.step; ok = it + 1 < my_tiles && ti.m_tile + ti.step < m_tiles && pc < p.achunks; }
+                  if (ok) {
+                    const uint32_t pd = p.chunk[pc];
+                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(&p.tmap[pd & 0x7f])),
+                                 "r"((int)(pd >> 16)), "r"(pm0)
+                                 : "memory");
+                  }
+                }
               }
             }
             if (!p.resident) {
@@ -936,6 +950,14 @@ int launch_gemm_tc(const GemmParams& g, const ConvGeom& cg, int block_n, int num
   if (stages > max_stages) stages = max_stages;
   if (stages < 2) return -1;
   p.stages = stages;
+  {
+    // LCM_TC_PREFETCH: chunks ahead (0 = off).  Same-box sweep on the model: 4 -> 2.97 ms over the 21 launches, 8 -> 3.00, 0 -> 3.03,
+    // 16 -> 3.12; nearly all of it is the K = 768 + 192 project of the 128^2 level (0.398 -> 0.351 ms).  The same prefetch one tile
+    // ahead in gemm_wide (whose activation ring already spans a tile) measured 1 % slower and is not in that kernel.
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("LCM_TC_PREFETCH"); pf = e ? atoi(e) : 4; }
+    p.prefetch = (p.conv_mode < 0 && !p.conv_tma && !p.conv_halo && p.achunks > stages) ? pf : 0;
+  }
   uint32_t off = (uint32_t)stages * p.stage_bytes;
   p.bres_off = off; off += p.resident ? bres : 0u;
   p.stg_off = off; off += (uint32_t)p.nbuf * stg_bytes;
