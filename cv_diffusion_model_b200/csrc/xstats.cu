@@ -165,10 +165,15 @@ __device__ __forceinline__ void xstats_body(const XsParams& p, double* gs, doubl
     bar_sync(0, kXsWarps * 32);
   };
 
+  // loop invariants of the L2 prefetch (kernel parameters indexed by lane: read once, not per iteration)
+  const bf16* pf_src = lane ? p.x[1] : p.x[0];
+  const int pf_sk = lane ? p.segK[1] : p.segK[0];
+  const bool pf_on = p.prefetch && lane < p.nseg;
+  int img = (int)(tb / tiles_per_img);                         // image of `base`, tracked incrementally (no division per round)
+  long long img_end = (long long)(img + 1) * tiles_per_img;
   for (long long base = tb; base < te;) {
-    const int img = (int)(base / tiles_per_img);
+    if (base >= img_end) { ++img; img_end += tiles_per_img; }   // a round never crosses an image boundary
     long long end = base + TEAMS;
-    const long long img_end = (long long)(img + 1) * tiles_per_img;
     if (end > img_end) end = img_end;
     if (end > te) end = te;
     if (img != cur_img) {
@@ -196,10 +201,9 @@ __device__ __forceinline__ void xstats_body(const XsParams& p, double* gs, doubl
       // The loads of a warp are in flight for only part of an iteration (transform, stores, team barriers and the Gram MMAs
       // follow), so the DRAM latency of its NEXT tile is started now: one bulk L2 prefetch per segment (contiguous WPX pixels)
       const long long nt = end + team + (long long)(p.prefetch - 1) * TEAMS;
-      if (p.prefetch && lane < p.nseg && nt < te) {
-        const int sk = lane ? p.segK[1] : p.segK[0];
-        const bf16* nx = (lane ? p.x[1] : p.x[0]) + (size_t)(nt * TP + (long long)gw * WPX) * sk;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((uint32_t)(WPX * 2) * (uint32_t)sk) : "memory");
+      if (pf_on && nt < te) {
+        const bf16* nx = pf_src + (size_t)(nt * TP + (long long)gw * WPX) * pf_sk;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((uint32_t)(WPX * 2) * (uint32_t)pf_sk) : "memory");
       }
       if (lane_on) {
 #pragma unroll
