@@ -119,7 +119,7 @@ __device__ __forceinline__ void gram_flush(float (&acc)[mask_tiles<KT, MASK>()][
 
 template <int KT, int GROUP> struct Masks;
 template <int KT> struct Masks<KT, 1> { static constexpr uint32_t m[4] = {(1u << KT) - 1u, 0, 0, 0}; };
-template <> struct Masks<4, 2> { static constexpr uint32_t m[4] = {0x1, 0xe, 0, 0}; };              // 9 | 7 + 5 + 3 tiles
+template <> struct Masks<4, 2> { static constexpr uint32_t m[4] = {0x9, 0x6, 0, 0}; };              // 9 + 3 | 7 + 5 tiles
 template <> struct Masks<5, 4> { static constexpr uint32_t m[4] = {0x1, 0x2, 0x4, 0x18}; };
 template <> struct Masks<6, 4> { static constexpr uint32_t m[4] = {0x1, 0x2, 0x24, 0x18}; };         // 13 | 11 | 9 + 3 | 7 + 5
 
