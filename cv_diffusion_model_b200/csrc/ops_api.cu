@@ -188,15 +188,16 @@ int lcm_op_xdw(const lcm_gemm_seg* segs, int nseg, const float* w_dev, const voi
     Kt += segs[i].K;
   }
   gp.nseg = nseg; gp.P = H * W; gp.M = (long long)N * H * W;
-  if (Kt % 16 || Kt > 128 || !xstats_supported(Kt, H * W) || Nc % 128 || W % 64 || H % 2) return LCM_ERR_INVALID;
+  if (Kt % 16 || Kt > 128 || !xstats_supported(Kt, H * W) || Nc % 64 || Nc < 128 || W % 64 || H % 2) return LCM_ERR_INVALID;
   const int Kpad = (Kt + 63) / 64 * 64;
+  const int Npad = (Nc + 127) / 128 * 128;   // n-blocks of 128 rows, the last one zero-padded
   void* wbuf = nullptr; float* dwbuf = nullptr; void* scratch = nullptr;
-  if (cudaMalloc(&wbuf, (size_t)Nc * Kpad * 2) != cudaSuccess || cudaMalloc((void**)&dwbuf, (size_t)9 * Nc * 4) != cudaSuccess ||
+  if (cudaMalloc(&wbuf, (size_t)Npad * Kpad * 2) != cudaSuccess || cudaMalloc((void**)&dwbuf, (size_t)9 * Nc * 4) != cudaSuccess ||
       cudaMalloc(&scratch, gemm_expand_scratch_bytes(N)) != cudaSuccess) {
     cudaFree(wbuf); cudaFree(dwbuf); cudaFree(scratch);
     return LCM_ERR_CUDA;
   }
-  cudaMemsetAsync(wbuf, 0, (size_t)Nc * Kpad * 2, st);
+  cudaMemsetAsync(wbuf, 0, (size_t)Npad * Kpad * 2, st);
   {
     PackJob j{};
     j.kind = PACK_MAT; j.layout = WL_UMMA; j.bf16 = 1; j.dst = wbuf; j.R = Nc; j.Cc = Kt; j.src_ld = Kt; j.src_col0 = 0; j.ld = Kpad; j.off = 0;

@@ -383,7 +383,8 @@ struct Builder {
     p->ops.push_back(std::move(o));
   }
 
-  GemmW make_w(int Nc, const std::vector<int>& segK, int expand_P = 0) {
+  // fused_layout: the weights of the fused expand -> depthwise kernel (n-blocks of 128 rows, the last one zero-padded)
+  GemmW make_w(int Nc, const std::vector<int>& segK, int expand_P = 0, bool fused_layout = false) {
     GemmW g;
     g.Nc = Nc;
     g.expand = p->tc && expand_P > 0 && gemm_expand_supported((int)segK.size(), segK.data(), Nc, expand_P);
@@ -395,7 +396,10 @@ struct Builder {
       g.Ktot += k;
       g.Kpad += (k + 63) / 64 * 64;
     }
-    if (p->tc) { g.block_n = (g.expand || g.wide) ? 128 : gemm_tc_pick_block_n(Nc); g.off = p->walloc((size_t)Nc * g.Kpad * sizeof(bf16)); }
+    if (p->tc) {
+      g.block_n = (g.expand || g.wide || fused_layout) ? 128 : gemm_tc_pick_block_n(Nc);
+      g.off = p->walloc((size_t)(fused_layout ? (Nc + 127) / 128 * 128 : Nc) * g.Kpad * sizeof(bf16));
+    }
     else g.off = p->walloc((size_t)Nc * g.Ktot * p->esz);
     return g;
   }
@@ -502,10 +506,13 @@ struct Builder {
       }
       // Inference plans fuse expand -> norm2 / FiLM / ReLU6 -> depthwise into ONE kernel where the expand kernel applies
       // (xdw_fused.cu): h1 is never materialised; its statistics come from a pass over the block input alone.
-      fused = p->tc && !p->train && !p->taps && we.expand && xdw_fused_supported((int)segK.size(), segK.data(), Ch, h, w);
+      // (hidden widths of 128 m + 64 channels — the Base variant's 192 — are not the expand kernel's, but the fused kernel masks
+      //  the half-empty last n-block)
+      fused = p->tc && !p->train && !p->taps && (we.expand || (Ch % 128 == 64 && Ci <= 128)) &&
+              xdw_fused_supported((int)segK.size(), segK.data(), Ch, h, w);
       if (fused) {
         // the weights once more, packed as ONE dense K segment (t concatenates the input parts)
-        xw = make_w(Ch, std::vector<int>{Ci}, h * w);
+        xw = make_w(Ch, std::vector<int>{Ci}, h * w, true);
         p->add_weight(name + ".expand.weight", (int64_t)Ch * Ci, mat_job(xw, 0, PACK_MAT, Ch, Ci, Ci, 0));
         xt = p->new_tensor(Ci, h, w, false, "", false);
         lcm_plan* pl = p; const int n = N;

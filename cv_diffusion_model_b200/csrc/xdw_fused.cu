@@ -115,9 +115,11 @@ __device__ __forceinline__ ItemF decode_f(int item, const FParams& p) {
 
 typedef __half2 RowF[kPxS + 2][2];
 
-template <bool kRagged>
+// kPartial: the hidden width is not a multiple of 128 — lanes whose four channels lie beyond it (cvalid false) compute on zeros
+// and skip their stores
+template <bool kRagged, bool kPartial = false>
 __device__ __forceinline__ void emit_row_f(const RowF& r0, const RowF& r1, const RowF& r2, const __half2 (&w6)[9][2], __half* orow, int C,
-                                           int nvalid, float (&psum)[4]) {
+                                           int nvalid, float (&psum)[4], bool cvalid = true) {
   __half2 s0 = __float2half2_rn(0.f), s1 = s0;
 #pragma unroll
   for (int px = 0; px < kPxS; ++px) {
@@ -131,7 +133,7 @@ __device__ __forceinline__ void emit_row_f(const RowF& r0, const RowF& r1, const
     a0 = __hfma2(r2[px + 1][0], w6[7][0], a0); a1 = __hfma2(r2[px + 1][1], w6[7][1], a1);
     a0 = __hfma2(r2[px + 2][0], w6[8][0], a0); a1 = __hfma2(r2[px + 2][1], w6[8][1], a1);
     if (!kRagged || px < nvalid) {
-      *reinterpret_cast<uint2*>(orow + (size_t)px * C) = make_uint2(as_u32f(a0), as_u32f(a1));
+      if (!kPartial || cvalid) *reinterpret_cast<uint2*>(orow + (size_t)px * C) = make_uint2(as_u32f(a0), as_u32f(a1));
       s0 = __hadd2(s0, a0); s1 = __hadd2(s1, a1);
     }
   }
@@ -152,6 +154,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool spin = kDbg && p.spin != 0;
   const int dbg = kDbg ? p.dbg : 0;
+  // hidden widths that are not a multiple of the 128-channel n-block (Base variant: 192): the last block is half empty — its weight
+  // rows and coefficients are zero, its stores and pool sums masked.  Compile-time false for the widths of the Small / Large variants.
+  constexpr bool kPartial = kCh == 0 || (kCh % 128) != 0;
   auto waitf = [&](uint32_t bar, uint32_t parity) { if (kDbg) waitf_impl(bar, parity, spin); else mbar_wait_relaxed(bar, parity); };
 
   const uint32_t bar0 = sbase + p.misc_off;
@@ -211,10 +216,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       const int hb = k & 1;
       const uint32_t halo = sbase + p.halo_off + (uint32_t)hb * p.halo_bytes + (uint32_t)lane * 8u;
 
+      const bool cvalid = !kPartial || c < p.Ch;
       __half2 w6[9][2];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float4 wv = *reinterpret_cast<const float4*>(p.wdw + (size_t)t * p.Ch + c);
+        const float4 wv = cvalid ? *reinterpret_cast<const float4*>(p.wdw + (size_t)t * p.Ch + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         w6[t][0] = __floats2half2_rn(6.f * wv.x, 6.f * wv.y);
         w6[t][1] = __floats2half2_rn(6.f * wv.z, 6.f * wv.w);
       }
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       __half* orow = p.out + (((size_t)q.n * p.H + y0) * p.W + xs) * p.Ch + c;
       const size_t ostep = (size_t)p.W * p.Ch;
       auto emit = [&](const RowF& r0, const RowF& r1, const RowF& r2) {   // (W % 64 == 0: a strip is never ragged)
-        if (!(dbg & 1)) emit_row_f<false>(r0, r1, r2, w6, orow, kCh ? kCh : p.Ch, kPxS, psum);
+        if (!(dbg & 1)) emit_row_f<false, kPartial>(r0, r1, r2, w6, orow, kCh ? kCh : p.Ch, kPxS, psum, cvalid);
         orow += ostep;
       };
       for (int y = y0; y < y1; y += 3) {
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       float* red = s_red + hb * (kConvWarps * 128);
       *reinterpret_cast<float4*>(red + strip * 128 + lane * 4) = make_float4(psum[0], psum[1], psum[2], psum[3]);
       bar_sync(1, kConvWarps * 32);
-      if (tid < 128) {
+      if (tid < 128 && (!kPartial || q.nb * 128 + tid < p.Ch)) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kConvWarps; ++i) s += red[i * 128 + tid];
@@ -296,7 +302,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) xdw_fused_kernel(const __grid_co
       // a2/6, b2/6 of this (image, n-block) as half2 pairs
       bar_sync(2, 128);      // previous item's reads of s_ab2 are done
       if (et < 64) {
-        const float4 cf = *reinterpret_cast<const float4*>(p.coef2 + (size_t)q.n * p.Ch + q.nb * 128 + et * 2);
+        const float4 cf = (!kPartial || q.nb * 128 + et * 2 < p.Ch)
+                              ? *reinterpret_cast<const float4*>(p.coef2 + (size_t)q.n * p.Ch + q.nb * 128 + et * 2)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
         const __half2 a = __floats2half2_rn(cf.x * (1.f / 6.f), cf.z * (1.f / 6.f));
         const __half2 b = __floats2half2_rn(cf.y * (1.f / 6.f), cf.w * (1.f / 6.f));
         s_ab2[et] = as_u32f(a);
@@ -513,7 +521,7 @@ bool xdw_fused_supported(int nseg, const int* segK, int Nc, int H, int W) {
   // LCM_NO_XDW=1 falls back to the unfused kernel pair (A/B timing; tests/diag_xdw.py)
   static int off = -1;
   if (off < 0) { const char* e = getenv("LCM_NO_XDW"); off = (e && atoi(e)) ? 1 : 0; }
-  if (off || nseg < 1 || nseg > 2 || Nc % 128 || Nc < 128 || W % 64 || H % 2 || H < 2) return false;
+  if (off || nseg < 1 || nseg > 2 || Nc % 64 || Nc < 128 || W % 64 || H % 2 || H < 2) return false;
   int Kt = 0;
   for (int s = 0; s < nseg; ++s) {
     if (segK[s] % 16 || segK[s] < 16) return false;
@@ -527,7 +535,7 @@ bool xdw_fused_supported(int nseg, const int* segK, int Nc, int H, int W) {
 // out: h2 fp16 [N][H][W][Nc]; pool [N][Nc] fp64 (+=).
 int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2* coef2, const float* wdw, void* out, double* pool,
                      int N, int H, int Wd, int num_sms, cudaStream_t st) {
-  if (Kt % 16 || Kt < 16 || Kt > 128 || Nc % 128 || Nc < 128 || Wd % 64 || H % 2 || H < 2) return -1;
+  if (Kt % 16 || Kt < 16 || Kt > 128 || Nc % 64 || Nc < 128 || Wd % 64 || H % 2 || H < 2) return -1;
   FParams p;
   memset(&p, 0, sizeof(p));
   if (!x_map(t, N, H, Wd, Kt, 0, &p.tmap_main) || !x_map(t, N, H, Wd, Kt, 1, &p.tmap_halo)) return -3;
@@ -536,7 +544,7 @@ int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2
   p.nchunks = nch;
   p.Wp = reinterpret_cast<const bf16*>(Wp);
   p.coef2 = coef2; p.wdw = wdw; p.out = reinterpret_cast<__half*>(out); p.pool = pool;
-  p.N = N; p.H = H; p.W = Wd; p.Ch = Nc; p.NB = Nc / 128;
+  p.N = N; p.H = H; p.W = Wd; p.Ch = Nc; p.NB = (Nc + 127) / 128;
   p.hseg = pick_hseg(H);
   p.bandsX = Wd / 64;
   p.segsY = (H + p.hseg - 1) / p.hseg;
@@ -568,6 +576,7 @@ int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2
   if (p.dbg || p.spin) return go(xdw_fused_kernel<true, 0>);
   switch (Nc) {
     case 128: return go(xdw_fused_kernel<false, 128>);
+    case 192: return go(xdw_fused_kernel<false, 192>);
     case 256: return go(xdw_fused_kernel<false, 256>);
     case 384: return go(xdw_fused_kernel<false, 384>);
     default: return go(xdw_fused_kernel<false, 0>);

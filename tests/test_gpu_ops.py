@@ -176,6 +176,8 @@ XDW_CASES = [  # (N, H, W, [K...], Nc)
     (5, 128, 128, [32, 32], 128),
     (2, 34, 64, [16], 128),           # ragged row segments (H not a multiple of the segment height)
     (1, 64, 192, [48], 256),          # base-variant widths
+    (2, 64, 64, [48], 192),           # hidden width 128 + 64: the second n-block is half empty (masked stores / pool / coefficients)
+    (3, 32, 128, [48, 48], 192),
 ]
 
 
