@@ -228,7 +228,7 @@ __device__ __forceinline__ void xstats_body(const XsParams& p, double* gs, doubl
 }
 
 template <int KT, int GROUP, int KSW>
-__global__ void __launch_bounds__(kXsWarps * 32, KT <= 2 ? 3 : 2) xstats_kernel(const XsParams p) {
+__global__ void __launch_bounds__(kXsWarps * 32, KT <= 1 ? 3 : 2) xstats_kernel(const XsParams p) {
   constexpr int K = KT * 16, LD = K + 1, TP = 16 * KSW * GROUP;
   constexpr uint32_t PITCH = K * 2 + 16;
   extern __shared__ __align__(16) uint8_t xs_raw[];   // (K (K + 2) * 8 is a multiple of 16)
