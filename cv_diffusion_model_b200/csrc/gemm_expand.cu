@@ -460,11 +460,12 @@ __global__ void __launch_bounds__(128) expand_stats_kernel(const double* __restr
   float w[KW];
   {
     const int jb = n >> 7, r = n & 127;
+    constexpr int NCH = (KW + 63) / 64, UPC = KW >= 64 ? 8 : KW / 8;   // KW = 32: the first four units of the only chunk
 #pragma unroll
-    for (int c = 0; c < KW / 64; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const uint4* row = reinterpret_cast<const uint4*>(W + ((size_t)(jb * nchunks + c) * 128 + r) * 64);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < UPC; ++u) {
         const uint4 v = row[u ^ (r & 7)];   // logical unit u sits in slot u ^ (r & 7)
         float f[8];
         tc::unpack8(v, f);
@@ -583,14 +584,16 @@ size_t gemm_expand_scratch_bytes(int images) { return (size_t)images * (kGramLd 
 
 // (S, G) scratch -> (sum, sum^2) of the expand output; W packed as for gemm_expand with `nchunks` 64-wide K chunks per n-block
 // (the statistics pass of the fused expand -> depthwise path, xstats.cu, ends with this)
-int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st) {
+int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st, int Ktot) {
   if (nchunks < 1 || nchunks > 2 || Nc % 32) return -1;
   if (ensure_dyn_smem_fn(expand_stats_kernel<128>, (128 * 128 + 128 + 128 * 32 + 512) * 4) ||
       ensure_dyn_smem_fn(expand_stats_kernel<64>, (64 * 64 + 64 + 64 * 32 + 512) * 4)) return -2;
   const double* gram = reinterpret_cast<const double*>(scratch);
   const double* colsum = gram + (size_t)images * kGramLd * kGramLd;
   const dim3 sg(images, Nc / 32);
-  if (nchunks == 1)
+  if (nchunks == 1 && Ktot > 0 && Ktot <= 32)   // (the level-0 blocks: a quarter of the 64-wide instantiation's products)
+    launch_pdl(expand_stats_kernel<32>, sg, dim3(128), (size_t)(32 * 32 + 32 + 32 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
+  else if (nchunks == 1)
     launch_pdl(expand_stats_kernel<64>, sg, dim3(128), (size_t)(64 * 64 + 64 + 64 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
   else
     launch_pdl(expand_stats_kernel<128>, sg, dim3(128), (size_t)(128 * 128 + 128 + 128 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);

@@ -160,7 +160,7 @@ size_t gemm_expand_scratch_bytes(int images);   // Gram / column-sum scratch; mu
 //  launch_expand_stats_finalize turns those into the statistics of the expand output h1, which is never materialised)
 bool xstats_supported(int Ktot, int P);
 int launch_xstats(const GemmParams& g, void* t, void* scratch, int num_sms, cudaStream_t st);
-int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st);
+int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, int images, int Nc, int nchunks, cudaStream_t st, int Ktot = 0);
 bool xdw_fused_supported(int nseg, const int* segK, int Nc, int H, int W);
 int launch_xdw_fused(const void* t, int Kt, const void* Wp, int Nc, const float2* coef2, const float* wdw, void* out, double* pool,
                      int N, int H, int W, int num_sms, cudaStream_t st);

@@ -222,7 +222,7 @@ int lcm_op_xdw(const lcm_gemm_seg* segs, int nseg, const float* w_dev, const voi
       fprintf(stderr, "lcm_op_xdw: %s -> rc %d, %s\n", what, rc, cudaGetErrorString(e));
     };
     rc = launch_xstats(gp, t_dev, scratch, sms, st); stage("xstats");
-    if (!rc) { rc = launch_expand_stats_finalize(scratch, wbuf, stats_dev, N, Nc, Kpad / 64, st); stage("finalize"); }
+    if (!rc) { rc = launch_expand_stats_finalize(scratch, wbuf, stats_dev, N, Nc, Kpad / 64, st, Kt); stage("finalize"); }
     if (!rc) { rc = launch_xdw_fused(t_dev, Kt, wbuf, Nc, (const float2*)coef2_dev, dwbuf, out_dev, pool_dev, N, H, W, sms, st); stage("fused"); }
   }
   t.stop();

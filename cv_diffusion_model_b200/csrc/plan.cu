@@ -530,7 +530,7 @@ struct Builder {
           }
           gp.P = h * w; gp.M = (long long)n * gp.P;
           if (launch_xstats(gp, c.a + tt->off, c.z + xs, pl->num_sms, st) ||
-              launch_expand_stats_finalize(c.z + xs, pl->wbase + wv.off, (double*)(c.z + h1->stats_off), n, wv.Nc, (wv.Ktot + 63) / 64, st))
+              launch_expand_stats_finalize(c.z + xs, pl->wbase + wv.off, (double*)(c.z + h1->stats_off), n, wv.Nc, (wv.Ktot + 63) / 64, st, wv.Ktot))
             *c.launch_err = 1;
         }, (Ci + Ch) * N * P * es + (double)Ci * Ch * es);
         p->ops.back().launches = 2;
