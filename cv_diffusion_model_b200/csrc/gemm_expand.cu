@@ -460,12 +460,13 @@ __global__ void __launch_bounds__(128) expand_stats_kernel(const double* __restr
   float w[KW];
   {
     const int jb = n >> 7, r = n & 127;
-    constexpr int NCH = (KW + 63) / 64, UPC = KW >= 64 ? 8 : KW / 8;   // KW = 32: the first four units of the only chunk
+    constexpr int NCH = (KW + 63) / 64;   // KW = 32 / 48 / 96: only the first units of the last chunk
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const uint4* row = reinterpret_cast<const uint4*>(W + ((size_t)(jb * nchunks + c) * 128 + r) * 64);
 #pragma unroll
-      for (int u = 0; u < UPC; ++u) {
+      for (int u = 0; u < 8; ++u) {
+        if (c * 64 + u * 8 >= KW) continue;
         const uint4 v = row[u ^ (r & 7)];   // logical unit u sits in slot u ^ (r & 7)
         float f[8];
         tc::unpack8(v, f);
@@ -591,9 +592,15 @@ int launch_expand_stats_finalize(void* scratch, const void* W, double* stats, in
   const double* gram = reinterpret_cast<const double*>(scratch);
   const double* colsum = gram + (size_t)images * kGramLd * kGramLd;
   const dim3 sg(images, Nc / 32);
-  if (nchunks == 1 && Ktot > 0 && Ktot <= 32)   // (the level-0 blocks: a quarter of the 64-wide instantiation's products)
+  // instantiations at the actual width (the 64- / 128-wide ones multiply the zero padding too: 4x the products at K = 32)
+  if (nchunks == 1 && Ktot > 0 && Ktot <= 32)
     launch_pdl(expand_stats_kernel<32>, sg, dim3(128), (size_t)(32 * 32 + 32 + 32 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
-  else if (nchunks == 1)
+  else if (nchunks == 1 && Ktot > 0 && Ktot <= 48)
+    launch_pdl(expand_stats_kernel<48>, sg, dim3(128), (size_t)(48 * 48 + 48 + 48 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
+  else if (nchunks == 2 && Ktot > 0 && Ktot <= 96) {
+    if (ensure_dyn_smem_fn(expand_stats_kernel<96>, (96 * 96 + 96 + 96 * 32 + 512) * 4)) return -2;
+    launch_pdl(expand_stats_kernel<96>, sg, dim3(128), (size_t)(96 * 96 + 96 + 96 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
+  } else if (nchunks == 1)
     launch_pdl(expand_stats_kernel<64>, sg, dim3(128), (size_t)(64 * 64 + 64 + 64 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
   else
     launch_pdl(expand_stats_kernel<128>, sg, dim3(128), (size_t)(128 * 128 + 128 + 128 * 32 + 512) * 4, st, gram, colsum, reinterpret_cast<const bf16*>(W), stats, Nc, nchunks);
