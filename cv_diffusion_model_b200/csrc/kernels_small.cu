@@ -116,7 +116,7 @@ void launch_film(const float* silu_temb, const float* W, const float* b, float* 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm finalise (efficient_unet.py:170-171,207,212 ; F.group_norm semantics: biased variance,
 // eps = 1e-5 inside the sqrt).  One block per image.
-__global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const double* __restrict__ s1, int C1,
+__global__ void __launch_bounds__(1024) gn_coef_kernel(const double* __restrict__ s0, int C0, const double* __restrict__ s1, int C1,
                                int groups, double count, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                                float2* __restrict__ coef) {
@@ -179,7 +179,13 @@ __global__ void gn_coef_kernel(const double* __restrict__ s0, int C0, const doub
 void launch_gn_coef(const double* stats0, int C0, const double* stats1, int C1, int groups, double count,
                     const float* gamma, const float* beta, const float* film, int film_ld, float2* coef, int N,
                     cudaStream_t st) {
-  launch_pdl(gn_coef_kernel, dim3(N), dim3(256), 0, st, stats0, C0, stats1, C1, groups, count, gamma, beta, film, film_ld, coef);
+  // one warp per group in a single pass (32 groups -> 1024 threads): the group loop is a chain of dependent L2 loads and
+  // fp64 shuffles, and this kernel sits on the critical path 47 times per forward
+  static int thr = -1;
+  if (thr < 0) { const char* e = getenv("LCM_GN_THREADS"); thr = e ? atoi(e) : 1024; if (thr < 32 || thr > 1024 || thr % 32) thr = 256; }
+  int block = groups * 32 < thr ? groups * 32 : thr;
+  if (block < 64) block = 64;
+  launch_pdl(gn_coef_kernel, dim3(N), dim3(block), 0, st, stats0, C0, stats1, C1, groups, count, gamma, beta, film, film_ld, coef);
 }
 
 // ------------------------------------------------------------------------------------------------
